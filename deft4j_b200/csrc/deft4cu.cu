@@ -1,0 +1,826 @@
+// deft4cu.cu — host side of libdeft4cu.so: the C ABI of include/deft4cu.h on top of the kernels in
+// parse.cuh / engine.cuh / optimise.cuh / write.cuh.  Host code only moves bytes and sizes buffers; all
+// deflate work (decode, LZ77, cost model, enumeration, bit writing) is in the kernels.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/deft4cu.h"
+
+namespace d4 {
+static thread_local std::string g_err;
+static void set_error(const std::string& s) { g_err = s; }
+}  // namespace d4
+
+#include "write.cuh"
+
+namespace d4 {
+
+static int g_device = -1;
+static int g_sms = 148;
+static std::mutex g_mu;
+
+static int ensure_init() {
+    if (g_device >= 0) return DEFT4CU_OK;
+    return deft4cu_init(0);
+}
+
+#define LAUNCH(kern, grid, block, stream, ...)                                   \
+    do {                                                                         \
+        kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                     \
+        launches++;                                                              \
+        D4_CUDA_CHECK(cudaGetLastError());                                       \
+    } while (0)
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n, cudaStream_t s) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    return cudaMallocAsync((void**)p, n * sizeof(T), s);
+}
+template <typename T>
+static void dfree(T*& p, cudaStream_t s) {
+    if (p) cudaFreeAsync((void*)p, s);
+    p = nullptr;
+}
+
+struct BlkSummary { uint32_t type, n_sym; uint64_t out_len; };
+
+__global__ void k_blk_summary(const BlockRec* __restrict__ recs, BlkSummary* __restrict__ out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i].type = recs[i].type;
+    out[i].n_sym = recs[i].n_sym;
+    out[i].out_len = recs[i].out_len;
+}
+
+// CRC-32 / Adler-32 of the decoded bytes on the device (GZFile.java:130-145,
+// ZLibFile.java:42-51).  One CTA per stream; each thread folds a contiguous slice, slices are combined
+// with the standard length-aware combination (crc: multiply by x^(8*len) mod P; adler: closed form).
+__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b) {  // GF(2) polynomial product mod P (reflected)
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++) {
+        if (a & 0x80000000u) r ^= b;
+        a <<= 1;
+        b = (b >> 1) ^ ((b & 1) ? 0xEDB88320u : 0);
+    }
+    return r;
+}
+__device__ inline uint32_t crc_xpow8n(uint64_t n) {  // x^(8n) mod P
+    uint32_t r = 0x80000000u;  // x^0
+    uint32_t p = 0x00800000u;  // x^8
+    while (n) {
+        if (n & 1) r = crc_mulmod(r, p);
+        p = crc_mulmod(p, p);
+        n >>= 1;
+    }
+    return r;
+}
+struct Sums { uint32_t crc; uint32_t a, b; uint64_t len; };
+
+__global__ void __launch_bounds__(256)
+k_checksums(const uint8_t* __restrict__ out, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
+            uint32_t* __restrict__ crc_out, uint32_t* __restrict__ adler_out) {
+    __shared__ uint32_t tab[256];
+    __shared__ Sums part[256];
+    const int tid = threadIdx.x;
+    {
+        uint32_t c = (uint32_t)tid;
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1) ? 0xEDB88320u : 0);
+        tab[tid] = c;
+    }
+    __syncthreads();
+    const uint8_t* p = out + off[blockIdx.x];
+    const uint64_t n = len[blockIdx.x];
+    const uint64_t per = (n + 255) / 256;
+    uint64_t lo = per * tid, hi = lo + per;
+    if (lo > n) lo = n;
+    if (hi > n) hi = n;
+    uint32_t crc = 0;  // raw register (no pre/post inversion) of this slice
+    uint32_t a = 0, b = 0;
+    uint64_t k = lo;
+    while (k < hi) {
+        uint64_t stop = k + 5552 < hi ? k + 5552 : hi;
+        for (; k < stop; k++) {
+            uint8_t v = p[k];
+            crc = tab[(crc ^ v) & 0xff] ^ (crc >> 8);
+            a += v; b += a;
+        }
+        a %= 65521u; b %= 65521u;
+    }
+    part[tid].crc = crc; part[tid].a = a; part[tid].b = b; part[tid].len = hi - lo;
+    __syncthreads();
+    if (tid == 0) {
+        // crc of concatenation: raw(A|B) = raw(A) * x^(8|B|) + raw(B), with the initial 0xFFFFFFFF folded in
+        uint32_t c = 0xFFFFFFFFu;
+        uint32_t A = 1, Bs = 0;
+        for (int t = 0; t < 256; t++) {
+            uint64_t l = part[t].len;
+            if (!l) continue;
+            c = crc_mulmod(c, crc_xpow8n(l)) ^ part[t].crc;
+            uint32_t lm = (uint32_t)(l % 65521u);
+            Bs = (uint32_t)((Bs + (uint64_t)lm * A + part[t].b) % 65521u);
+            A = (A + part[t].a) % 65521u;
+        }
+        crc_out[blockIdx.x] = ~c;
+        adler_out[blockIdx.x] = (Bs << 16) | A;
+    }
+}
+
+class Batch {
+   public:
+    uint32_t n = 0;
+    cudaStream_t cs = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    float ms[8] = {0};
+
+    std::vector<uint64_t> in_len, in_off;
+    uint64_t total_in = 0;
+    uint8_t* d_in = nullptr;
+
+    std::vector<StreamDesc> descs;
+    std::vector<StreamInfo> infos;
+    StreamDesc* d_descs = nullptr;
+    StreamInfo* d_infos = nullptr;
+    BlockRec* d_blocks = nullptr;
+    ChunkRec* d_chunks = nullptr;
+    uint64_t nblk_total = 0, nsym_total = 0, nout_total = 0;
+    uint32_t* d_sym = nullptr;
+    uint32_t* d_symout = nullptr;
+    uint8_t* d_out = nullptr;
+
+    std::vector<BlkSummary> summ;
+    std::vector<uint32_t> blk_stream;
+    std::vector<uint64_t> mask_offs;
+    uint64_t maskwords_total = 0;
+    uint32_t* d_blk_stream = nullptr;
+    BlkState* d_bs = nullptr;
+    RoundLog* d_logs = nullptr;
+    uint32_t* d_maskpool = nullptr;
+    std::vector<StreamState> sstate;
+    StreamState* d_sstate = nullptr;
+    int* d_gerr = nullptr;
+    std::vector<int64_t> size_bits_in;
+
+    uint8_t* d_dst = nullptr;
+    std::vector<uint64_t> dst_off, dst_len;
+    uint64_t dst_total = 0;
+    uint64_t* d_dst_off = nullptr;
+    std::vector<uint32_t> crc, adler;
+    bool have_sums = false;
+    bool parsed = false;
+
+    ~Batch() { release_all(); if (own_stream && cs) cudaStreamDestroy(cs); }
+
+    void release_model() {
+        dfree(d_descs, cs); dfree(d_infos, cs); dfree(d_blocks, cs); dfree(d_chunks, cs);
+        dfree(d_sym, cs); dfree(d_symout, cs); dfree(d_out, cs);
+        dfree(d_blk_stream, cs); dfree(d_bs, cs); dfree(d_logs, cs); dfree(d_maskpool, cs);
+        dfree(d_sstate, cs); dfree(d_gerr, cs); dfree(d_dst, cs); dfree(d_dst_off, cs);
+        parsed = false; have_sums = false;
+    }
+    void release_all() {
+        release_model();
+        dfree(d_in, cs);
+        if (cs) cudaStreamSynchronize(cs);
+    }
+
+    int upload(const uint8_t* const* in, const uint64_t* len, uint32_t count) {
+        n = count;
+        if (!cs) { D4_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking)); own_stream = true; }
+        in_len.assign(len, len + n);
+        in_off.resize(n);
+        uint64_t off = 0;
+        for (uint32_t i = 0; i < n; i++) { in_off[i] = off; off += (in_len[i] + 32 + 15) & ~15ull; }
+        total_in = off + 64;
+        D4_CUDA_CHECK(dalloc(&d_in, total_in, cs));
+        D4_CUDA_CHECK(cudaMemsetAsync(d_in, 0, total_in, cs));
+        for (uint32_t i = 0; i < n; i++)
+            if (in_len[i]) D4_CUDA_CHECK(cudaMemcpyAsync(d_in + in_off[i], in[i], in_len[i], cudaMemcpyHostToDevice, cs));
+        return DEFT4CU_OK;
+    }
+
+    // ---- parse: count, emit, LZ77 resolve, model init ------------------------------------------------
+    int parse() {
+        release_model();
+        cudaEvent_t ev[4];
+        for (auto& e : ev) cudaEventCreate(&e);
+        descs.assign(n + 1, StreamDesc{});
+        infos.assign(n, StreamInfo{});
+        D4_CUDA_CHECK(dalloc(&d_descs, (size_t)n + 1, cs));
+        D4_CUDA_CHECK(dalloc(&d_infos, n, cs));
+        D4_CUDA_CHECK(dalloc(&d_gerr, 1, cs));
+        D4_CUDA_CHECK(cudaMemsetAsync(d_gerr, 0, sizeof(int), cs));
+        std::vector<uint64_t> bcap(n), ccap(n);
+        for (uint32_t i = 0; i < n; i++) {
+            bcap[i] = in_len[i] / 4096 + 8;
+            ccap[i] = in_len[i] * 8 / CHUNK_BITS + bcap[i] + 8;
+        }
+        cudaEventRecord(ev[0], cs);
+        for (int attempt = 0; attempt < 2; attempt++) {
+            uint64_t bt = 0, ct = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                descs[i].in_off = in_off[i]; descs[i].in_len = in_len[i];
+                descs[i].blk_base = bt; descs[i].blk_cap = bcap[i]; bt += bcap[i];
+                descs[i].chunk_base = ct; descs[i].chunk_cap = ccap[i]; ct += ccap[i];
+            }
+            dfree(d_blocks, cs); dfree(d_chunks, cs);
+            D4_CUDA_CHECK(dalloc(&d_blocks, bt, cs));
+            D4_CUDA_CHECK(dalloc(&d_chunks, ct, cs));
+            D4_CUDA_CHECK(cudaMemcpyAsync(d_descs, descs.data(), sizeof(StreamDesc) * (n + 1), cudaMemcpyHostToDevice, cs));
+            if (n) LAUNCH(k_count, n, PARSE_NT, cs, d_in, d_descs, d_infos, d_blocks, d_chunks);
+            D4_CUDA_CHECK(cudaMemcpyAsync(infos.data(), d_infos, sizeof(StreamInfo) * n, cudaMemcpyDeviceToHost, cs));
+            D4_CUDA_CHECK(cudaStreamSynchronize(cs));
+            bool again = false;
+            for (uint32_t i = 0; i < n; i++) {
+                if (infos[i].status != ST_OK) continue;
+                if (infos[i].n_blocks > bcap[i] || infos[i].n_chunks > ccap[i]) {
+                    again = true;
+                    bcap[i] = infos[i].n_blocks; ccap[i] = infos[i].n_chunks;
+                }
+            }
+            if (!again) break;
+            if (attempt == 1) { set_error("block/chunk capacity retry failed"); return DEFT4CU_ERR_CUDA; }
+        }
+        cudaEventRecord(ev[1], cs);
+        // pool bases
+        uint64_t sb = 0, ob = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            descs[i].sym_base = sb; descs[i].out_base = ob;
+            if (infos[i].status == ST_OK) { sb += infos[i].n_syms; ob += infos[i].out_len; }
+        }
+        descs[n].sym_base = sb; descs[n].out_base = ob;
+        nsym_total = sb; nout_total = ob;
+        if (ob >= 0xF8000000ull) {
+            for (uint32_t i = 0; i < n; i++) if (infos[i].status == ST_OK) infos[i].status = ST_UNSUPPORTED;
+            set_error("decoded size of the batch exceeds 4 GiB; split the batch");
+            return DEFT4CU_ERR_UNSUPPORTED;
+        }
+        D4_CUDA_CHECK(cudaMemcpyAsync(d_descs, descs.data(), sizeof(StreamDesc) * (n + 1), cudaMemcpyHostToDevice, cs));
+        D4_CUDA_CHECK(dalloc(&d_sym, sb, cs));
+        D4_CUDA_CHECK(dalloc(&d_symout, sb, cs));
+        D4_CUDA_CHECK(dalloc(&d_out, ob + 16, cs));
+        // block list (compact, in stream order)
+        std::vector<EmitJob> jobs;
+        blk_stream.clear();
+        std::vector<uint64_t> sblk_base(n);
+        for (uint32_t i = 0; i < n; i++) {
+            sblk_base[i] = blk_stream.size();
+            if (infos[i].status != ST_OK) continue;
+            for (uint32_t k = 0; k < infos[i].n_blocks; k++) { jobs.push_back(EmitJob{i, k}); blk_stream.push_back(i); }
+        }
+        nblk_total = jobs.size();
+        EmitJob* d_jobs = nullptr;
+        D4_CUDA_CHECK(dalloc(&d_jobs, jobs.size(), cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(EmitJob) * jobs.size(), cudaMemcpyHostToDevice, cs));
+        if (!jobs.empty())
+            LAUNCH(k_emit, (unsigned)jobs.size(), 256, cs, d_in, d_descs, d_blocks, d_chunks, d_jobs, d_infos, d_sym, d_symout, d_out);
+        cudaEventRecord(ev[2], cs);
+        // LZ77
+        if (ob) {
+            uint32_t* d_ptr = nullptr;
+            int* d_changed = nullptr;
+            D4_CUDA_CHECK(dalloc(&d_ptr, ob, cs));
+            D4_CUDA_CHECK(dalloc(&d_changed, 1, cs));
+            if (sb) LAUNCH(k_lz_fill, (unsigned)((sb + 255) / 256), 256, cs, d_sym, d_symout, sb, d_out, d_ptr);
+            // stored bytes: roots
+            // (k_emit wrote them into d_out; their pointers are set here)
+            {
+                // ptr for stored block bytes = self: a tiny kernel over blocks would do; reuse k_lz_root
+            }
+            LAUNCH(k_lz_root_stored, (unsigned)std::max<uint64_t>(1, nblk_total), 256, cs, d_descs, d_blocks, d_jobs, (uint32_t)nblk_total, d_ptr);
+            for (int it = 0; it < 64; it++) {
+                int changed = 0;
+                D4_CUDA_CHECK(cudaMemsetAsync(d_changed, 0, sizeof(int), cs));
+                for (int rep = 0; rep < 3; rep++) LAUNCH(k_lz_jump, (unsigned)((ob + 255) / 256), 256, cs, d_ptr, ob, d_changed);
+                D4_CUDA_CHECK(cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, cs));
+                D4_CUDA_CHECK(cudaStreamSynchronize(cs));
+                if (!changed) break;
+            }
+            LAUNCH(k_lz_gather, (unsigned)((ob + 255) / 256), 256, cs, d_out, d_ptr, ob);
+            dfree(d_ptr, cs); dfree(d_changed, cs);
+        }
+        cudaEventRecord(ev[3], cs);
+        // compact the BlockRec array to stream order without gaps: rebase through a gather of summaries
+        // (BlockRecs stay where they are; blk index -> record via descs[stream].blk_base + k)
+        BlkSummary* d_summ = nullptr;
+        BlockRec* d_compact = nullptr;
+        D4_CUDA_CHECK(dalloc(&d_compact, nblk_total, cs));
+        if (nblk_total) LAUNCH(k_compact_blocks, (unsigned)((nblk_total * 32 + 255) / 256), 256, cs, d_descs, d_blocks, d_jobs, nblk_total, d_compact);
+        dfree(d_blocks, cs);
+        d_blocks = d_compact;
+        D4_CUDA_CHECK(dalloc(&d_summ, nblk_total, cs));
+        summ.resize(nblk_total);
+        if (nblk_total) LAUNCH(k_blk_summary, (unsigned)((nblk_total + 255) / 256), 256, cs, d_blocks, d_summ, nblk_total);
+        D4_CUDA_CHECK(cudaMemcpyAsync(summ.data(), d_summ, sizeof(BlkSummary) * nblk_total, cudaMemcpyDeviceToHost, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(infos.data(), d_infos, sizeof(StreamInfo) * n, cudaMemcpyDeviceToHost, cs));
+        D4_CUDA_CHECK(cudaStreamSynchronize(cs));
+        dfree(d_summ, cs); dfree(d_jobs, cs); dfree(d_chunks, cs);
+        // model
+        mask_offs.resize(nblk_total);
+        uint64_t mo = 0;
+        for (uint64_t b = 0; b < nblk_total; b++) { mask_offs[b] = mo; mo += (summ[b].n_sym + 31) / 32; }
+        maskwords_total = mo;
+        sstate.assign(n, StreamState{});
+        size_bits_in.assign(n, 0);
+        for (uint32_t i = 0; i < n; i++) {
+            StreamState& s = sstate[i];
+            s.blk_base = sblk_base[i];
+            s.status = infos[i].status;
+            s.n_blocks = infos[i].status == ST_OK ? infos[i].n_blocks : 0;
+            s.cut = s.n_blocks;
+            for (uint32_t k = 0; k < s.n_blocks; k++) {
+                const BlkSummary& bsu = summ[s.blk_base + k];
+                if (bsu.out_len == 0 && !(k == 0 && s.n_blocks == 1)) { s.cut = k; break; }
+            }
+            s.total_bits = infos[i].total_bits;
+            size_bits_in[i] = (int64_t)infos[i].total_bits;
+        }
+        uint64_t* d_moffs = nullptr;
+        D4_CUDA_CHECK(dalloc(&d_moffs, nblk_total, cs));
+        D4_CUDA_CHECK(dalloc(&d_blk_stream, nblk_total, cs));
+        D4_CUDA_CHECK(dalloc(&d_bs, nblk_total, cs));
+        D4_CUDA_CHECK(dalloc(&d_logs, nblk_total, cs));
+        D4_CUDA_CHECK(dalloc(&d_maskpool, mo + 2, cs));
+        D4_CUDA_CHECK(dalloc(&d_sstate, n, cs));
+        D4_CUDA_CHECK(cudaMemsetAsync(d_maskpool, 0, (mo + 2) * 4, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(d_moffs, mask_offs.data(), 8 * nblk_total, cudaMemcpyHostToDevice, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(d_blk_stream, blk_stream.data(), 4 * nblk_total, cudaMemcpyHostToDevice, cs));
+        if (nblk_total) LAUNCH(k_init_state, (unsigned)((nblk_total + 127) / 128), 128, cs, d_blocks, d_descs, d_blk_stream, d_moffs, d_bs, nblk_total);
+        D4_CUDA_CHECK(cudaStreamSynchronize(cs));
+        dfree(d_moffs, cs);
+        float t;
+        cudaEventElapsedTime(&t, ev[0], ev[1]); ms[0] = t;
+        cudaEventElapsedTime(&t, ev[1], ev[2]); ms[1] = t;
+        cudaEventElapsedTime(&t, ev[2], ev[3]); ms[2] = t;
+        for (auto& e : ev) cudaEventDestroy(e);
+        parsed = true;
+        return DEFT4CU_OK;
+    }
+
+    // ---- optimise: phase A over blocks, then per-stream replay/merge/layout ----------------------------
+    int optimise(uint32_t flags, const std::vector<uint8_t>& selected) {
+        cudaEvent_t ev[3];
+        for (auto& e : ev) cudaEventCreate(&e);
+        const int merge = (flags & DEFT4CU_MERGE_BLOCKS) ? 1 : 0;
+        std::vector<uint32_t> jobs;
+        uint32_t maxsym = 1, maxstream = 1;
+        for (uint32_t i = 0; i < n; i++) {
+            StreamState& s = sstate[i];
+            s.selected = selected[i] && s.status == ST_OK;
+            s.saved_bits = 0;
+            if (!s.selected) continue;
+            uint64_t ssum = 0;
+            for (uint32_t k = 0; k < s.n_blocks; k++) {
+                const BlkSummary& b = summ[s.blk_base + k];
+                ssum += b.n_sym;
+                if (k < s.cut && b.type != 0) { jobs.push_back((uint32_t)(s.blk_base + k)); maxsym = std::max(maxsym, b.n_sym); }
+            }
+            maxstream = (uint32_t)std::max<uint64_t>(maxstream, ssum);
+        }
+        std::stable_sort(jobs.begin(), jobs.end(), [&](uint32_t a, uint32_t b) { return summ[a].n_sym > summ[b].n_sym; });
+        D4_CUDA_CHECK(cudaMemcpyAsync(d_sstate, sstate.data(), sizeof(StreamState) * n, cudaMemcpyHostToDevice, cs));
+        cudaEventRecord(ev[0], cs);
+        if (!jobs.empty()) {
+            uint32_t* d_jobs = nullptr;
+            unsigned* d_counter = nullptr;
+            D4_CUDA_CHECK(dalloc(&d_jobs, jobs.size(), cs));
+            D4_CUDA_CHECK(dalloc(&d_counter, 1, cs));
+            D4_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, 4, cs));
+            D4_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), 4 * jobs.size(), cudaMemcpyHostToDevice, cs));
+            int perSM = 0;
+            D4_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_opt_blocks, ENG_NT, 0));
+            if (perSM < 1) perSM = 1;
+            unsigned grid = (unsigned)std::min<uint64_t>(jobs.size(), (uint64_t)g_sms * perSM);
+            EngScratch sc;
+            sc.maxwords = (maxsym + 31) / 32 + 1;
+            D4_CUDA_CHECK(dalloc(&sc.masks, (size_t)grid * NCAND * sc.maxwords, cs));
+            D4_CUDA_CHECK(dalloc(&sc.memoH, (size_t)grid * MEMO_H, cs));
+            D4_CUDA_CHECK(dalloc(&sc.memoT, (size_t)grid * MEMO_T, cs));
+            LAUNCH(k_opt_blocks, grid, ENG_NT, cs, d_jobs, (uint32_t)jobs.size(), d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, d_counter, d_gerr);
+            dfree(sc.masks, cs); dfree(sc.memoH, cs); dfree(sc.memoT, cs);
+            dfree(d_jobs, cs); dfree(d_counter, cs);
+        }
+        cudaEventRecord(ev[1], cs);
+        {
+            EngScratch sc{};
+            sc.maxwords = (maxstream + 31) / 32 + 2;
+            if (merge) {
+                D4_CUDA_CHECK(dalloc(&sc.masks, (size_t)n * NCAND * sc.maxwords, cs));
+                D4_CUDA_CHECK(dalloc(&sc.memoH, (size_t)n * MEMO_H, cs));
+                D4_CUDA_CHECK(dalloc(&sc.memoT, (size_t)n * MEMO_T, cs));
+            }
+            if (n) LAUNCH(k_finish, n, ENG_NT, cs, d_sstate, d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, merge, d_gerr);
+            if (merge) { dfree(sc.masks, cs); dfree(sc.memoH, cs); dfree(sc.memoT, cs); }
+        }
+        cudaEventRecord(ev[2], cs);
+        int gerr = 0;
+        D4_CUDA_CHECK(cudaMemcpyAsync(sstate.data(), d_sstate, sizeof(StreamState) * n, cudaMemcpyDeviceToHost, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(&gerr, d_gerr, sizeof(int), cudaMemcpyDeviceToHost, cs));
+        D4_CUDA_CHECK(cudaStreamSynchronize(cs));
+        float t;
+        cudaEventElapsedTime(&t, ev[0], ev[1]); ms[3] = t;
+        cudaEventElapsedTime(&t, ev[1], ev[2]); ms[4] = t;
+        for (auto& e : ev) cudaEventDestroy(e);
+        if (gerr) {
+            set_error("optimiser hit an internal limit (tree node pool / round cap)");
+            for (uint32_t i = 0; i < n; i++) if (sstate[i].selected) sstate[i].status = ST_UNSUPPORTED;
+            return DEFT4CU_ERR_UNSUPPORTED;
+        }
+        dfree(d_dst, cs);  // stale output
+        return DEFT4CU_OK;
+    }
+
+    // ---- write ---------------------------------------------------------------------------------------
+    int write() {
+        cudaEvent_t ev[2];
+        for (auto& e : ev) cudaEventCreate(&e);
+        dst_off.assign(n, 0); dst_len.assign(n, 0);
+        uint64_t off = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            dst_off[i] = off;
+            if (sstate[i].status != ST_OK) continue;
+            dst_len[i] = (sstate[i].total_bits + 7) / 8;
+            off += (dst_len[i] + 16 + 7) & ~7ull;
+        }
+        dst_total = off + 8;
+        dfree(d_dst, cs); dfree(d_dst_off, cs);
+        D4_CUDA_CHECK(dalloc(&d_dst, dst_total, cs));
+        D4_CUDA_CHECK(dalloc(&d_dst_off, n, cs));
+        D4_CUDA_CHECK(cudaMemsetAsync(d_dst, 0, dst_total, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(d_dst_off, dst_off.data(), 8 * n, cudaMemcpyHostToDevice, cs));
+        cudaEventRecord(ev[0], cs);
+        if (nblk_total)
+            LAUNCH(k_write, (unsigned)nblk_total, WR_NT, cs, d_sstate, d_blk_stream, d_bs, d_sym, d_symout, d_out, d_maskpool, d_dst_off,
+                   (unsigned long long*)d_dst, d_gerr);
+        cudaEventRecord(ev[1], cs);
+        int gerr = 0;
+        D4_CUDA_CHECK(cudaMemcpyAsync(&gerr, d_gerr, sizeof(int), cudaMemcpyDeviceToHost, cs));
+        D4_CUDA_CHECK(cudaStreamSynchronize(cs));
+        float t;
+        cudaEventElapsedTime(&t, ev[0], ev[1]); ms[5] = t;
+        for (auto& e : ev) cudaEventDestroy(e);
+        if (gerr) { set_error("writer and cost model disagree on a block size"); return DEFT4CU_ERR_WRITE; }
+        return DEFT4CU_OK;
+    }
+
+    int checksums() {
+        if (have_sums) return DEFT4CU_OK;
+        cudaEvent_t ev[2];
+        for (auto& e : ev) cudaEventCreate(&e);
+        std::vector<uint64_t> off(n), len(n);
+        for (uint32_t i = 0; i < n; i++) { off[i] = descs[i].out_base; len[i] = infos[i].status == ST_OK ? infos[i].out_len : 0; }
+        uint64_t *d_off = nullptr, *d_len = nullptr;
+        uint32_t *d_crc = nullptr, *d_ad = nullptr;
+        D4_CUDA_CHECK(dalloc(&d_off, n, cs)); D4_CUDA_CHECK(dalloc(&d_len, n, cs));
+        D4_CUDA_CHECK(dalloc(&d_crc, n, cs)); D4_CUDA_CHECK(dalloc(&d_ad, n, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), 8 * n, cudaMemcpyHostToDevice, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(d_len, len.data(), 8 * n, cudaMemcpyHostToDevice, cs));
+        cudaEventRecord(ev[0], cs);
+        if (n) LAUNCH(k_checksums, n, 256, cs, d_out, d_off, d_len, d_crc, d_ad);
+        cudaEventRecord(ev[1], cs);
+        crc.resize(n); adler.resize(n);
+        D4_CUDA_CHECK(cudaMemcpyAsync(crc.data(), d_crc, 4 * n, cudaMemcpyDeviceToHost, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(adler.data(), d_ad, 4 * n, cudaMemcpyDeviceToHost, cs));
+        D4_CUDA_CHECK(cudaStreamSynchronize(cs));
+        float t;
+        cudaEventElapsedTime(&t, ev[0], ev[1]); ms[6] = t;
+        for (auto& e : ev) cudaEventDestroy(e);
+        dfree(d_off, cs); dfree(d_len, cs); dfree(d_crc, cs); dfree(d_ad, cs);
+        have_sums = true;
+        return DEFT4CU_OK;
+    }
+};
+
+}  // namespace d4
+
+using namespace d4;
+
+struct deft4cu_stream {
+    std::shared_ptr<Batch> batch;
+    uint32_t idx;
+    bool written = false;
+};
+struct deft4cu_device_batch {
+    std::shared_ptr<Batch> batch;
+};
+
+static int status_of(const Batch& b, uint32_t i) { return b.sstate.size() > i ? b.sstate[i].status : b.infos[i].status; }
+
+extern "C" {
+
+int deft4cu_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(std::string("no CUDA device: ") + cudaGetErrorString(e));
+        return DEFT4CU_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { set_error("bad device index"); return DEFT4CU_ERR_ARG; }
+    D4_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp p;
+    D4_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    g_sms = p.multiProcessorCount;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    g_device = device;
+    return DEFT4CU_OK;
+}
+const char* deft4cu_last_error(void) { return g_err.c_str(); }
+const char* deft4cu_version(void) { return "deft4cu 0.1 (sm_100a)"; }
+
+// ---- handle API ------------------------------------------------------------------------------------------
+int deft4cu_stream_parse_batch(const uint8_t* const* data, const uint64_t* len, uint32_t n, deft4cu_stream** handles,
+                               int32_t* status, uint64_t* consumed) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    auto b = std::make_shared<Batch>();
+    rc = b->upload(data, len, n);
+    if (rc) return rc;
+    rc = b->parse();
+    if (rc && rc != DEFT4CU_ERR_UNSUPPORTED) return rc;
+    for (uint32_t i = 0; i < n; i++) {
+        int st = b->infos[i].status;
+        if (status) status[i] = st;
+        if (consumed) consumed[i] = b->infos[i].consumed;
+        handles[i] = nullptr;
+        if (st == ST_OK) handles[i] = new deft4cu_stream{b, i};
+    }
+    return DEFT4CU_OK;
+}
+int deft4cu_stream_parse(const uint8_t* data, uint64_t len, deft4cu_stream** out, uint64_t* consumed) {
+    int32_t st = 0;
+    uint64_t c = 0;
+    *out = nullptr;
+    int rc = deft4cu_stream_parse_batch(&data, &len, 1, out, &st, &c);
+    if (consumed) *consumed = c;
+    if (rc) return rc;
+    return st;
+}
+void deft4cu_stream_free(deft4cu_stream* s) { delete s; }
+
+int deft4cu_stream_optimise_batch(deft4cu_stream* const* s, uint32_t n, uint32_t flags, int64_t* saved_bits) {
+    // group by batch
+    std::vector<Batch*> batches;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!s[i]) return DEFT4CU_ERR_ARG;
+        if (std::find(batches.begin(), batches.end(), s[i]->batch.get()) == batches.end()) batches.push_back(s[i]->batch.get());
+    }
+    int worst = DEFT4CU_OK;
+    for (Batch* b : batches) {
+        std::vector<uint8_t> sel(b->n, 0);
+        for (uint32_t i = 0; i < n; i++) if (s[i]->batch.get() == b) sel[s[i]->idx] = 1;
+        int rc = b->optimise(flags, sel);
+        if (rc) worst = rc;
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        s[i]->written = false;
+        if (saved_bits) saved_bits[i] = s[i]->batch->sstate[s[i]->idx].saved_bits;
+    }
+    return worst;
+}
+int deft4cu_stream_optimise(deft4cu_stream* s, uint32_t flags, int64_t* saved_bits) {
+    return deft4cu_stream_optimise_batch(&s, 1, flags, saved_bits);
+}
+int64_t deft4cu_stream_size_bits(const deft4cu_stream* s) { return (int64_t)s->batch->sstate[s->idx].total_bits; }
+uint64_t deft4cu_stream_uncompressed_len(const deft4cu_stream* s) { return s->batch->infos[s->idx].out_len; }
+int deft4cu_stream_uncompressed(const deft4cu_stream* s, uint8_t* dst, uint64_t cap) {
+    Batch& b = *s->batch;
+    uint64_t len = b.infos[s->idx].out_len;
+    if (cap < len) return DEFT4CU_ERR_ARG;
+    if (len) D4_CUDA_CHECK(cudaMemcpyAsync(dst, b.d_out + b.descs[s->idx].out_base, len, cudaMemcpyDeviceToHost, b.cs));
+    D4_CUDA_CHECK(cudaStreamSynchronize(b.cs));
+    return DEFT4CU_OK;
+}
+int deft4cu_stream_checksums(const deft4cu_stream* s, uint32_t* crc32, uint32_t* adler32) {
+    Batch& b = *s->batch;
+    int rc = b.checksums();
+    if (rc) return rc;
+    if (crc32) *crc32 = b.crc[s->idx];
+    if (adler32) *adler32 = b.adler[s->idx];
+    return DEFT4CU_OK;
+}
+int deft4cu_stream_write(const deft4cu_stream* s, uint8_t* dst, uint64_t cap, uint64_t* len) {
+    Batch& b = *s->batch;
+    if (b.sstate[s->idx].status != ST_OK) return DEFT4CU_ERR_WRITE;
+    if (!b.d_dst) {
+        int rc = b.write();
+        if (rc) return rc;
+    }
+    uint64_t l = b.dst_len[s->idx];
+    if (len) *len = l;
+    if (dst && cap >= l) {
+        if (l) D4_CUDA_CHECK(cudaMemcpyAsync(dst, b.d_dst + b.dst_off[s->idx], l, cudaMemcpyDeviceToHost, b.cs));
+        D4_CUDA_CHECK(cudaStreamSynchronize(b.cs));
+    }
+    return DEFT4CU_OK;
+}
+
+uint32_t deft4cu_stream_block_count(const deft4cu_stream* s) {
+    Batch& b = *s->batch;
+    const StreamState& st = b.sstate[s->idx];
+    std::vector<BlkState> bs(st.n_blocks);
+    if (st.n_blocks) cudaMemcpy(bs.data(), b.d_bs + st.blk_base, sizeof(BlkState) * st.n_blocks, cudaMemcpyDeviceToHost);
+    uint32_t c = 0;
+    for (auto& x : bs) c += x.alive ? 1 : 0;
+    return c;
+}
+static int fetch_block(const deft4cu_stream* s, uint32_t block, BlkState* out) {
+    Batch& b = *s->batch;
+    const StreamState& st = b.sstate[s->idx];
+    std::vector<BlkState> bs(st.n_blocks);
+    if (st.n_blocks) cudaMemcpy(bs.data(), b.d_bs + st.blk_base, sizeof(BlkState) * st.n_blocks, cudaMemcpyDeviceToHost);
+    uint32_t c = 0;
+    for (auto& x : bs) {
+        if (!x.alive) continue;
+        if (c == block) { *out = x; return 0; }
+        c++;
+    }
+    return 1;
+}
+// final symbol list of a block on the host (inspection only): expands replaced matches into literals
+static int fetch_symbols(const deft4cu_stream* s, const BlkState& x, std::vector<int32_t>& triples) {
+    Batch& b = *s->batch;
+    std::vector<uint32_t> sym(x.n_sym), so(x.n_sym), mask((x.n_sym + 31) / 32 + 1);
+    std::vector<uint8_t> out(x.out_len + 1);
+    if (x.n_sym) {
+        cudaMemcpy(sym.data(), b.d_sym + x.sym_off, 4ull * x.n_sym, cudaMemcpyDeviceToHost);
+        cudaMemcpy(so.data(), b.d_symout + x.sym_off, 4ull * x.n_sym, cudaMemcpyDeviceToHost);
+        cudaMemcpy(mask.data(), b.d_maskpool + x.mask_off, 4ull * ((x.n_sym + 31) / 32), cudaMemcpyDeviceToHost);
+    }
+    if (x.out_len) cudaMemcpy(out.data(), b.d_out + x.out_off, x.out_len, cudaMemcpyDeviceToHost);
+    for (uint32_t i = 0; i < x.n_sym; i++) {
+        uint32_t v = sym[i];
+        if (!sym_is_match(v)) {
+            if (v <= 256) { triples.push_back(0); triples.push_back((int32_t)v); triples.push_back(0); }
+        } else if ((mask[i >> 5] >> (i & 31)) & 1) {
+            for (int k = 0; k < sym_len(v); k++) {
+                triples.push_back(0); triples.push_back(out[so[i] - x.out_off + k]); triples.push_back(0);
+            }
+        } else {
+            triples.push_back(sym_dist(v)); triples.push_back(sym_len(v)); triples.push_back(sym_edge(v));
+        }
+    }
+    return 0;
+}
+int deft4cu_stream_block_info(const deft4cu_stream* s, uint32_t block, deft4cu_block_info* o) {
+    BlkState x;
+    if (fetch_block(s, block, &x)) return DEFT4CU_ERR_ARG;
+    memset(o, 0, sizeof *o);
+    o->type = x.cand.tab.type;
+    o->size_bits = x.size_bits;
+    o->position = (int64_t)x.bit_pos;
+    o->uncompressed_len = x.out_len;
+    if (x.cand.tab.type != 0) {
+        std::vector<int32_t> t;
+        fetch_symbols(s, x, t);
+        o->n_symbols = (uint32_t)(t.size() / 3);
+        o->litlen_size_bits = x.cand.payload;
+        if (x.cand.tab.type == 2) {
+            o->n_rle_pairs = x.cand.hdr.np;
+            o->num_litlen_lens = x.cand.tab.nL; o->num_dist_lens = x.cand.tab.nD; o->num_codelen_lens = x.cand.hdr.ncl;
+            o->header_size_bits = x.cand.hdr.bits;
+        }
+    }
+    return DEFT4CU_OK;
+}
+uint32_t deft4cu_stream_block_symbols(const deft4cu_stream* s, uint32_t block, int32_t* dst, uint32_t cap) {
+    BlkState x;
+    if (fetch_block(s, block, &x) || x.cand.tab.type == 0) return 0;
+    std::vector<int32_t> t;
+    fetch_symbols(s, x, t);
+    uint32_t nsy = (uint32_t)(t.size() / 3);
+    for (uint32_t i = 0; i < nsy && i < cap; i++) { dst[3 * i] = t[3 * i]; dst[3 * i + 1] = t[3 * i + 1]; dst[3 * i + 2] = t[3 * i + 2]; }
+    return nsy;
+}
+uint32_t deft4cu_stream_block_rle_pairs(const deft4cu_stream* s, uint32_t block, int32_t* dst, uint32_t cap) {
+    BlkState x;
+    if (fetch_block(s, block, &x) || x.cand.tab.type != 2) return 0;
+    for (uint32_t i = 0; i < x.cand.hdr.np && i < cap; i++) { dst[2 * i] = pair_run(x.cand.hdr.pairs[i]); dst[2 * i + 1] = pair_sym(x.cand.hdr.pairs[i]); }
+    return x.cand.hdr.np;
+}
+uint32_t deft4cu_stream_block_codelens(const deft4cu_stream* s, uint32_t block, int which, int32_t* dst, uint32_t cap) {
+    BlkState x;
+    if (fetch_block(s, block, &x) || x.cand.tab.type == 0) return 0;
+    uint32_t nn = which == 0 ? x.cand.tab.nL : which == 1 ? x.cand.tab.nD : (x.cand.tab.type == 2 ? 19 : 0);
+    for (uint32_t i = 0; i < nn && i < cap; i++) dst[i] = which == 0 ? x.cand.tab.L[i] : which == 1 ? x.cand.tab.D[i] : x.cand.hdr.CL[i];
+    return nn;
+}
+
+// ---- batch entry -------------------------------------------------------------------------------------------
+static int fill_results(Batch& b, deft4cu_result* results, bool fetch_out) {
+    for (uint32_t i = 0; i < b.n; i++) {
+        deft4cu_result& r = results[i];
+        memset(&r, 0, sizeof r);
+        r.status = b.sstate[i].status;
+        r.consumed_bytes = b.infos[i].consumed;
+        if (r.status != ST_OK) continue;
+        r.saved_bits = b.sstate[i].saved_bits;
+        r.uncompressed_len = b.infos[i].out_len;
+        r.size_bits_in = b.size_bits_in[i];
+        r.size_bits_out = (int64_t)b.sstate[i].total_bits;
+        r.crc32 = b.crc.size() > i ? b.crc[i] : 0;
+        r.adler32 = b.adler.size() > i ? b.adler[i] : 0;
+        r.out_len = b.dst_len[i];
+        if (fetch_out) {
+            r.out = (uint8_t*)malloc(r.out_len ? r.out_len : 1);
+            if (r.out_len) D4_CUDA_CHECK(cudaMemcpyAsync(r.out, b.d_dst + b.dst_off[i], r.out_len, cudaMemcpyDeviceToHost, b.cs));
+        }
+    }
+    D4_CUDA_CHECK(cudaStreamSynchronize(b.cs));
+    return DEFT4CU_OK;
+}
+
+int deft4cu_optimise_batch(const uint8_t* const* in, const uint64_t* in_len, uint32_t n, uint32_t flags, deft4cu_result* results) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    Batch b;
+    rc = b.upload(in, in_len, n);
+    if (rc) return rc;
+    rc = b.parse();
+    if (rc) {
+        if (rc == DEFT4CU_ERR_UNSUPPORTED && b.infos.size() == n) {
+            for (uint32_t i = 0; i < n; i++) { memset(&results[i], 0, sizeof results[i]); results[i].status = b.infos[i].status; }
+        }
+        return rc;
+    }
+    std::vector<uint8_t> sel(n, 1);
+    rc = b.optimise(flags, sel);
+    if (rc && rc != DEFT4CU_ERR_UNSUPPORTED) return rc;
+    int rc2 = b.write();
+    if (rc2) return rc2;
+    rc2 = b.checksums();
+    if (rc2) return rc2;
+    rc2 = fill_results(b, results, true);
+    return rc2 ? rc2 : rc;
+}
+void deft4cu_free_results(deft4cu_result* results, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) { free(results[i].out); results[i].out = nullptr; }
+}
+
+// ---- facade -------------------------------------------------------------------------------------------------
+int deft4cu_optimise_deflate_stream(const uint8_t* in, uint64_t len, int merge_blocks, uint8_t** out, uint64_t* out_len) {
+    *out = nullptr;
+    *out_len = 0;
+    deft4cu_result r;
+    int rc = deft4cu_optimise_batch(&in, &len, 1, merge_blocks ? DEFT4CU_MERGE_BLOCKS : 0, &r);
+    if (rc == DEFT4CU_ERR_CUDA || rc == DEFT4CU_ERR_ARG) return rc;
+    if (r.status == ST_OK && r.saved_bits > 0) { *out = r.out; *out_len = r.out_len; }
+    else free(r.out);
+    return DEFT4CU_OK;
+}
+void deft4cu_free_buffer(uint8_t* p) { free(p); }
+int64_t deft4cu_size_bits_fallback(const uint8_t* in, uint64_t len) {
+    deft4cu_stream* s = nullptr;
+    uint64_t c;
+    if (deft4cu_stream_parse(in, len, &s, &c) != DEFT4CU_OK || !s) return (int64_t)len * 8;
+    int64_t v = deft4cu_stream_size_bits(s);
+    deft4cu_stream_free(s);
+    return v;
+}
+
+// ---- device-resident batch (bench) -----------------------------------------------------------------------
+int deft4cu_device_batch_create(const uint8_t* const* in, const uint64_t* in_len, uint32_t n, deft4cu_device_batch** out) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    auto b = std::make_shared<Batch>();
+    rc = b->upload(in, in_len, n);
+    if (rc) return rc;
+    D4_CUDA_CHECK(cudaStreamSynchronize(b->cs));
+    *out = new deft4cu_device_batch{b};
+    return DEFT4CU_OK;
+}
+int deft4cu_device_batch_run(deft4cu_device_batch* db, uint32_t flags, uint64_t* launches, void* cuda_stream) {
+    Batch& b = *db->batch;
+    (void)cuda_stream;
+    b.launches = 0;
+    int rc = b.parse();
+    if (rc) return rc;
+    std::vector<uint8_t> sel(b.n, 1);
+    rc = b.optimise(flags, sel);
+    if (rc && rc != DEFT4CU_ERR_UNSUPPORTED) return rc;
+    int rc2 = b.write();
+    if (rc2) return rc2;
+    rc2 = b.checksums();
+    if (rc2) return rc2;
+    if (launches) *launches = b.launches;
+    return rc;
+}
+int deft4cu_device_batch_fetch(deft4cu_device_batch* db, deft4cu_result* results) { return fill_results(*db->batch, results, true); }
+int deft4cu_device_batch_timings(const deft4cu_device_batch* db, float* ms, uint32_t n) {
+    for (uint32_t i = 0; i < n && i < 8; i++) ms[i] = db->batch->ms[i];
+    return DEFT4CU_OK;
+}
+void deft4cu_device_batch_free(deft4cu_device_batch* db) { delete db; }
+
+}  // extern "C"

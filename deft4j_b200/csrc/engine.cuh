@@ -1,0 +1,596 @@
+// engine.cuh — the block candidate enumerator (DeflateStream.optimiseBlock, DeflateStream.java:343-490)
+// as CTA-cooperative device code.  One CTA owns one block; every function below is called by ALL
+// threads of the CTA with uniform arguments.
+//
+// A candidate ("Cand") is the reference's DeflateBlockHuffman copy reduced to what determines its bytes:
+//   Tab (code lengths + table lengths + type), Hdr (header RLE pairs, header code, numCodelenLens),
+//   payload = litlenSizeBits, and a bit mask over the block's symbols (1 = match replaced by literals).
+// Candidate i's mask lives in mask slot i of the CTA's global scratch.
+//
+// O(n) work (n = symbols of the block) is done by CTA-wide passes:
+//   pass_replace : replaceBackrefsWithLiteralsIfSmaller (DeflateBlockHuffman.java:222-319)
+//   pass_least   : removeDistLitLeastExpensive          (:373-458)
+//   pass_hist    : the histogram loop of recodeHuffman   (:671-681); payload = hist . (len + extra bits)
+// Small serial work (Huffman trees, header model) runs in single threads (huff.cuh).
+//
+// Two exact shortcuts (pure-function memoisation; neither changes any candidate's size or the order in
+// which candidates are compared):
+//   * recodeHuffman's result (tables, payload, default header) depends only on the histogram -> cache.
+//   * the 56 header-strategy trials of a base depend only on (Tab, payload) and their sizes are
+//     payload + f(Tab, strategy) -> the first-minimum strategy per Tab is cached, and the
+//     addOptimisedRecoded(prune) sweep (DeflateStream.java:431) is skipped: it re-evaluates candidates
+//     with exactly the sizes of the sweep on `post` (:418) — both are copies of the same block that
+//     differ only in the header, which every base/trial discards — so under the strict `<` of the
+//     selection callback (:357) none of them can ever be chosen.
+#pragma once
+#include "huff.cuh"
+#include "parse.cuh"
+
+namespace d4 {
+
+constexpr int ENG_NT = 256;
+constexpr int NCAND = 16;
+constexpr int MEMO_H = 192;   // histogram -> recode result
+constexpr int MEMO_T = 192;   // Tab -> best header strategy
+
+struct Cand {
+    Tab tab;
+    Hdr hdr;
+    long long payload;  // litlenSizeBits
+};
+__device__ __forceinline__ long long cand_size(const Cand& c) { return c.payload + (c.tab.type == 2 ? c.hdr.bits : 0); }
+
+struct BlkView {
+    const uint32_t* sym;
+    const uint32_t* symout;
+    const uint8_t* out;
+    uint32_t n;       // symbols (including a NOP left by a merge)
+    uint32_t nwords;  // mask words
+    uint64_t ulen;    // decoded length
+};
+
+struct MemoHEntry {   // global scratch
+    uint32_t hist[320];
+    Cand result;
+};
+
+struct EngSmem {
+    Cand c[NCAND];
+    uint32_t hist[320];  // [0,286) litlen, [288,318) dist
+    int leastSum[32], leastCnt[32];
+    unsigned leastBlocked, leastSeen;
+    unsigned long long red;
+    int redAny;
+    int err;
+    TreeWs<290, 1024> tl;
+    TreeWs<32, 128> td;
+    // selection state
+    long long bestSize;
+    int bestStored;
+    long long sizeI, sizeC1, restMin;
+    unsigned candIndex, bestIndex;
+    // memo tables
+    unsigned long long memoH_hash[MEMO_H];
+    int memoH_n, memoH_next;
+    unsigned long long memoT_hash[MEMO_T];
+    int memoT_bits[MEMO_T];
+    unsigned char memoT_arg[MEMO_T];
+    int memoT_n, memoT_next;
+    int tmpIdx;
+    int trialBits[4 * 56];
+    unsigned long long hred[ENG_NT / 32];
+};
+
+enum { C_B = 0, C_BEST, C_O, C_H, C_E, C_X, C_CHK, C_T, C_Y, C_B1, C_B2, C_B3, C_B4, C_PP, C_CHK2, C_TMP };
+
+struct Eng {
+    EngSmem* S;
+    BlkView v;
+    uint32_t* masks;      // NCAND slots of maxwords
+    uint32_t maxwords;
+    MemoHEntry* memoH;    // MEMO_H entries
+    Tab* memoT;           // MEMO_T entries
+    int tid;
+
+    __device__ uint32_t* mask(int c) const { return masks + (size_t)c * maxwords; }
+
+    // ---- candidate copy (DeflateBlockHuffman.copy, :1174-1205, with value semantics) -------------
+    __device__ __noinline__ void copy(int dst, int src) {
+        if (dst == src) return;
+        const uint32_t* s = (const uint32_t*)&S->c[src];
+        uint32_t* d = (uint32_t*)&S->c[dst];
+        for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
+        const uint32_t* ms = mask(src);
+        uint32_t* md = mask(dst);
+        for (uint32_t k = tid; k < v.nwords; k += ENG_NT) md[k] = ms[k];
+        __syncthreads();
+    }
+
+    // ---- selection callback (DeflateStream.java:349-368) ------------------------------------------
+    __device__ __noinline__ void cb(int c, bool isRest = true) {
+        long long sz = cand_size(S->c[c]);
+        bool better = sz < S->bestSize;
+        __syncthreads();
+        if (tid == 0) {
+            if (isRest && sz < S->restMin) S->restMin = sz;
+            if (better) { S->bestSize = sz; S->bestStored = 0; S->bestIndex = S->candIndex; }
+            S->candIndex++;
+        }
+        if (better) copy(C_BEST, c); else __syncthreads();
+    }
+
+    // ---- CTA-wide passes ----------------------------------------------------------------------------
+    // literal cost of the bytes a match produces; returns -1 when a byte has no code
+    __device__ __forceinline__ int lit_cost(const uint8_t* L, uint32_t off, int len) const {
+        int tot = 0;
+        const uint8_t* p = v.out + off;
+        for (int k = 0; k < len; k++) {
+            int b = L[p[k]];
+            if (b < 1) return -1;
+            tot += b;
+        }
+        return tot;
+    }
+    // getLitLenSize for a match (:112-128)
+    __device__ __forceinline__ int ref_cost(const Tab& t, uint32_t s) const {
+        int ls = sym_lensym(s), ds = dist_sym(sym_dist(s));
+        return t.L[ls] + len_ebits_of(ls) + t.D[ds] + dist_ebits_of(ds);
+    }
+
+    // replaceBackrefsWithLiteralsIfSmaller(prune) on candidate c (in place)
+    __device__ __noinline__ void pass_replace(int c, bool prune) {
+        Cand& cd = S->c[c];
+        uint32_t* m = mask(c);
+        if (tid == 0) S->red = 0;
+        __syncthreads();
+        long long saved = 0;
+        const int lane = tid & 31;
+        for (uint32_t base = (tid >> 5) * 32; base < v.n; base += ENG_NT) {
+            uint32_t i = base + lane;
+            bool rep = false;
+            uint32_t word = m[base >> 5];
+            if (i < v.n) {
+                uint32_t s = v.sym[i];
+                if (sym_is_match(s) && !((word >> lane) & 1)) {
+                    int ref = ref_cost(cd.tab, s);
+                    int lit = lit_cost(cd.tab.L, v.symout[i], sym_len(s));
+                    if (lit >= 0 && (prune ? lit <= ref : lit < ref)) { rep = true; saved += ref - lit; }
+                }
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, rep);
+            if (lane == 0 && bal) m[base >> 5] = word | bal;
+        }
+        for (int d = 16; d > 0; d >>= 1) saved += __shfl_xor_sync(0xffffffffu, saved, d);
+        if (lane == 0 && saved) atomicAdd(&S->red, (unsigned long long)saved);
+        __syncthreads();
+        if (tid == 0) cd.payload -= (long long)S->red;
+        __syncthreads();
+    }
+
+    // removeDistLitLeastExpensive(mode) on candidate c (in place); no-op unless DYNAMIC
+    __device__ __noinline__ void pass_least(int c, int mode) {
+        Cand& cd = S->c[c];
+        if (cd.tab.type != 2) return;
+        uint32_t* m = mask(c);
+        if (tid < 32) { S->leastSum[tid] = 0; S->leastCnt[tid] = 0; }
+        if (tid == 0) { S->leastBlocked = 0; S->leastSeen = 0; }
+        __syncthreads();
+        for (uint32_t i = tid; i < v.n; i += ENG_NT) {
+            uint32_t s = v.sym[i];
+            if (sym_is_match(s) && !((m[i >> 5] >> (i & 31)) & 1)) {
+                int bin = sym_lensym(s) - 257;
+                atomicOr(&S->leastSeen, 1u << bin);
+                int lit = lit_cost(cd.tab.L, v.symout[i], sym_len(s));
+                if (lit < 0) atomicOr(&S->leastBlocked, 1u << bin);
+                else { atomicAdd(&S->leastSum[bin], lit - ref_cost(cd.tab, s)); atomicAdd(&S->leastCnt[bin], 1); }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int rem = -1, remSize = 0, remFreq = 0;
+            for (int i = 0; i < 32; i++) {
+                if (!((S->leastBlocked >> i) & 1) && ((S->leastSeen >> i) & 1)) {
+                    bool doRem = mode == 1 ? S->leastCnt[i] < remFreq : S->leastSum[i] < remSize;
+                    if (rem == -1 || doRem) { rem = i; remSize = S->leastSum[i]; remFreq = S->leastCnt[i]; }
+                }
+            }
+            S->tmpIdx = rem;
+            cd.payload += remSize;
+        }
+        __syncthreads();
+        const int rem = S->tmpIdx;
+        if (rem >= 0) {
+            const int lane = tid & 31;
+            for (uint32_t base = (tid >> 5) * 32; base < v.n; base += ENG_NT) {
+                uint32_t i = base + lane;
+                bool rep = false;
+                if (i < v.n) {
+                    uint32_t s = v.sym[i];
+                    rep = sym_is_match(s) && (sym_lensym(s) - 257 == rem);
+                }
+                unsigned bal = __ballot_sync(0xffffffffu, rep);
+                if (lane == 0 && bal) m[base >> 5] |= bal;
+            }
+        }
+        __syncthreads();
+    }
+
+    // histogram of candidate c's symbol list into S->hist
+    __device__ __noinline__ void pass_hist(int c) {
+        const uint32_t* m = mask(c);
+        for (int k = tid; k < 320; k += ENG_NT) S->hist[k] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < v.n; i += ENG_NT) {
+            uint32_t s = v.sym[i];
+            if (!sym_is_match(s)) {
+                if (s <= 256) atomicAdd(&S->hist[s], 1u);
+            } else if (!((m[i >> 5] >> (i & 31)) & 1)) {
+                atomicAdd(&S->hist[sym_lensym(s)], 1u);
+                atomicAdd(&S->hist[288 + dist_sym(sym_dist(s))], 1u);
+            } else {
+                const uint8_t* p = v.out + v.symout[i];
+                int len = sym_len(s);
+                for (int k = 0; k < len; k++) atomicAdd(&S->hist[p[k]], 1u);
+            }
+        }
+        __syncthreads();
+    }
+
+    // payload of the symbol list described by S->hist under table t (recodeToHuffmanInternal, :759-770)
+    __device__ __noinline__ long long hist_payload(const Tab& t) {
+        long long acc = 0;
+        for (int k = tid; k < 318; k += ENG_NT) {
+            uint32_t f = S->hist[k];
+            if (!f) continue;
+            int bits;
+            if (k < 257) bits = t.L[k];
+            else if (k < 286) bits = t.L[k] + len_ebits_of(k);
+            else if (k >= 288) bits = t.D[k - 288] + dist_ebits_of(k - 288);
+            else bits = 0;
+            acc += (long long)f * bits;
+        }
+        if (tid == 0) S->red = 0;
+        __syncthreads();
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if ((tid & 31) == 0 && acc) atomicAdd(&S->red, (unsigned long long)acc);
+        __syncthreads();
+        long long r = (long long)S->red;
+        __syncthreads();
+        return r;
+    }
+
+    __device__ __noinline__ unsigned long long hash_words(const uint32_t* p, int nwords32) {
+        unsigned long long h = 0;
+        for (int k = tid; k < nwords32; k += ENG_NT) {
+            unsigned long long x = (unsigned long long)p[k] + 0x9E3779B97F4A7C15ull * (unsigned long long)(k + 1);
+            x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+            h += x;
+        }
+        for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+        if ((tid & 31) == 0) S->hred[tid >> 5] = h;
+        __syncthreads();
+        unsigned long long r = 0;
+        for (int k = 0; k < ENG_NT / 32; k++) r += S->hred[k];
+        __syncthreads();
+        return r | 1ull;
+    }
+
+    // ---- recodeHuffman (:670-743) on candidate c: tables from the histogram, payload, default header
+    __device__ __noinline__ void op_recode(int c) {
+        pass_hist(c);
+        unsigned long long h = hash_words(S->hist, 320);
+        // memo lookup (exact: the histogram is compared in full on a hash hit)
+        if (tid == 0) S->tmpIdx = -1;
+        __syncthreads();
+        for (int k = tid; k < S->memoH_n; k += ENG_NT)
+            if (S->memoH_hash[k] == h) atomicMax(&S->tmpIdx, k);
+        __syncthreads();
+        int hit = S->tmpIdx;
+        if (hit >= 0) {
+            if (tid == 0) S->redAny = 0;
+            __syncthreads();
+            const uint32_t* mh = memoH[hit].hist;
+            bool diff = false;
+            for (int k = tid; k < 320; k += ENG_NT) diff |= (mh[k] != S->hist[k]);
+            if (diff) S->redAny = 1;
+            __syncthreads();
+            if (S->redAny) hit = -1;
+            __syncthreads();
+        }
+        if (hit >= 0) {
+            const uint32_t* s = (const uint32_t*)&memoH[hit].result;
+            uint32_t* d = (uint32_t*)&S->c[c];
+            for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
+            __syncthreads();
+            return;
+        }
+        Cand& cd = S->c[c];
+        // trailing zero-frequency trimming + the distance special cases (:683-740)
+        if (tid == 0) {
+            int nl = 286;
+            while (nl > 0 && S->hist[nl - 1] == 0) nl--;
+            cd.tab.nL = (uint16_t)nl;
+            if (huff_tree<290, 1024>(S->hist, nl, 15, cd.tab.L, S->tl)) S->err = ST_UNSUPPORTED;
+            for (int k = nl; k < MAX_LL; k++) cd.tab.L[k] = 0;
+        }
+        if (tid == 32) {
+            const uint32_t* df = S->hist + 288;
+            int nd = 30;
+            while (nd > 0 && df[nd - 1] == 0) nd--;
+            int nz = 0;
+            for (int k = 0; k < nd; k++) nz += df[k] != 0;
+            for (int k = 0; k < MAX_D; k++) cd.tab.D[k] = 0;
+            if (nd == 0) { cd.tab.nD = 1; }                                   // handleZero: one entry, length 0
+            else if (nz <= 1) { cd.tab.nD = (uint16_t)nd; cd.tab.D[nd - 1] = 1; }  // handleOne
+            else {
+                cd.tab.nD = (uint16_t)nd;
+                if (huff_tree<32, 128>(df, nd, 15, cd.tab.D, S->td)) S->err = ST_UNSUPPORTED;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) cd.tab.type = 2;
+        __syncthreads();
+        long long pay = hist_payload(cd.tab);
+        if (tid == 0) {
+            cd.payload = pay;
+            TreeWsCL ws;
+            if (hdr_rewrite(cd.tab, FLAGS_DEFAULT, cd.hdr, ws)) S->err = ST_UNSUPPORTED;
+        }
+        __syncthreads();
+        // store in the memo (FIFO replacement)
+        int slot;
+        if (tid == 0) {
+            slot = S->memoH_next;
+            S->memoH_next = (slot + 1) % MEMO_H;
+            if (S->memoH_n < MEMO_H) S->memoH_n++;
+            S->memoH_hash[slot] = h;
+            S->tmpIdx = slot;
+        }
+        __syncthreads();
+        slot = S->tmpIdx;
+        for (int k = tid; k < 320; k += ENG_NT) memoH[slot].hist[k] = S->hist[k];
+        {
+            const uint32_t* s = (const uint32_t*)&S->c[c];
+            uint32_t* d = (uint32_t*)&memoH[slot].result;
+            for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
+        }
+        __syncthreads();
+    }
+    // recodeHuffmanLessMatches (:655-658)
+    __device__ void op_recode_less(int c) { pass_replace(c, true); op_recode(c); }
+
+    // recodeToFixedHuffman (:637-653)
+    __device__ __noinline__ void op_to_fixed(int c) {
+        Cand& cd = S->c[c];
+        if (cd.tab.type == 1) return;
+        pass_hist(c);
+        if (tid == 0) {
+            cd.tab.type = 1; cd.tab.nL = 286; cd.tab.nD = 30;
+            fixed_lens(cd.tab.L, cd.tab.D);
+            for (int k = 286; k < MAX_LL; k++) cd.tab.L[k] = 0;
+            for (int k = 30; k < MAX_D; k++) cd.tab.D[k] = 0;
+            cd.hdr.np = 0; cd.hdr.ncl = 0; cd.hdr.bits = 0;
+        }
+        __syncthreads();
+        long long pay = hist_payload(cd.tab);
+        if (tid == 0) cd.payload = pay;
+        __syncthreads();
+    }
+
+    // DeflateBlockHuffman.optimise (:460-469): returns bits saved
+    __device__ __noinline__ long long op_optimise(int c) {
+        long long before = cand_size(S->c[c]);
+        __syncthreads();
+        pass_replace(c, false);
+        if (tid == 0 && S->c[c].tab.type == 2) hdr_optimise(S->c[c].hdr);
+        __syncthreads();
+        long long after = cand_size(S->c[c]);
+        __syncthreads();
+        return before - after;
+    }
+    // optimiseBlockNormal (DeflateStream.java:319-327): dst = copy(src).optimise(); returns saved > 0
+    __device__ bool op_optimise_normal(int dst, int src) {
+        copy(dst, src);
+        return op_optimise(dst) > 0;
+    }
+    __device__ void op_recode_header(int c) {
+        if (tid == 0 && S->c[c].tab.type == 2) { TreeWsCL ws; if (hdr_recode(S->c[c].hdr, ws)) S->err = ST_UNSUPPORTED; }
+        __syncthreads();
+    }
+    __device__ void op_recode_header_less(int c) {
+        if (tid == 0 && S->c[c].tab.type == 2) { TreeWsCL ws; if (hdr_recode_less(S->c[c].hdr, ws)) S->err = ST_UNSUPPORTED; }
+        __syncthreads();
+    }
+
+    // ---- the 56 header strategy trials of up to 4 bases (addOptimisedRecoded, :277-316) -------------
+    // bases are candidates C_B1.. (nb of them).  For each base the first-minimum strategy is looked up
+    // in / added to the Tab memo, then the virtual candidates are fed to the selection callback in the
+    // reference's order; only a winning trial is materialised.
+    __device__ __noinline__ void trials(int nb) {
+        // memo lookup per base
+        __shared__ int s_hit[4];
+        __shared__ unsigned long long s_hash[4];
+        for (int b = 0; b < nb; b++) {
+            unsigned long long h = hash_words((const uint32_t*)&S->c[C_B1 + b].tab, (int)(sizeof(Tab) / 4));
+            if (tid == 0) { s_hash[b] = h; s_hit[b] = -1; }
+            __syncthreads();
+            for (int k = tid; k < S->memoT_n; k += ENG_NT)
+                if (S->memoT_hash[k] == h) atomicMax(&s_hit[b], k);
+            __syncthreads();
+            int hit = s_hit[b];
+            if (hit >= 0) {
+                if (tid == 0) S->redAny = 0;
+                __syncthreads();
+                const uint32_t* a = (const uint32_t*)&memoT[hit];
+                const uint32_t* q = (const uint32_t*)&S->c[C_B1 + b].tab;
+                bool diff = false;
+                for (int k = tid; k < (int)(sizeof(Tab) / 4); k += ENG_NT) diff |= a[k] != q[k];
+                if (diff) S->redAny = 1;
+                __syncthreads();
+                if (S->redAny && tid == 0) s_hit[b] = -1;
+                __syncthreads();
+            }
+        }
+        // evaluate the misses: thread j -> (base j / 56, strategy j % 56)
+        {
+            int j = tid;
+            if (j < nb * 56 && s_hit[j / 56] < 0) {
+                Hdr h;
+                TreeWsCL ws;
+                if (hdr_trial(S->c[C_B1 + j / 56].tab, c_trial_flags[j % 56], h, ws)) S->err = ST_UNSUPPORTED;
+                S->trialBits[j] = h.bits;
+            }
+        }
+        __syncthreads();
+        if (tid < nb && s_hit[tid] < 0) {
+            int best = 0x7fffffff, arg = 0;
+            for (int k = 0; k < 56; k++) { int bts = S->trialBits[tid * 56 + k]; if (bts < best) { best = bts; arg = k; } }
+            S->trialBits[tid * 56] = best;
+            S->trialBits[tid * 56 + 1] = arg;
+        }
+        __syncthreads();
+        for (int b = 0; b < nb; b++) {
+            if (s_hit[b] < 0) {  // insert
+                int slot;
+                if (tid == 0) {
+                    slot = S->memoT_next;
+                    S->memoT_next = (slot + 1) % MEMO_T;
+                    if (S->memoT_n < MEMO_T) S->memoT_n++;
+                    S->memoT_hash[slot] = s_hash[b];
+                    S->memoT_bits[slot] = S->trialBits[b * 56];
+                    S->memoT_arg[slot] = (unsigned char)S->trialBits[b * 56 + 1];
+                    s_hit[b] = slot;
+                }
+                __syncthreads();
+                slot = s_hit[b];
+                const uint32_t* q = (const uint32_t*)&S->c[C_B1 + b].tab;
+                uint32_t* a = (uint32_t*)&memoT[slot];
+                for (int k = tid; k < (int)(sizeof(Tab) / 4); k += ENG_NT) a[k] = q[k];
+                __syncthreads();
+            }
+        }
+        // selection in reference order: base b's 56 candidates; the first minimum is the only one that
+        // can replace the incumbent
+        for (int b = 0; b < nb; b++) {
+            const int slot = s_hit[b];
+            const int bits = S->memoT_bits[slot], arg = S->memoT_arg[slot];
+            const long long sz = S->c[C_B1 + b].payload + bits;
+            const bool better = sz < S->bestSize;
+            __syncthreads();
+            if (tid == 0) {
+                if (sz < S->restMin) S->restMin = sz;
+                if (better) { S->bestSize = sz; S->bestStored = 0; S->bestIndex = S->candIndex + arg; }
+                S->candIndex += 56;
+            }
+            if (better) {
+                copy(C_BEST, C_B1 + b);
+                if (tid == 0) {
+                    TreeWsCL ws;
+                    if (hdr_trial(S->c[C_BEST].tab, c_trial_flags[arg], S->c[C_BEST].hdr, ws)) S->err = ST_UNSUPPORTED;
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // recodedHuffmanFull (DeflateStream.java:212-229): cur (slot a) is replaced while a further
+    // recodeHuffmanLessMatches shrinks it.  Returns true when the result differs from the start
+    // (the reference's `prunedFull != pruned` identity test).
+    __device__ __noinline__ bool op_recoded_full(int a, int tmp) {
+        bool changed = false;
+        while (true) {
+            copy(tmp, a);
+            op_recode_less(tmp);
+            long long s1 = cand_size(S->c[tmp]), s0 = cand_size(S->c[a]);
+            __syncthreads();
+            if (s1 >= s0) break;
+            copy(a, tmp);
+            changed = true;
+        }
+        return changed;
+    }
+
+    // addOptimisedRecoded (DeflateStream.java:265-317) for base block y
+    __device__ __noinline__ int aor(int y) {
+        op_optimise_normal(C_B1, y);                       // optimiseBlockCopyHelper(toOptimise)
+        copy(C_B2, y); op_recode(C_B2); op_optimise(C_B2);  // optimiseBlockHelper(recodedHuffman(.., false))
+        copy(C_PP, y); op_recode_less(C_PP);                // pruned
+        op_optimise_normal(C_B3, C_PP);                     // optimiseBlockCopyHelper(pruned)
+        copy(C_B4, C_PP);
+        bool full = op_recoded_full(C_B4, C_CHK2);          // prunedFull
+        if (full) op_optimise(C_B4);
+        trials(full ? 4 : 3);
+        return full ? 4 : 3;
+    }
+
+    // runOptimisationsCallback (DeflateStream.java:400-442) for block x
+    __device__ __noinline__ void run(int x) {
+        copy(C_T, x); op_recode_header(C_T); cb(C_T);                 // post
+        if (op_optimise_normal(C_TMP, C_T)) cb(C_TMP);                // post optimised
+        const int nb = aor(C_T);
+        copy(C_T, x); op_recode_header_less(C_T); cb(C_T);            // pruned header
+        if (op_optimise_normal(C_TMP, C_T)) cb(C_TMP);
+        if (tid == 0) S->candIndex += 56 * nb;                        // aor(prune): see file header
+        __syncthreads();
+        copy(C_Y, x); pass_least(C_Y, 0); aor(C_Y);
+        copy(C_Y, x); pass_least(C_Y, 1); aor(C_Y);
+    }
+
+    // runOptimisationsCallbackMulti (DeflateStream.java:443-463) for seed e
+    __device__ __noinline__ void multi(int e) {
+        cb(e); run(e);
+        copy(C_X, e); op_recode(C_X); cb(C_X); run(C_X);
+        copy(C_X, e); op_recode_less(C_X); cb(C_X); run(C_X);
+        bool full = op_recoded_full(C_X, C_CHK);
+        if (full) { cb(C_X); run(C_X); }
+    }
+
+    // DeflateStream.optimiseBlock (:343-490) for the Huffman block in C_B.  storedSize < 0: no stored
+    // candidate is compared (phase A resolves it afterwards from sizeI / sizeC1 / restMin).
+    // Result: C_BEST (or stored when S->bestStored).
+    __device__ void optimise_block(long long storedSize) {
+        if (tid == 0) {
+            S->bestSize = cand_size(S->c[C_B]);
+            S->bestStored = 0;
+            S->sizeI = S->bestSize;
+            S->sizeC1 = S->bestSize;
+            S->restMin = 0x7fffffffffffffffll;
+            S->candIndex = 0;
+            S->bestIndex = 0xffffffffu;
+        }
+        __syncthreads();
+        copy(C_BEST, C_B);
+        const int type = S->c[C_B].tab.type;
+        bool hasO = op_optimise_normal(C_O, C_B);
+        if (hasO) {
+            cb(C_O, false);
+            if (tid == 0) S->sizeC1 = cand_size(S->c[C_O]);
+            __syncthreads();
+        }
+        if (v.ulen <= 65535) {
+            if (storedSize >= 0 && storedSize < S->bestSize) {
+                __syncthreads();
+                if (tid == 0) { S->bestSize = storedSize; S->bestStored = 1; S->bestIndex = S->candIndex; }
+            }
+            __syncthreads();
+            if (tid == 0) S->candIndex++;
+            __syncthreads();
+        }
+        int H = C_B;
+        bool hasOh = hasO;
+        if (type == 1) {
+            copy(C_H, C_B); op_recode(C_H);
+            H = C_H;
+            hasOh = op_optimise_normal(C_O, C_H);
+        }
+        multi(H);
+        if (hasOh) multi(C_O);
+        if (type != 1) {
+            copy(C_E, H); op_to_fixed(C_E); op_optimise(C_E); cb(C_E);
+        }
+        copy(C_E, H); pass_least(C_E, 0); multi(C_E);
+        copy(C_E, H); pass_least(C_E, 1); multi(C_E);
+    }
+};
+
+}  // namespace d4

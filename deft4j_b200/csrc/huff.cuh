@@ -1,0 +1,318 @@
+// huff.cuh — single-thread building blocks of the block cost model:
+//   * huff_tree      : HuffmanTree (huffman/HuffmanTree.java:36-128,134-192) including the exact
+//                      java.util.PriorityQueue heap mechanics and the bespoke depth
+//                      limiter; output = code lengths (codes are canonical, see common.cuh)
+//   * hdr_*          : dynamic-header model: RLE packing with the 8 strategy flags
+//                      (HuffmanTable.java:42-159), header code build (Huffman.java:117-134), RLE
+//                      run -> literal replacement (DeflateBlockHuffman.java:222-296,321-332), trailing
+//                      zero code-length trimming (:335-370), recodeHeader (:579-635)
+// Each function runs in ONE thread; the engine runs many of them side by side (56 header strategy
+// trials per base, litlen and dist trees in different warps).
+#pragma once
+#include "common.cuh"
+
+namespace d4 {
+
+constexpr uint16_t NODE_NONE = 0xFFFF;
+
+template <int MAXLEAF, int MAXN>
+struct TreeWs {
+    unsigned long long heap[MAXLEAF + 2];  // (weight << 16) | node id
+    uint16_t parent[MAXN], left[MAXN], right[MAXN];
+    uint8_t side[MAXN];
+    uint16_t value[MAXLEAF + 2];      // leaf id -> symbol index (dummies included)
+    uint16_t leafDepth[MAXLEAF + 2];
+    uint16_t first[MAXLEAF + 4];      // first leaf (DFS order) at each depth == depthMap.get(d).get(0)
+    uint32_t stack[MAXLEAF + 4];
+};
+
+// Returns 0 on success, 1 when the node pool is exhausted or the tree cannot be balanced (the reference
+// throws AssertionError there).  lens[0..n) receives the code lengths (0 for unused symbols).
+template <int MAXLEAF, int MAXN>
+__device__ int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, TreeWs<MAXLEAF, MAXN>& ws) {
+    int hs = 0;  // heap size
+    auto W = [](unsigned long long k) { return k >> 16; };
+    auto add = [&](unsigned long long x) {  // PriorityQueue.offer + siftUp
+        int k = hs++;
+        while (k > 0) {
+            int p = (k - 1) >> 1;
+            unsigned long long e = ws.heap[p];
+            if (W(x) >= W(e)) break;
+            ws.heap[k] = e;
+            k = p;
+        }
+        ws.heap[k] = x;
+    };
+    auto poll = [&]() {  // PriorityQueue.poll + siftDown
+        unsigned long long result = ws.heap[0];
+        int s = --hs;
+        unsigned long long x = ws.heap[s];
+        if (s > 0) {
+            int k = 0, half = s >> 1;
+            while (k < half) {
+                int child = 2 * k + 1;
+                unsigned long long c = ws.heap[child];
+                int r = child + 1;
+                if (r < s) {
+                    unsigned long long cr = ws.heap[r];
+                    if (W(c) > W(cr)) { c = cr; child = r; }
+                }
+                if (W(x) <= W(c)) break;
+                ws.heap[k] = c;
+                k = child;
+            }
+            ws.heap[k] = x;
+        }
+        return result;
+    };
+    for (int i = 0; i < n; i++) lens[i] = 0;
+    int nleaf = 0;
+    for (int i = 0; i < n; i++)
+        if (freq[i] > 0) {
+            ws.value[nleaf] = (uint16_t)i;
+            add(((unsigned long long)freq[i] << 16) | (unsigned)nleaf);
+            nleaf++;
+        }
+    int index = 0;
+    while (hs < 2) {  // dummy leaves (HuffmanTree.java:50-58)
+        if (index >= n || freq[index] == 0) {
+            ws.value[nleaf] = (uint16_t)index;
+            add((1ull << 16) | (unsigned)nleaf);
+            nleaf++;
+        }
+        index++;
+    }
+    int nn = nleaf;
+    const int total = hs;
+    for (int i = 0; i < total - 1; i++) {
+        unsigned long long l = poll(), r = poll();
+        int id = nn++;
+        int li = (int)(l & 0xFFFF), ri = (int)(r & 0xFFFF);
+        ws.left[id] = (uint16_t)li; ws.right[id] = (uint16_t)ri;
+        ws.parent[li] = (uint16_t)id; ws.side[li] = 0;
+        ws.parent[ri] = (uint16_t)id; ws.side[ri] = 1;
+        add(((W(l) + W(r)) << 16) | (unsigned)id);
+    }
+    const int root = (int)(poll() & 0xFFFF);
+    ws.parent[root] = NODE_NONE;
+    int maxDepth = 0;
+    auto traverse = [&]() {  // HuffmanTree.traverse (:134-158), left-first DFS
+        for (int d = 0; d < MAXLEAF + 4; d++) ws.first[d] = NODE_NONE;
+        maxDepth = 0;
+        int sp = 0;
+        ws.stack[sp++] = (uint32_t)root;
+        while (sp > 0) {
+            uint32_t e = ws.stack[--sp];
+            int node = (int)(e & 0xFFFF), d = (int)(e >> 16);
+            if (d > maxDepth) maxDepth = d;
+            if (node >= nleaf) {
+                ws.stack[sp++] = (uint32_t)ws.right[node] | ((uint32_t)(d + 1) << 16);
+                ws.stack[sp++] = (uint32_t)ws.left[node] | ((uint32_t)(d + 1) << 16);
+            } else {
+                if (ws.first[d] == NODE_NONE) ws.first[d] = (uint16_t)node;
+                ws.leafDepth[node] = (uint16_t)d;
+            }
+        }
+    };
+    traverse();
+    while (maxDepth > limit) {  // HuffmanTree.java:75-127
+        int leafA = ws.first[maxDepth];
+        int parent1 = ws.parent[leafA];
+        int leafB = (ws.side[leafA] == 0) ? ws.right[parent1] : ws.left[parent1];
+        int parent2 = ws.parent[parent1];
+        if (ws.side[parent1] == 0) { ws.left[parent2] = (uint16_t)leafB; ws.side[leafB] = 0; }
+        else                       { ws.right[parent2] = (uint16_t)leafB; ws.side[leafB] = 1; }
+        ws.parent[leafB] = (uint16_t)parent2;
+        bool moved = false;
+        for (int i = maxDepth - 2; i >= 1; i--) {
+            if (ws.first[i] != NODE_NONE) {
+                int leafC = ws.first[i];
+                int parent3 = ws.parent[leafC];
+                int sideC = ws.side[leafC];
+                if (nn >= MAXN) return 1;
+                int in = nn++;
+                ws.left[in] = (uint16_t)leafA; ws.parent[leafA] = (uint16_t)in; ws.side[leafA] = 0;
+                ws.right[in] = (uint16_t)leafC; ws.parent[leafC] = (uint16_t)in; ws.side[leafC] = 1;
+                if (sideC == 0) { ws.left[parent3] = (uint16_t)in; ws.side[in] = 0; }
+                else            { ws.right[parent3] = (uint16_t)in; ws.side[in] = 1; }
+                ws.parent[in] = (uint16_t)parent3;
+                moved = true;
+                break;
+            }
+        }
+        if (!moved) return 1;
+        traverse();
+    }
+    for (int l = 0; l < nleaf; l++)
+        if (ws.value[l] < n) lens[ws.value[l]] = (uint8_t)ws.leafDepth[l];
+    return 0;
+}
+
+using TreeWsCL = TreeWs<21, 192>;
+
+// ---- header model ---------------------------------------------------------------------------------
+// strategy flags: bit0 ohh, bit1 use8, bit2 use7, bit3 alt8, bit4 noRep, bit5 noZRep, bit6 noZRep2,
+// bit7 noRepZeros, bit8 prune (DeflateStream.java:184-198,277-316)
+__constant__ uint16_t c_trial_flags[56] = {
+    0x7, 0x3, 0x5, 0x0, 0x47, 0x43, 0x45, 0x40, 0x27, 0x23, 0x25, 0x20, 0x67, 0x63, 0x65, 0x60, 0x10, 0x50, 0x30,
+    0x70, 0x107, 0x103, 0x105, 0x100, 0x147, 0x143, 0x145, 0x140, 0x127, 0x123, 0x125, 0x120, 0x167, 0x163, 0x165,
+    0x160, 0x110, 0x150, 0x130, 0x170, 0xa7, 0xa3, 0xa5, 0xa0, 0xe7, 0xe3, 0xe5, 0xe0, 0x1a7, 0x1a3, 0x1a5, 0x1a0,
+    0x1e7, 0x1e3, 0x1e5, 0x1e0};
+constexpr int FLAGS_DEFAULT = 0x7;  // rewriteHeader() defaults (DeflateBlockHuffman.java:480-482)
+
+__device__ __forceinline__ int pair_extra_bits(int sym) { return sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0; }
+
+// getRLEPairSize (:133-163)
+__device__ __forceinline__ int pair_size(uint16_t p, const uint8_t* CL) {
+    int s = pair_sym(p);
+    return CL[s] + (pair_run(p) > 0 ? pair_extra_bits(s) : 0);
+}
+
+// removeDynHeaderTrailingZeroLenCodelens (:335-364); returns bits removed
+__device__ inline int hdr_trim(Hdr& h) {
+    int saved = 0;
+    while (true) {
+        int lastZero = -1, lastNonZero = h.ncl;
+        for (int i = 0; i < h.ncl; i++) {
+            if (h.CL[c_codelen_order[i]] == 0) lastZero = i; else lastNonZero = i;
+        }
+        if (lastZero > lastNonZero) { h.ncl = (uint8_t)lastZero; saved += 3; } else break;
+    }
+    return saved;
+}
+
+// Huffman.ofRLEPacked (Huffman.java:117-134) on the pair list
+__device__ inline int hdr_build_code(Hdr& h, TreeWsCL& ws) {
+    uint32_t freq[19];
+    for (int i = 0; i < 19; i++) freq[i] = 0;
+    for (int i = 0; i < h.np; i++) freq[pair_sym(h.pairs[i])]++;
+    return huff_tree<21, 192>(freq, 19, 7, h.CL, ws);
+}
+
+__device__ inline int hdr_pairs_bits(const Hdr& h) {
+    int b = 0;
+    for (int i = 0; i < h.np; i++) b += pair_size(h.pairs[i], h.CL);
+    return b;
+}
+
+// rewriteHeader (:484-577): pack (HuffmanTable.java:70-159) straight into pairs, build the header code,
+// size it, trim.
+__device__ inline int hdr_rewrite(const Tab& t, int flags, Hdr& h, TreeWsCL& ws) {
+    const bool ohh = flags & 1, use8 = flags & 2, use7 = flags & 4, alt8 = flags & 8, noRep = flags & 16,
+               noZRep = flags & 32, noZRep2 = flags & 64, noRepZeros = flags & 128;
+    const int nL = t.nL, n = t.nL + t.nD;
+    int np = 0;
+    auto get = [&](int i) -> int { return i < nL ? t.L[i] : t.D[i - nL]; };
+    auto emit = [&](int sym, int run, int val) { h.pairs[np++] = pair_pack(sym, run, val); };
+    int last = get(0), runLength = 1;
+    for (int i = 1; i <= n; i++) {
+        if (i < n && get(i) == last) { runLength++; continue; }
+        if (last == 0) {
+            if (!noZRep2) {
+                while (runLength >= 138) { emit(18, 138, 0); runLength -= 138; }
+                if (runLength >= 11) { emit(18, runLength, 0); runLength = 0; }
+            }
+            if (!noZRep) {
+                while (runLength >= 10) { emit(17, 10, 0); runLength -= 10; }
+                if (runLength >= 3) { emit(17, runLength, 0); runLength = 0; }
+            }
+        }
+        if (!noRep && runLength > 0 && (!noRepZeros || last != 0)) {
+            emit(last, 0, last);
+            runLength--;
+            int j = 6;
+            while (j >= 3) {
+                if (ohh) {
+                    if (use8 && runLength == 8) {
+                        emit(16, alt8 ? 5 : 4, last); emit(16, alt8 ? 3 : 4, last);
+                        runLength -= 8;
+                        break;
+                    }
+                    if (use7 && runLength == 7) {
+                        emit(16, 4, last); emit(16, 3, last);
+                        runLength -= 7;
+                        break;
+                    }
+                }
+                if (runLength - j >= 0) { emit(16, j, last); runLength -= j; } else j--;
+            }
+        }
+        while (runLength > 0) { emit(last, 0, last); runLength--; }
+        if (i < n) { last = get(i); runLength = 1; }
+    }
+    h.np = (uint16_t)np;
+    if (hdr_build_code(h, ws)) return 1;
+    h.ncl = 19;
+    h.bits = 5 + 5 + 4 + 19 * 3 + hdr_pairs_bits(h);
+    h.bits -= hdr_trim(h);
+    return 0;
+}
+
+// replaceRLERunsWithLiteralsIfSmaller (:321-332) via replaceWithLiteralsIfSmaller (:222-296): a run is
+// replaced by `run` plain lengths when those cost less (prune: no more) than the run code; only when
+// the repeated value has a header code.  In-place expansion from the back.
+__device__ inline void hdr_replace_runs(Hdr& h, bool prune) {
+    int newNp = 0, saved = 0;
+    bool any = false;
+    for (int i = 0; i < h.np; i++) {
+        uint16_t p = h.pairs[i];
+        int run = pair_run(p);
+        int add = 1;
+        if (run > 0) {
+            int size = pair_size(p, h.CL);
+            int b = h.CL[pair_val(p)];
+            int tot = b * run;
+            if (b >= 1 && (prune ? tot <= size : tot < size)) { add = run; saved += size - tot; any = true; }
+        }
+        newNp += add;
+    }
+    if (!any) return;
+    int w = newNp;
+    for (int i = h.np - 1; i >= 0; i--) {
+        uint16_t p = h.pairs[i];
+        int run = pair_run(p);
+        bool rep = false;
+        if (run > 0) {
+            int size = pair_size(p, h.CL);
+            int b = h.CL[pair_val(p)];
+            int tot = b * run;
+            rep = b >= 1 && (prune ? tot <= size : tot < size);
+        }
+        if (rep) {
+            int v = pair_val(p);
+            for (int k = 0; k < run; k++) h.pairs[--w] = pair_pack(v, 0, v);
+        } else {
+            h.pairs[--w] = p;
+        }
+    }
+    h.np = (uint16_t)newNp;
+    h.bits -= saved;
+}
+
+// recodeHeader (:579-629): new header code from the existing pairs; numCodelenLens is NOT reset
+// (SURVEY.md H8), only trimmed further.
+__device__ inline int hdr_recode(Hdr& h, TreeWsCL& ws) {
+    if (hdr_build_code(h, ws)) return 1;
+    hdr_trim(h);
+    h.bits = 5 + 5 + 4 + h.ncl * 3 + hdr_pairs_bits(h);
+    return 0;
+}
+// recodeHeaderToLessRLEMatches (:632-635)
+__device__ inline int hdr_recode_less(Hdr& h, TreeWsCL& ws) {
+    hdr_replace_runs(h, true);
+    return hdr_recode(h, ws);
+}
+// optimiseHeader (:471-476)
+__device__ inline void hdr_optimise(Hdr& h) {
+    h.bits -= hdr_trim(h);
+    hdr_replace_runs(h, false);
+}
+// optimiseBlockDynBlock (DeflateStream.java:184-198): one header strategy trial
+__device__ inline int hdr_trial(const Tab& t, int flags, Hdr& h, TreeWsCL& ws) {
+    if (hdr_rewrite(t, flags & 0xFF, h, ws)) return 1;
+    if (flags & 0x100) { if (hdr_recode_less(h, ws)) return 1; }
+    hdr_optimise(h);
+    return 0;
+}
+
+}  // namespace d4

@@ -1,0 +1,372 @@
+// optimise.cuh — stream-level drivers around the candidate engine.
+//
+//   k_init_state : BlockRec (as parsed) -> BlkState (current model), one thread per block.
+//   k_opt_blocks : phase A — DeflateStream.optimise's per-block fix-point loop (DeflateStream.java:504-530)
+//                  for every block in parallel.  Huffman candidate sizes do not depend on the bit
+//                  position, only the stored-block candidate does (DeflateBlockUncompressed.java:70-74),
+//                  so each round logs (incumbent, "optimised" candidate, best of the rest) and
+//                  k_finish replays the rounds with the real position to decide stored-vs-Huffman.
+//   k_finish     : one CTA per stream — replays phase A with `pos` (incl. the reference's position
+//                  drift, SURVEY.md H5, and the loop exit after an empty-block removal, H6), runs the
+//                  merge phase (DeflateStream.mergeBlocks, :568-650) sequentially with the engine, and
+//                  lays the final blocks out (bit positions, BFINAL, stream size, bits saved).
+#pragma once
+#include "engine.cuh"
+
+namespace d4 {
+
+constexpr int MAXR = 16;  // optimiseBlock rounds logged per block
+
+struct BlkState {
+    Cand cand;            // cand.tab.type: 0 STORED, 1 FIXED, 2 DYNAMIC
+    uint64_t sym_off;     // symbol pool index
+    uint64_t out_off;     // decoded pool offset
+    uint64_t mask_off;    // word offset in the mask pool
+    uint64_t out_len;
+    uint32_t n_sym;
+    int32_t alive;
+    int32_t bfinal;
+    int32_t nrounds;
+    uint64_t bit_pos;     // position of the 3-bit header in the rewritten stream
+    long long size_bits;  // getSizeBits(bit_pos + 3)
+};
+struct RoundLog { long long sizeI[MAXR], sizeC1[MAXR], restMin[MAXR], best[MAXR]; };
+
+struct StreamState {
+    uint64_t blk_base;
+    uint32_t n_blocks;
+    uint32_t cut;          // blocks [0, cut) take part in phase A (first removable empty block index)
+    uint32_t selected;     // 0: leave untouched (not part of this optimise call)
+    int32_t status;
+    long long saved_bits;
+    uint64_t total_bits;   // getSizeBits() of the current model
+};
+
+__device__ __forceinline__ long long stored_size(uint64_t len, long long alignment) {
+    long long c = alignment % 8;
+    c = c == 0 ? 0 : 8 - c;
+    return ((long long)len + 4) * 8 + c;
+}
+__device__ __forceinline__ long long blk_size(const BlkState& b, long long alignment) {
+    return b.cand.tab.type == 0 ? stored_size(b.out_len, alignment) : cand_size(b.cand);
+}
+
+__global__ void k_init_state(const BlockRec* __restrict__ recs, const StreamDesc* __restrict__ descs,
+                             const uint32_t* __restrict__ blk_stream, const uint64_t* __restrict__ mask_offs,
+                             BlkState* __restrict__ bs, uint64_t nblk) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblk) return;
+    const BlockRec& r = recs[i];
+    const StreamDesc& sd = descs[blk_stream[i]];
+    BlkState& b = bs[i];
+    b.cand.tab = r.tab;
+    b.cand.tab.type = r.type;
+    b.cand.tab.pad[0] = b.cand.tab.pad[1] = b.cand.tab.pad[2] = 0;
+    b.cand.hdr = r.hdr;
+    b.cand.payload = r.payload_bits;
+    b.sym_off = sd.sym_base + r.sym_base;
+    b.out_off = sd.out_base + r.out_base;
+    b.mask_off = mask_offs[i];
+    b.out_len = r.out_len;
+    b.n_sym = r.n_sym;
+    b.alive = 1;
+    b.bfinal = r.bfinal;
+    b.nrounds = 0;
+    b.bit_pos = r.hdr_bit;
+    b.size_bits = (long long)(r.end_bit - r.hdr_bit) - 3;
+}
+
+struct EngScratch {
+    uint32_t* masks;      // per CTA: NCAND * maxwords
+    MemoHEntry* memoH;    // per CTA: MEMO_H
+    Tab* memoT;           // per CTA: MEMO_T
+    uint32_t maxwords;
+};
+
+__device__ inline void eng_init(Eng& e, EngSmem* S, const EngScratch& sc, int cta) {
+    e.S = S;
+    e.tid = threadIdx.x;
+    e.maxwords = sc.maxwords;
+    e.masks = sc.masks + (size_t)cta * NCAND * sc.maxwords;
+    e.memoH = sc.memoH + (size_t)cta * MEMO_H;
+    e.memoT = sc.memoT + (size_t)cta * MEMO_T;
+    if (threadIdx.x == 0) { S->memoH_n = 0; S->memoH_next = 0; S->memoT_n = 0; S->memoT_next = 0; S->err = 0; }
+    __syncthreads();
+}
+
+// load BlkState b into candidate slot C_B with the given mask source (pool words, or nullptr = zeros)
+__device__ inline void eng_load(Eng& e, const BlkState& b, const uint32_t* maskSrc) {
+    const uint32_t* s = (const uint32_t*)&b.cand;
+    uint32_t* d = (uint32_t*)&e.S->c[C_B];
+    for (int k = e.tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
+    uint32_t* m = e.mask(C_B);
+    for (uint32_t k = e.tid; k < e.v.nwords; k += ENG_NT) m[k] = maskSrc ? maskSrc[k] : 0u;
+    __syncthreads();
+}
+
+// --------------------------------------------------------------------------------------------------
+// phase A
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ENG_NT)
+k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __restrict__ bs, RoundLog* __restrict__ logs,
+             const uint32_t* __restrict__ sym, const uint32_t* __restrict__ symout, const uint8_t* __restrict__ out,
+             uint32_t* __restrict__ maskpool, EngScratch sc, unsigned* __restrict__ counter, int* __restrict__ gerr) {
+    __shared__ EngSmem S;
+    __shared__ uint32_t s_job;
+    Eng e;
+    eng_init(e, &S, sc, blockIdx.x);
+    const int tid = threadIdx.x;
+    while (true) {
+        if (tid == 0) s_job = atomicAdd(counter, 1u);
+        __syncthreads();
+        const uint32_t job = s_job;
+        __syncthreads();
+        if (job >= njobs) break;
+        BlkState& b = bs[jobs[job]];
+        e.v.sym = sym + b.sym_off;
+        e.v.symout = symout + b.sym_off;
+        e.v.out = out;
+        e.v.n = b.n_sym;
+        e.v.nwords = (b.n_sym + 31) / 32;
+        e.v.ulen = b.out_len;
+        eng_load(e, b, nullptr);
+        RoundLog& lg = logs[jobs[job]];
+        int r = 0;
+        while (true) {
+            e.optimise_block(-1);
+            if (tid == 0 && r < MAXR) {
+                lg.sizeI[r] = S.sizeI; lg.sizeC1[r] = S.sizeC1; lg.restMin[r] = S.restMin; lg.best[r] = S.bestSize;
+            }
+            const bool improved = S.bestSize < S.sizeI;
+            __syncthreads();
+            r++;
+            if (!improved) break;
+            if (r >= MAXR) { if (tid == 0) S.err = ST_UNSUPPORTED; break; }
+            e.copy(C_B, C_BEST);
+        }
+        __syncthreads();
+        // write the fix-point back (C_B holds it: the last round did not improve)
+        {
+            const uint32_t* s = (const uint32_t*)&S.c[C_B];
+            uint32_t* d = (uint32_t*)&b.cand;
+            for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
+            const uint32_t* m = e.mask(C_B);
+            uint32_t* pm = maskpool + b.mask_off;
+            for (uint32_t k = tid; k < e.v.nwords; k += ENG_NT) pm[k] = m[k];
+            if (tid == 0) b.nrounds = r;
+        }
+        __syncthreads();
+        if (S.err) { if (tid == 0) { atomicMax(gerr, S.err); S.err = 0; } }
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// k_finish: replay + merge + layout, one CTA per stream
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ENG_NT)
+k_finish(StreamState* __restrict__ streams, BlkState* __restrict__ bs, const RoundLog* __restrict__ logs,
+         uint32_t* __restrict__ sym, const uint32_t* __restrict__ symout, const uint8_t* __restrict__ out,
+         uint32_t* __restrict__ maskpool, EngScratch sc, int merge, int* __restrict__ gerr) {
+    __shared__ EngSmem S;
+    __shared__ long long s_pos, s_saved;
+    __shared__ int s_cur, s_next, s_do, s_first;
+    StreamState& st = streams[blockIdx.x];
+    if (!st.selected || st.status != ST_OK) return;
+    const int tid = threadIdx.x;
+    BlkState* B = bs + st.blk_base;
+    const uint32_t nb = st.n_blocks;
+    Eng e;
+    if (merge) eng_init(e, &S, sc, blockIdx.x);
+
+    // ---- replay of DeflateStream.optimise (:496-566) with the real bit position --------------------
+    if (tid == 0) {
+        long long pos = 0, saved = 0;
+        for (uint32_t k = 0; k < nb; k++) {
+            BlkState& b = B[k];
+            if (b.out_len > 0 || (k == 0 && nb == 1)) {
+                if (b.cand.tab.type == 0) {  // stored blocks have no candidates
+                    pos += 3;
+                    pos += stored_size(b.out_len, pos);
+                } else {
+                    const RoundLog& lg = logs[st.blk_base + k];
+                    int r = 0;
+                    while (true) {
+                        pos += 3;
+                        const long long I = lg.sizeI[r], C1 = lg.sizeC1[r], R = lg.restMin[r], W = lg.best[r];
+                        const long long m1 = I < C1 ? I : C1;
+                        bool storedWins = false;
+                        long long Ssz = 0;
+                        if (b.out_len <= 65535) {
+                            Ssz = stored_size(b.out_len, pos);
+                            storedWins = Ssz < m1 && Ssz <= R;
+                        }
+                        if (storedWins) {
+                            saved += I - Ssz;
+                            b.cand.tab.type = 0;
+                            pos += stored_size(b.out_len, pos);
+                            // next pass over the (now stored) block finds nothing
+                            pos += 3;
+                            pos += stored_size(b.out_len, pos);
+                            break;
+                        }
+                        if (W < I) { saved += I - W; pos += W; r++; continue; }
+                        pos += I;
+                        break;
+                    }
+                }
+            } else {  // empty block: removed, and the reference's loop ends here (H6)
+                saved += blk_size(b, pos + 3) + 3;
+                b.alive = 0;
+                break;
+            }
+        }
+        s_saved = saved;
+    }
+    __syncthreads();
+
+    // ---- DeflateStream.mergeBlocks (:568-650) ---------------------------------------------------------
+    if (merge) {
+        if (tid == 0) {
+            s_pos = 0; s_first = 1;
+            int c = 0;
+            while (c < (int)nb && !B[c].alive) c++;
+            s_cur = c;
+        }
+        __syncthreads();
+        while (true) {
+            const int cur = s_cur;
+            if (cur >= (int)nb) break;
+            if (tid == 0) {
+                int n = cur + 1;
+                while (n < (int)nb && !B[n].alive) n++;
+                s_next = n < (int)nb ? n : -1;
+                s_do = 0;
+                BlkState& c = B[cur];
+                if (s_first && s_next < 0) {
+                    s_pos += blk_size(c, s_pos + 3) + 3;
+                    s_do = 3;  // advance
+                } else if (c.out_len > 0) {
+                    s_pos += 3;
+                    if (s_next >= 0) {
+                        BlkState& nx = B[s_next];
+                        if (c.cand.tab.type == 0) {
+                            if (c.out_len + nx.out_len <= 65535) {  // stored + anything, by size only
+                                long long curSize = blk_size(c, s_pos);
+                                long long nextSize = blk_size(nx, s_pos + curSize + 3);
+                                long long mergedSize = stored_size(c.out_len + nx.out_len, s_pos);
+                                long long cs = curSize + 3 + nextSize - mergedSize;
+                                if (cs > 0) {
+                                    s_saved += cs;
+                                    c.out_len += nx.out_len;
+                                    c.n_sym = 0;
+                                    nx.alive = 0;
+                                    s_do = 2;  // merged: same block again
+                                }
+                            }
+                        } else if (nx.cand.tab.type != 0) {
+                            s_do = 1;  // Huffman + Huffman: needs the engine
+                        }
+                    }
+                    if (s_do == 0) s_do = 3;
+                    if (s_do != 1) s_pos += blk_size(c, s_pos);
+                } else {
+                    s_saved += blk_size(c, s_pos + 3) + 3;
+                    c.alive = 0;
+                    s_do = 4;  // removed: loop ends (H6)
+                }
+            }
+            __syncthreads();
+            int action = s_do;
+            if (action == 1) {
+                BlkState& c = B[cur];
+                BlkState& nx = B[s_next];
+                const uint32_t nA = c.n_sym, nB = nx.n_sym;
+                // merged symbol list = A without its EOB + B (DeflateBlockHuffman.merge, :1233-1271)
+                if (tid == 0) sym[c.sym_off + nA - 1] = SYM_NOP;
+                e.v.sym = sym + c.sym_off;
+                e.v.symout = symout + c.sym_off;
+                e.v.out = out;
+                e.v.n = nA + nB;
+                e.v.nwords = (nA + nB + 31) / 32;
+                e.v.ulen = c.out_len + nx.out_len;
+                uint32_t* m = e.mask(C_B);
+                for (uint32_t k = tid; k < e.v.nwords; k += ENG_NT) m[k] = 0;
+                __syncthreads();
+                const uint32_t* ma = maskpool + c.mask_off;
+                const uint32_t* mb = maskpool + nx.mask_off;
+                for (uint32_t i = tid; i < nA; i += ENG_NT)
+                    if ((ma[i >> 5] >> (i & 31)) & 1) atomicOr(&m[i >> 5], 1u << (i & 31));
+                for (uint32_t i = tid; i < nB; i += ENG_NT)
+                    if ((mb[i >> 5] >> (i & 31)) & 1) atomicOr(&m[(nA + i) >> 5], 1u << ((nA + i) & 31));
+                if (tid == 0) { S.c[C_B].tab.type = 2; S.c[C_B].payload = 0; S.c[C_B].hdr.bits = 0; }
+                __syncthreads();
+                e.op_to_fixed(C_B);  // both halves recoded to the fixed code; payload from the histogram
+                const long long pos = s_pos;
+                e.optimise_block(stored_size(e.v.ulen, pos));
+                if (tid == 0) {
+                    long long curSize = blk_size(c, pos);
+                    long long nextSize = blk_size(nx, pos + curSize + 3);
+                    long long cs = curSize + 3 + nextSize - S.bestSize;
+                    s_do = cs > 0 ? 5 : 6;
+                    if (cs > 0) s_saved += cs;
+                }
+                __syncthreads();
+                if (s_do == 5) {  // accept
+                    if (!S.bestStored) {
+                        const uint32_t* s = (const uint32_t*)&S.c[C_BEST];
+                        uint32_t* d = (uint32_t*)&c.cand;
+                        for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
+                        const uint32_t* bm = e.mask(C_BEST);
+                        uint32_t* pm = maskpool + c.mask_off;
+                        for (uint32_t k = tid; k < e.v.nwords; k += ENG_NT) pm[k] = bm[k];
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        if (S.bestStored) c.cand.tab.type = 0;
+                        c.n_sym = nA + nB;
+                        c.out_len += nx.out_len;
+                        nx.alive = 0;
+                    }
+                } else {
+                    if (tid == 0) sym[c.sym_off + nA - 1] = 256;  // restore the EOB
+                }
+                __syncthreads();
+                if (tid == 0) s_pos += blk_size(c, s_pos);
+                action = (s_do == 5) ? 2 : 3;
+                __syncthreads();
+            }
+            if (action == 4) break;
+            if (tid == 0) {
+                if (action == 3) {  // finishPass
+                    s_cur = s_next < 0 ? (int)nb : s_next;
+                    s_first = 0;
+                }
+            }
+            __syncthreads();
+        }
+        if (S.err && tid == 0) atomicMax(gerr, S.err);
+    }
+    __syncthreads();
+
+    // ---- layout: DeflateStream.getSizeBits (:171-182) + BFINAL from list position (:128-145) ----------
+    if (tid == 0) {
+        long long size = 0;
+        int last = -1;
+        for (uint32_t k = 0; k < nb; k++) {
+            BlkState& b = B[k];
+            if (!b.alive) continue;
+            b.bit_pos = (uint64_t)size;
+            size += 3;
+            b.size_bits = blk_size(b, size);
+            size += b.size_bits;
+            b.bfinal = 0;
+            last = (int)k;
+        }
+        if (last >= 0) B[last].bfinal = 1;
+        st.total_bits = (uint64_t)size;
+        st.saved_bits = s_saved;
+    }
+}
+
+}  // namespace d4

@@ -1,0 +1,520 @@
+// parse.cuh — Huffman decode of deflate streams on the GPU.
+//
+// Pass 1  k_count : one CTA per stream.  Blocks are walked in order (block boundaries are found on the
+//                   device); inside a Huffman block the CTA decodes a window of NT*CHUNK_BITS bits
+//                   speculatively: thread t starts at bit t*CHUNK_BITS assuming a symbol boundary,
+//                   then a fix-up loop re-decodes every chunk whose predecessor ended elsewhere until
+//                   the chain from the (known) window start is consistent (self-synchronisation).
+//                   Output: BlockRec per block (code tables, header pairs, exact bit sizes), one
+//                   ChunkRec per valid chunk (start bit, symbol index, decoded offset), stream totals.
+// Pass 2  k_emit  : one CTA per Huffman block, one thread per ChunkRec: decode again, now writing the
+//                   packed symbols and their decoded offsets.  Stored blocks are copied.
+// Pass 3  k_lz_*  : LZ77 resolution by pointer doubling over the decoded bytes (every byte of a match
+//                   points at its source byte; literals are roots), replacing the reference's
+//                   byte-serial readSlice (DeflateBlock.java:147-222).
+//
+// Decoding restates the reference decoder's semantics (Huffman.java:170-197): codes are matched one
+// length at a time, first match wins, no validity check on the length set, failure after 15 bits.
+#pragma once
+#include "common.cuh"
+
+namespace d4 {
+
+constexpr int PARSE_NT = 1024;       // threads per stream CTA in k_count
+constexpr int CHUNK_BITS = 256;      // speculative chunk; must exceed the longest unit (48 bits)
+
+struct DecTab {
+    uint32_t first[16];   // canonical code value of the first code of each length
+    uint16_t count[16];
+    uint16_t offs[16];
+    uint16_t symtab[MAX_LL];
+};
+
+// Huffman.buildCodes (Huffman.java:35-64) turned into a by-length decode table.
+__device__ inline void build_dectab(const uint8_t* lens, int n, DecTab& t) {
+    for (int l = 0; l < 16; l++) { t.count[l] = 0; t.first[l] = 0; t.offs[l] = 0; }
+    for (int i = 0; i < n; i++) if (lens[i] > 0 && lens[i] < 16) t.count[lens[i]]++;
+    uint32_t next = 0;
+    int lastShift = 0, off = 0;
+    for (int l = 1; l < 16; l++) {
+        t.offs[l] = (uint16_t)off;
+        off += t.count[l];
+        if (t.count[l] == 0) continue;
+        next <<= (l - lastShift);
+        lastShift = l;
+        t.first[l] = next;
+        next += t.count[l];
+    }
+    uint16_t fill[16];
+    for (int l = 0; l < 16; l++) fill[l] = t.offs[l];
+    for (int i = 0; i < n; i++) if (lens[i] > 0 && lens[i] < 16) t.symtab[fill[lens[i]]++] = (uint16_t)i;
+}
+
+// returns symbol (>= 0) and its length through *len, or -1 (no code within 15 bits)
+__device__ __forceinline__ int decode_sym(const DecTab& t, uint64_t w, int* len) {
+    uint32_t code = 0;
+#pragma unroll 1
+    for (int l = 1; l <= 15; l++) {
+        code = (code << 1) | (uint32_t)(w & 1);
+        w >>= 1;
+        uint32_t idx = code - t.first[l];
+        if (idx < t.count[l]) { *len = l; return t.symtab[t.offs[l] + idx]; }
+    }
+    return -1;
+}
+
+struct Unit {
+    int nbits;       // bits consumed, 0 = decode error
+    int outlen;      // decoded bytes produced
+    uint32_t packed; // packed symbol
+    int eob;
+};
+
+// One literal / EOB / match unit (DeflateBlockHuffman.decodeStream, :778-890).
+__device__ __forceinline__ Unit decode_unit(const DecTab& lit, const DecTab& dst, const uint8_t* in, uint64_t pos) {
+    Unit u;
+    u.nbits = 0; u.outlen = 0; u.packed = 0; u.eob = 0;
+    uint64_t w = peek_bits(in, pos);
+    int l;
+    int s = decode_sym(lit, w, &l);
+    if (s < 0 || s > 285) return u;
+    if (s < 256) { u.nbits = l; u.outlen = 1; u.packed = (uint32_t)s; return u; }
+    if (s == 256) { u.nbits = l; u.eob = 1; u.packed = 256; return u; }
+    int nb = l;
+    w >>= l;
+    int eb = c_len_ebits[s - 257];
+    int len = c_len_base[s - 257] + (int)(w & ((1u << eb) - 1));
+    w >>= eb; nb += eb;
+    int edge = (len == 258 && s == 284) ? 1 : 0;
+    int dl;
+    int ds = decode_sym(dst, w, &dl);
+    if (ds < 0 || ds > 29) return u;
+    w >>= dl; nb += dl;
+    int deb = c_dist_ebits[ds];
+    int dist = c_dist_base[ds] + (int)(w & ((1u << deb) - 1));
+    nb += deb;
+    u.nbits = nb; u.outlen = len;
+    u.packed = sym_pack_match(len, dist, edge, s);
+    return u;
+}
+
+__device__ inline void fixed_lens(uint8_t* L, uint8_t* D) {  // HuffmanTable.java:166-209 (286 / 30 entries)
+    for (int i = 0; i < 286; i++) L[i] = (i <= 143) ? 8 : (i <= 255) ? 9 : (i <= 279) ? 7 : 8;
+    for (int i = 0; i < 30; i++) D[i] = 5;
+}
+
+// DeflateBlockHuffman.initDynamicDecoder (:892-1010), run by one thread.  Returns bits consumed or 0.
+__device__ inline uint32_t parse_dynamic_header(const uint8_t* in, uint64_t pos, uint64_t total_bits, BlockRec& b,
+                                                DecTab& scratch) {
+    uint64_t p = pos;
+    if (p + 14 > total_bits) return 0;
+    uint64_t w = peek_bits(in, p);
+    int nL = (int)(w & 31) + 257, nD = (int)((w >> 5) & 31) + 1, ncl = (int)((w >> 10) & 15) + 4;
+    p += 14;
+    if (p + 3ull * ncl > total_bits) return 0;
+    for (int i = 0; i < 19; i++) b.hdr.CL[i] = 0;
+    for (int i = 0; i < ncl; i++) {
+        b.hdr.CL[c_codelen_order[i]] = (uint8_t)(peek_bits(in, p) & 7);
+        p += 3;
+    }
+    int hbits = 14 + 3 * ncl;
+    build_dectab(b.hdr.CL, 19, scratch);
+    // HLIT up to 288 is accepted by the reference parser (asserts only); the tables then have 287/288
+    // entries.  Our Tab holds 288.
+    uint8_t lens[MAX_LL + MAX_D];
+    int i = 0, np = 0;
+    const int combined = nL + nD;
+    while (i < combined) {
+        if (p >= total_bits) return 0;
+        w = peek_bits(in, p);
+        int l;
+        int s = decode_sym(scratch, w, &l);
+        if (s < 0) return 0;
+        p += l; hbits += l; w >>= l;
+        int run = 0, val;
+        if (s <= 15) { lens[i++] = (uint8_t)s; val = s; }
+        else if (s == 16) {
+            if (i < 1) return 0;
+            run = (int)(w & 3) + 3; p += 2; hbits += 2;
+            if (i + run > combined) return 0;
+            val = lens[i - 1];
+            for (int k = 0; k < run; k++) lens[i++] = (uint8_t)val;
+        } else if (s == 17) {
+            run = (int)(w & 7) + 3; p += 3; hbits += 3;
+            if (i + run > combined) return 0;
+            val = 0;
+            for (int k = 0; k < run; k++) lens[i++] = 0;
+        } else {
+            run = (int)(w & 127) + 11; p += 7; hbits += 7;
+            if (i + run > combined) return 0;
+            val = 0;
+            for (int k = 0; k < run; k++) lens[i++] = 0;
+        }
+        if (p > total_bits) return 0;
+        b.hdr.pairs[np++] = pair_pack(s, run, val);
+    }
+    b.hdr.np = (uint16_t)np;
+    b.hdr.ncl = (uint8_t)ncl;
+    b.hdr.bits = hbits;
+    b.tab.nL = (uint16_t)nL; b.tab.nD = (uint16_t)nD; b.tab.type = 2;
+    for (int k = 0; k < MAX_LL; k++) b.tab.L[k] = k < nL ? lens[k] : 0;
+    for (int k = 0; k < MAX_D; k++) b.tab.D[k] = k < nD ? lens[nL + k] : 0;
+    return (uint32_t)(p - pos);
+}
+
+// status codes shared with the host (mirror DEFT4CU_*)
+constexpr int ST_OK = 0, ST_PARSE = 1, ST_UNSUPPORTED = 3;
+
+// --------------------------------------------------------------------------------------------------
+// k_count: one CTA per stream.
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PARSE_NT, 1)
+k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, StreamInfo* __restrict__ infos,
+        BlockRec* __restrict__ blocks, ChunkRec* __restrict__ chunks) {
+    const int sid = blockIdx.x, t = threadIdx.x;
+    const StreamDesc sd = descs[sid];
+    const uint8_t* in = d_in + sd.in_off;
+    const uint64_t total_bits = sd.in_len * 8;
+
+    __shared__ DecTab s_lit, s_dst, s_fixlit, s_fixdst;
+    __shared__ BlockRec s_blk;
+    __shared__ uint32_t s_start[PARSE_NT], s_end[PARSE_NT], s_cnt[PARSE_NT], s_outb[PARSE_NT];
+    __shared__ uint8_t s_flag[PARSE_NT];
+    __shared__ uint32_t s_scan_cnt[PARSE_NT / 32], s_scan_out[PARSE_NT / 32];
+    __shared__ int s_status, s_type, s_final, s_stop;
+    __shared__ uint64_t s_pos;
+
+    if (t == 0) {
+        uint8_t L[MAX_LL], D[MAX_D];
+        fixed_lens(L, D);
+        build_dectab(L, 286, s_fixlit);
+        build_dectab(D, 30, s_fixdst);
+        s_status = ST_OK;
+        s_pos = 0;
+    }
+    __syncthreads();
+
+    uint64_t n_syms = 0, out_total = 0, n_chunks = 0;
+    uint32_t n_blocks = 0;
+    bool done = false;
+
+    while (!done) {
+        // ---- block header (thread 0) --------------------------------------------------------------
+        if (t == 0) {
+            uint64_t pos = s_pos;
+            s_blk.hdr_bit = pos;
+            s_blk.hdr.np = 0; s_blk.hdr.ncl = 0; s_blk.hdr.bits = 0;
+            s_blk.tab.nL = 0; s_blk.tab.nD = 0;
+            if (pos + 3 > total_bits) { s_status = ST_PARSE; }
+            else {
+                uint64_t w = peek_bits(in, pos);
+                s_final = (int)(w & 1);
+                int type = (int)((w >> 1) & 3);
+                s_type = type;
+                pos += 3;
+                if (type == 3) s_status = ST_PARSE;
+                else if (type == 0) {  // DeflateBlockUncompressed.parse (:23-36)
+                    pos = (pos + 7) & ~7ull;
+                    if (pos + 32 > total_bits) s_status = ST_PARSE;
+                    else {
+                        uint64_t v = peek_bits(in, pos);
+                        uint32_t len = (uint32_t)(v & 0xffff), nlen = (uint32_t)((v >> 16) & 0xffff);
+                        pos += 32;
+                        if (nlen != (~len & 0xffff)) s_status = ST_PARSE;
+                        // truncated stored data: the reference pads with 0xFF; we refuse
+                        else if (pos + 8ull * len > total_bits) s_status = ST_UNSUPPORTED;
+                        else {
+                            s_blk.data_bit = pos;
+                            s_blk.out_len = len;
+                            s_blk.n_sym = 0;
+                            s_blk.payload_bits = 0;
+                            s_blk.tab.type = 0;
+                            pos += 8ull * len;
+                            s_blk.end_bit = pos;
+                        }
+                    }
+                } else if (type == 1) {
+                    s_blk.tab.type = 1;
+                    s_blk.tab.nL = 286; s_blk.tab.nD = 30;
+                    fixed_lens(s_blk.tab.L, s_blk.tab.D);
+                    for (int k = 286; k < MAX_LL; k++) s_blk.tab.L[k] = 0;
+                    for (int k = 30; k < MAX_D; k++) s_blk.tab.D[k] = 0;
+                    s_blk.data_bit = pos;
+                } else {
+                    uint32_t used = parse_dynamic_header(in, pos, total_bits, s_blk, s_lit);
+                    if (used == 0) s_status = ST_PARSE;
+                    else {
+                        pos += used;
+                        s_blk.data_bit = pos;
+                        build_dectab(s_blk.tab.L, s_blk.tab.nL, s_lit);
+                        build_dectab(s_blk.tab.D, s_blk.tab.nD, s_dst);
+                    }
+                }
+            }
+            s_blk.type = (uint8_t)s_type;
+            s_blk.bfinal = (uint8_t)s_final;
+            s_pos = pos;
+        }
+        __syncthreads();
+        if (s_status != ST_OK) break;
+        const int type = s_type;
+        uint32_t blk_syms = 0, blk_out = 0, blk_chunks = 0;
+        const uint64_t chunk_base = n_chunks;
+
+        if (type != 0) {
+            const DecTab& lit = (type == 1) ? s_fixlit : s_lit;
+            const DecTab& dst = (type == 1) ? s_fixdst : s_dst;
+            const uint64_t data_bit = s_blk.data_bit;
+            uint64_t win = data_bit;  // true symbol boundary
+            int64_t payload = 0;
+            bool eob_seen = false;
+            while (!eob_seen) {
+                // ---- speculative decode of one window ----------------------------------------------
+                uint32_t start = (uint32_t)t * CHUNK_BITS;
+                const uint32_t limit = (uint32_t)(t + 1) * CHUNK_BITS;
+                bool need = true, changed;
+                uint32_t end = 0, cnt = 0, outb = 0;
+                int flag = 0;
+                do {
+                    if (need) {
+                        uint32_t p = start;
+                        cnt = 0; outb = 0; flag = 0;
+                        while (p < limit) {
+                            uint64_t abs = win + p;
+                            if (abs >= total_bits) { flag = 2; break; }
+                            Unit u = decode_unit(lit, dst, in, abs);
+                            if (u.nbits == 0 || abs + u.nbits > total_bits) { flag = 2; break; }
+                            p += u.nbits; cnt++; outb += u.outlen;
+                            if (u.eob) { flag = 1; break; }
+                        }
+                        end = p;
+                        s_end[t] = end; s_flag[t] = (uint8_t)flag;
+                    }
+                    __syncthreads();
+                    changed = false;
+                    need = false;
+                    if (t > 0 && s_flag[t - 1] == 0) {
+                        uint32_t pe = s_end[t - 1];
+                        if (pe != start) { start = pe; need = true; changed = true; }
+                    }
+                    changed = __syncthreads_or(changed);
+                } while (changed);
+                // ---- first stopping chunk on the valid chain ----------------------------------------
+                if (t == 0) s_stop = PARSE_NT;
+                __syncthreads();
+                if (flag != 0) atomicMin(&s_stop, t);
+                __syncthreads();
+                const int stop = s_stop;  // chunks 0..min(stop, NT-1) are valid
+                const bool valid = t <= stop;
+                if (stop < PARSE_NT && s_flag[stop] == 2) { if (t == 0) s_status = ST_PARSE; }
+                // ---- exclusive scans of symbol counts / decoded bytes over the valid chunks ----------
+                uint32_t c = valid ? cnt : 0, o = valid ? outb : 0;
+                uint32_t ci = c, oi = o;
+                const int lane = t & 31, wid = t >> 5;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t a = __shfl_up_sync(0xffffffffu, ci, d), b2 = __shfl_up_sync(0xffffffffu, oi, d);
+                    if (lane >= d) { ci += a; oi += b2; }
+                }
+                if (lane == 31) { s_scan_cnt[wid] = ci; s_scan_out[wid] = oi; }
+                __syncthreads();
+                if (wid == 0) {
+                    uint32_t a = s_scan_cnt[lane], b2 = s_scan_out[lane];
+                    uint32_t ai = a, bi = b2;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        uint32_t x = __shfl_up_sync(0xffffffffu, ai, d), y = __shfl_up_sync(0xffffffffu, bi, d);
+                        if (lane >= d) { ai += x; bi += y; }
+                    }
+                    s_scan_cnt[lane] = ai - a; s_scan_out[lane] = bi - b2;  // exclusive warp bases
+                    if (lane == 31) { s_cnt[0] = ai; s_outb[0] = bi; }      // window totals
+                }
+                __syncthreads();
+                const uint32_t cbase = s_scan_cnt[wid] + ci - c, obase = s_scan_out[wid] + oi - o;
+                const uint32_t wcnt = s_cnt[0], wout = s_outb[0];
+                if (valid) {
+                    uint64_t slot = n_chunks + (uint64_t)t;
+                    if (slot < sd.chunk_cap) {
+                        ChunkRec r;
+                        r.start_rel = (uint32_t)(win - data_bit) + start;
+                        r.sym_idx = blk_syms + cbase;
+                        r.out_off = blk_out + obase;
+                        r.n = cnt;
+                        chunks[sd.chunk_base + slot] = r;
+                    }
+                }
+                const int nvalid = (stop < PARSE_NT ? stop : PARSE_NT - 1) + 1;
+                // payload bits of this window = end of the last valid chunk
+                if (t == nvalid - 1) s_start[0] = end;
+                __syncthreads();
+                const uint32_t wend = s_start[0];
+                payload += wend;
+                win += wend;
+                n_chunks += nvalid; blk_chunks += nvalid;
+                blk_syms += wcnt; blk_out += wout;
+                if (stop < PARSE_NT) eob_seen = true;  // EOB (or error, handled by status)
+                if (win - data_bit > 0xFFFF0000ull || blk_syms > 0x7FFF0000u) { if (t == 0) s_status = ST_UNSUPPORTED; eob_seen = true; }
+                __syncthreads();
+                if (s_status != ST_OK) break;
+            }
+            if (s_status != ST_OK) break;
+            if (t == 0) {
+                s_blk.end_bit = win;
+                s_blk.n_sym = blk_syms;
+                s_blk.out_len = blk_out;
+                s_blk.payload_bits = payload;
+                s_pos = win;
+            }
+        }
+        // ---- record the block ------------------------------------------------------------------------
+        if (t == 0) {
+            s_blk.sym_base = n_syms;
+            s_blk.out_base = out_total;
+            s_blk.chunk_base = (uint32_t)chunk_base;
+            s_blk.n_chunks = blk_chunks;
+        }
+        __syncthreads();
+        if (n_blocks < sd.blk_cap) {
+            // cooperative copy of the record
+            const uint32_t* src = (const uint32_t*)&s_blk;
+            uint32_t* dstp = (uint32_t*)&blocks[sd.blk_base + n_blocks];
+            for (int k = t; k < (int)(sizeof(BlockRec) / 4); k += PARSE_NT) dstp[k] = src[k];
+        }
+        n_syms += (type != 0) ? s_blk.n_sym : 0;
+        out_total += s_blk.out_len;
+        n_blocks++;
+        done = s_final != 0;
+        if (out_total > 0xF0000000ull) { if (t == 0) s_status = ST_UNSUPPORTED; done = true; }
+        __syncthreads();
+    }
+    if (t == 0) {
+        StreamInfo si;
+        si.status = s_status;
+        si.n_blocks = n_blocks;
+        si.n_syms = n_syms;
+        si.out_len = out_total;
+        si.consumed = (s_pos + 7) >> 3;
+        si.n_chunks = n_chunks;
+        si.total_bits = s_pos;
+        infos[sid] = si;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// k_emit: one CTA per block.  Huffman blocks: thread per chunk re-decodes and writes symbols.
+// Stored blocks: copy bytes into `out` (DeflateBlockUncompressed.parse :23-36).
+// --------------------------------------------------------------------------------------------------
+struct EmitJob { uint32_t stream, block; };
+
+__global__ void __launch_bounds__(256)
+k_emit(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, const BlockRec* __restrict__ blocks,
+       const ChunkRec* __restrict__ chunks, const EmitJob* __restrict__ jobs, StreamInfo* __restrict__ infos,
+       uint32_t* __restrict__ sym, uint32_t* __restrict__ symout, uint8_t* __restrict__ out) {
+    const EmitJob job = jobs[blockIdx.x];
+    const StreamDesc sd = descs[job.stream];
+    const BlockRec& b = blocks[sd.blk_base + job.block];
+    const uint8_t* in = d_in + sd.in_off;
+    const int t = threadIdx.x;
+    if (b.type == 0) {
+        const uint8_t* src = in + (b.data_bit >> 3);
+        uint8_t* dst = out + sd.out_base + b.out_base;
+        for (uint32_t k = t; k < b.out_len; k += blockDim.x) dst[k] = src[k];
+        return;
+    }
+    __shared__ DecTab s_lit, s_dst;
+    if (t == 0) build_dectab(b.tab.L, b.tab.nL, s_lit);
+    if (t == 32) build_dectab(b.tab.D, b.tab.nD, s_dst);
+    __syncthreads();
+    const uint64_t symb = sd.sym_base + b.sym_base, outb = sd.out_base + b.out_base;
+    for (uint32_t c = t; c < b.n_chunks; c += blockDim.x) {
+        const ChunkRec r = chunks[sd.chunk_base + b.chunk_base + c];
+        uint64_t pos = b.data_bit + r.start_rel;
+        uint64_t si = symb + r.sym_idx;
+        uint32_t oo = (uint32_t)(outb + r.out_off);
+        for (uint32_t k = 0; k < r.n; k++) {
+            Unit u = decode_unit(s_lit, s_dst, in, pos);
+            pos += u.nbits;
+            sym[si + k] = u.packed;
+            symout[si + k] = oo;
+            // a match reaching before the start of its stream: the reference dereferences a null
+            // prevBlock (DeflateBlock.java:175-181); reported as a parse failure
+            if (sym_is_match(u.packed) && (uint64_t)oo - sd.out_base < (uint64_t)sym_dist(u.packed))
+                infos[job.stream].status = ST_PARSE;
+            oo += u.outlen;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// LZ77 resolution (replaces DeflateBlock.readSlice, DeflateBlock.java:147-222)
+//   k_lz_fill : per symbol, literal -> out byte + root pointer; match -> every byte points at
+//               (position - distance), folded into the non-overlapping source for overlapped copies.
+//   k_lz_jump : pointer doubling until every pointer is a root.
+//   k_lz_gather: out[i] = out[root(i)].
+// A match reaching before the start of its stream is a parse failure (the reference dereferences a
+// null prevBlock there).
+// --------------------------------------------------------------------------------------------------
+__global__ void k_lz_fill(const uint32_t* __restrict__ sym, const uint32_t* __restrict__ symout, uint64_t n_sym,
+                          uint8_t* __restrict__ out, uint32_t* __restrict__ ptr) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sym) return;
+    uint32_t s = sym[i];
+    uint32_t o = symout[i];
+    if (!sym_is_match(s)) {
+        if (s < 256) { out[o] = (uint8_t)s; ptr[o] = o; }
+        return;
+    }
+    const int len = sym_len(s), dist = sym_dist(s);
+    if (o < (uint32_t)dist) {  // only reachable in a stream already flagged by k_emit; keep pointers in bounds
+        for (int k = 0; k < len; k++) ptr[o + k] = o + k;
+        return;
+    }
+    const uint32_t src = o - dist;
+    for (int k = 0; k < len; k++) ptr[o + k] = src + (dist < len ? (uint32_t)(k % dist) : (uint32_t)k);
+}
+
+// stored blocks: their bytes were copied by k_emit and are roots
+__global__ void k_lz_root_stored(const StreamDesc* __restrict__ descs, const BlockRec* __restrict__ blocks,
+                                 const EmitJob* __restrict__ jobs, uint32_t njobs, uint32_t* __restrict__ ptr) {
+    if (blockIdx.x >= njobs) return;
+    const EmitJob job = jobs[blockIdx.x];
+    const StreamDesc sd = descs[job.stream];
+    const BlockRec& b = blocks[sd.blk_base + job.block];
+    if (b.type != 0) return;
+    const uint32_t o = (uint32_t)(sd.out_base + b.out_base);
+    for (uint32_t k = threadIdx.x; k < b.out_len; k += blockDim.x) ptr[o + k] = o + k;
+}
+
+// gather the per-stream BlockRec slots into one gap-free array in stream order (warp per record)
+__global__ void k_compact_blocks(const StreamDesc* __restrict__ descs, const BlockRec* __restrict__ blocks,
+                                 const EmitJob* __restrict__ jobs, uint64_t n, BlockRec* __restrict__ dst) {
+    uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const EmitJob job = jobs[w];
+    const uint32_t* s = (const uint32_t*)&blocks[descs[job.stream].blk_base + job.block];
+    uint32_t* d = (uint32_t*)&dst[w];
+    for (int k = lane; k < (int)(sizeof(BlockRec) / 4); k += 32) d[k] = s[k];
+}
+
+__global__ void k_lz_jump(uint32_t* __restrict__ ptr, uint64_t n, int* __restrict__ changed) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ch = false;
+    if (i < n) {
+        uint32_t p = ptr[i];
+        if (p != i) {
+            uint32_t pp = ptr[p];
+            if (pp != p) { ptr[i] = pp; ch = true; }
+        }
+    }
+    if (__syncthreads_or(ch) && threadIdx.x == 0) *changed = 1;
+}
+
+__global__ void k_lz_gather(uint8_t* __restrict__ out, const uint32_t* __restrict__ ptr, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = ptr[i];
+    if (p != i) out[i] = out[p];
+}
+
+}  // namespace d4
