@@ -61,6 +61,8 @@ SYMBOLS = {
     "deft4cu_device_batch_fetch": (C.c_int, [_P, C.POINTER(Result)]),
     "deft4cu_device_batch_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.c_uint32]),
     "deft4cu_device_batch_free": (None, [_P]),
+    "deft4cu_debug_trace_begin": (C.c_int, [C.c_uint32]),
+    "deft4cu_debug_trace_end": (C.c_int, [C.POINTER(C.c_int64), C.c_uint32, C.POINTER(C.c_uint32)]),
 }
 
 _lib = None

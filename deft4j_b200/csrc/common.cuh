@@ -16,6 +16,16 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// D4_HOST_TEST builds the single-thread building blocks (huff.cuh) as host code so that CPU-only tests
+// can pin the very source the kernels run against the oracle (tests/test_host_units.py).
+#ifdef D4_HOST_TEST
+#define D4_DEV inline
+#define D4_CONST static const
+#else
+#define D4_DEV __device__ inline
+#define D4_CONST __constant__
+#endif
+
 namespace d4 {
 
 // ---- packed symbol ------------------------------------------------------------------------------
@@ -36,15 +46,15 @@ __host__ __device__ inline uint32_t sym_pack_match(int len, int dist, int edge, 
 }
 
 // ---- RFC 1951 tables (Constants.java:63-128) ------------------------------------------------------
-__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59,
+D4_CONST uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59,
                                         67, 83, 99, 115, 131, 163, 195, 227, 258};
-__constant__ uint8_t c_len_ebits[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3,
+D4_CONST uint8_t c_len_ebits[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3,
                                         4, 4, 4, 4, 5, 5, 5, 5, 0};
-__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769,
+D4_CONST uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769,
                                          1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-__constant__ uint8_t c_dist_ebits[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8,
+D4_CONST uint8_t c_dist_ebits[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8,
                                          9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-__constant__ uint8_t c_codelen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+D4_CONST uint8_t c_codelen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 // Constants.distance2dist (Constants.java:9-13) in closed form.
 __host__ __device__ inline int dist_sym(int distance) {
@@ -67,11 +77,14 @@ __host__ __device__ inline int len_ebits_of(int lensym) {  // lensym 257..285
 constexpr int MAX_LL = 288, MAX_D = 32, MAX_CL = 19, MAX_PAIRS = 320;
 
 // header RLE pair (the reference stores these as LitLen(dist=run, litlen=sym), DeflateBlockHuffman
-// .java:997-999): sym 5 bits | run length 8 bits << 5 | repeated value 4 bits << 13
-__host__ __device__ inline uint16_t pair_pack(int sym, int run, int val) { return (uint16_t)(sym | (run << 5) | (val << 13)); }
+// .java:997-999) in 16 bits: sym 5 bits | run field 7 bits << 5 | repeated value 4 bits << 12.  The run
+// field holds the run length (0 = plain length, 3..10 for 16/17) except for sym 18, where it holds run - 11.
+__host__ __device__ inline uint16_t pair_pack(int sym, int run, int val) {
+    return (uint16_t)(sym | ((sym == 18 ? run - 11 : run) << 5) | (val << 12));
+}
 __host__ __device__ inline int pair_sym(uint16_t p) { return p & 31; }
-__host__ __device__ inline int pair_run(uint16_t p) { return (p >> 5) & 255; }
-__host__ __device__ inline int pair_val(uint16_t p) { return (p >> 13) & 15; }
+__host__ __device__ inline int pair_run(uint16_t p) { return (p & 31) == 18 ? ((p >> 5) & 127) + 11 : (p >> 5) & 127; }
+__host__ __device__ inline int pair_val(uint16_t p) { return (p >> 12) & 15; }
 
 // Code tables of a Huffman block: lengths only — every code the reference ever writes is the canonical
 // code of its length set (Huffman.java:35-64, HuffmanTree.java:164-192, HuffmanTable.java:166-209).
@@ -131,6 +144,7 @@ struct StreamInfo {                 // result of the count pass
 // ---- little bit reader ----------------------------------------------------------------------------
 // >= 57 valid bits starting at bit position `bitpos`; the input buffer is padded so the 16-byte
 // over-read is always in bounds.
+#ifndef D4_HOST_TEST
 __device__ __forceinline__ uint64_t peek_bits(const uint8_t* in, uint64_t bitpos) {
     const uint8_t* p = in + (bitpos >> 3);
     uintptr_t a = (uintptr_t)p;
@@ -140,6 +154,7 @@ __device__ __forceinline__ uint64_t peek_bits(const uint8_t* in, uint64_t bitpos
     uint64_t w = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
     return w >> (bitpos & 7);
 }
+#endif
 
 #define D4_CUDA_CHECK(x)                                                                      \
     do {                                                                                      \

@@ -539,6 +539,36 @@ int deft4cu_init(int device) {
 const char* deft4cu_last_error(void) { return g_err.c_str(); }
 const char* deft4cu_version(void) { return "deft4cu 0.1 (sm_100a)"; }
 
+// ---- parity-debug trace (engine.cuh g_trace) ---------------------------------------------------------------
+static long long* g_trace_dev = nullptr;
+static uint32_t g_trace_dev_cap = 0;
+int deft4cu_debug_trace_begin(uint32_t cap) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (g_trace_dev) { cudaFree(g_trace_dev); g_trace_dev = nullptr; }
+    D4_CUDA_CHECK(cudaMalloc((void**)&g_trace_dev, 16ull * cap));
+    g_trace_dev_cap = cap;
+    unsigned zero = 0;
+    D4_CUDA_CHECK(cudaMemcpyToSymbol(g_trace, &g_trace_dev, sizeof(g_trace_dev)));
+    D4_CUDA_CHECK(cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap)));
+    D4_CUDA_CHECK(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero)));
+    return DEFT4CU_OK;
+}
+int deft4cu_debug_trace_end(int64_t* dst, uint32_t cap, uint32_t* n) {
+    if (!g_trace_dev) { set_error("trace not armed"); return DEFT4CU_ERR_ARG; }
+    D4_CUDA_CHECK(cudaDeviceSynchronize());
+    unsigned cnt = 0;
+    D4_CUDA_CHECK(cudaMemcpyFromSymbol(&cnt, g_trace_n, sizeof(cnt)));
+    long long* null = nullptr;
+    D4_CUDA_CHECK(cudaMemcpyToSymbol(g_trace, &null, sizeof(null)));
+    if (n) *n = cnt;
+    uint32_t m = std::min(std::min(cnt, cap), g_trace_dev_cap);
+    if (m) D4_CUDA_CHECK(cudaMemcpy(dst, g_trace_dev, 16ull * m, cudaMemcpyDeviceToHost));
+    cudaFree(g_trace_dev);
+    g_trace_dev = nullptr;
+    return DEFT4CU_OK;
+}
+
 // ---- handle API ------------------------------------------------------------------------------------------
 int deft4cu_stream_parse_batch(const uint8_t* const* data, const uint64_t* len, uint32_t n, deft4cu_stream** handles,
                                int32_t* status, uint64_t* consumed) {

@@ -29,6 +29,16 @@
 namespace d4 {
 
 constexpr int ENG_NT = 256;
+
+// parity-debug instrumentation (deft4cu_debug_trace): when armed, every candidate the selection callback sees
+// is logged as (candidate index, size) and the header-strategy memo is bypassed so all 56 trials are logged
+__device__ long long* g_trace = nullptr;
+__device__ unsigned g_trace_cap = 0;
+__device__ unsigned g_trace_n = 0;
+__device__ __forceinline__ void trace_put(long long idx, long long sz) {
+    unsigned k = atomicAdd(&g_trace_n, 1u);
+    if (k < g_trace_cap) { g_trace[2 * k] = idx; g_trace[2 * k + 1] = sz; }
+}
 constexpr int NCAND = 16;
 constexpr int MEMO_H = 192;   // histogram -> recode result
 constexpr int MEMO_T = 192;   // Tab -> best header strategy
@@ -62,8 +72,8 @@ struct EngSmem {
     unsigned long long red;
     int redAny;
     int err;
-    TreeWs<290, 1024> tl;
-    TreeWs<32, 128> td;
+    TreeWs<290, 584> tl;
+    TreeWs<32, 68> td;
     // selection state
     long long bestSize;
     int bestStored;
@@ -112,6 +122,7 @@ struct Eng {
         bool better = sz < S->bestSize;
         __syncthreads();
         if (tid == 0) {
+            if (g_trace) trace_put(S->candIndex, sz);
             if (isRest && sz < S->restMin) S->restMin = sz;
             if (better) { S->bestSize = sz; S->bestStored = 0; S->bestIndex = S->candIndex; }
             S->candIndex++;
@@ -310,7 +321,7 @@ struct Eng {
             int nl = 286;
             while (nl > 0 && S->hist[nl - 1] == 0) nl--;
             cd.tab.nL = (uint16_t)nl;
-            if (huff_tree<290, 1024>(S->hist, nl, 15, cd.tab.L, S->tl)) S->err = ST_UNSUPPORTED;
+            if (huff_tree<290, 584>(S->hist, nl, 15, cd.tab.L, S->tl)) S->err = ST_UNSUPPORTED;
             for (int k = nl; k < MAX_LL; k++) cd.tab.L[k] = 0;
         }
         if (tid == 32) {
@@ -324,7 +335,7 @@ struct Eng {
             else if (nz <= 1) { cd.tab.nD = (uint16_t)nd; cd.tab.D[nd - 1] = 1; }  // handleOne
             else {
                 cd.tab.nD = (uint16_t)nd;
-                if (huff_tree<32, 128>(df, nd, 15, cd.tab.D, S->td)) S->err = ST_UNSUPPORTED;
+                if (huff_tree<32, 68>(df, nd, 15, cd.tab.D, S->td)) S->err = ST_UNSUPPORTED;
             }
         }
         __syncthreads();
@@ -418,6 +429,7 @@ struct Eng {
                 if (S->memoT_hash[k] == h) atomicMax(&s_hit[b], k);
             __syncthreads();
             int hit = s_hit[b];
+            if (g_trace) { hit = -1; __syncthreads(); if (tid == 0) s_hit[b] = -1; __syncthreads(); }
             if (hit >= 0) {
                 if (tid == 0) S->redAny = 0;
                 __syncthreads();
@@ -441,6 +453,10 @@ struct Eng {
                 S->trialBits[j] = h.bits;
             }
         }
+        __syncthreads();
+        if (g_trace && tid == 0)
+            for (int b = 0; b < nb; b++)
+                for (int k = 0; k < 56; k++) trace_put(S->candIndex + b * 56 + k, S->c[C_B1 + b].payload + S->trialBits[b * 56 + k]);
         __syncthreads();
         if (tid < nb && s_hit[tid] < 0) {
             int best = 0x7fffffff, arg = 0;
@@ -550,6 +566,7 @@ struct Eng {
     // Result: C_BEST (or stored when S->bestStored).
     __device__ void optimise_block(long long storedSize) {
         if (tid == 0) {
+            if (g_trace) trace_put(-1, cand_size(S->c[C_B]));
             S->bestSize = cand_size(S->c[C_B]);
             S->bestStored = 0;
             S->sizeI = S->bestSize;

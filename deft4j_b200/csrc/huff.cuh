@@ -26,10 +26,10 @@ struct TreeWs {
     uint32_t stack[MAXLEAF + 4];
 };
 
-// Returns 0 on success, 1 when the node pool is exhausted or the tree cannot be balanced (the reference
-// throws AssertionError there).  lens[0..n) receives the code lengths (0 for unused symbols).
+// Returns 0 on success, 1 when the tree cannot be balanced (the reference throws AssertionError there).
+// Node ids: [0, nleaf) leaves in insertion order, then internal nodes; MAXN >= 2 * (MAXLEAF + 2).  lens[0..n) receives the code lengths (0 for unused symbols).
 template <int MAXLEAF, int MAXN>
-__device__ int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, TreeWs<MAXLEAF, MAXN>& ws) {
+D4_DEV int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, TreeWs<MAXLEAF, MAXN>& ws) {
     int hs = 0;  // heap size
     auto W = [](unsigned long long k) { return k >> 16; };
     auto add = [&](unsigned long long x) {  // PriorityQueue.offer + siftUp
@@ -129,8 +129,7 @@ __device__ int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, 
                 int leafC = ws.first[i];
                 int parent3 = ws.parent[leafC];
                 int sideC = ws.side[leafC];
-                if (nn >= MAXN) return 1;
-                int in = nn++;
+                const int in = parent1;  // parent1 has just left the tree: its slot becomes the new internal node
                 ws.left[in] = (uint16_t)leafA; ws.parent[leafA] = (uint16_t)in; ws.side[leafA] = 0;
                 ws.right[in] = (uint16_t)leafC; ws.parent[leafC] = (uint16_t)in; ws.side[leafC] = 1;
                 if (sideC == 0) { ws.left[parent3] = (uint16_t)in; ws.side[in] = 0; }
@@ -148,28 +147,28 @@ __device__ int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, 
     return 0;
 }
 
-using TreeWsCL = TreeWs<21, 192>;
+using TreeWsCL = TreeWs<21, 46>;
 
 // ---- header model ---------------------------------------------------------------------------------
 // strategy flags: bit0 ohh, bit1 use8, bit2 use7, bit3 alt8, bit4 noRep, bit5 noZRep, bit6 noZRep2,
 // bit7 noRepZeros, bit8 prune (DeflateStream.java:184-198,277-316)
-__constant__ uint16_t c_trial_flags[56] = {
+D4_CONST uint16_t c_trial_flags[56] = {
     0x7, 0x3, 0x5, 0x0, 0x47, 0x43, 0x45, 0x40, 0x27, 0x23, 0x25, 0x20, 0x67, 0x63, 0x65, 0x60, 0x10, 0x50, 0x30,
     0x70, 0x107, 0x103, 0x105, 0x100, 0x147, 0x143, 0x145, 0x140, 0x127, 0x123, 0x125, 0x120, 0x167, 0x163, 0x165,
     0x160, 0x110, 0x150, 0x130, 0x170, 0xa7, 0xa3, 0xa5, 0xa0, 0xe7, 0xe3, 0xe5, 0xe0, 0x1a7, 0x1a3, 0x1a5, 0x1a0,
     0x1e7, 0x1e3, 0x1e5, 0x1e0};
 constexpr int FLAGS_DEFAULT = 0x7;  // rewriteHeader() defaults (DeflateBlockHuffman.java:480-482)
 
-__device__ __forceinline__ int pair_extra_bits(int sym) { return sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0; }
+D4_DEV int pair_extra_bits(int sym) { return sym == 16 ? 2 : sym == 17 ? 3 : sym == 18 ? 7 : 0; }
 
 // getRLEPairSize (:133-163)
-__device__ __forceinline__ int pair_size(uint16_t p, const uint8_t* CL) {
+D4_DEV int pair_size(uint16_t p, const uint8_t* CL) {
     int s = pair_sym(p);
     return CL[s] + (pair_run(p) > 0 ? pair_extra_bits(s) : 0);
 }
 
 // removeDynHeaderTrailingZeroLenCodelens (:335-364); returns bits removed
-__device__ inline int hdr_trim(Hdr& h) {
+D4_DEV int hdr_trim(Hdr& h) {
     int saved = 0;
     while (true) {
         int lastZero = -1, lastNonZero = h.ncl;
@@ -182,14 +181,14 @@ __device__ inline int hdr_trim(Hdr& h) {
 }
 
 // Huffman.ofRLEPacked (Huffman.java:117-134) on the pair list
-__device__ inline int hdr_build_code(Hdr& h, TreeWsCL& ws) {
+D4_DEV int hdr_build_code(Hdr& h, TreeWsCL& ws) {
     uint32_t freq[19];
     for (int i = 0; i < 19; i++) freq[i] = 0;
     for (int i = 0; i < h.np; i++) freq[pair_sym(h.pairs[i])]++;
-    return huff_tree<21, 192>(freq, 19, 7, h.CL, ws);
+    return huff_tree<21, 46>(freq, 19, 7, h.CL, ws);
 }
 
-__device__ inline int hdr_pairs_bits(const Hdr& h) {
+D4_DEV int hdr_pairs_bits(const Hdr& h) {
     int b = 0;
     for (int i = 0; i < h.np; i++) b += pair_size(h.pairs[i], h.CL);
     return b;
@@ -197,7 +196,7 @@ __device__ inline int hdr_pairs_bits(const Hdr& h) {
 
 // rewriteHeader (:484-577): pack (HuffmanTable.java:70-159) straight into pairs, build the header code,
 // size it, trim.
-__device__ inline int hdr_rewrite(const Tab& t, int flags, Hdr& h, TreeWsCL& ws) {
+D4_DEV int hdr_rewrite(const Tab& t, int flags, Hdr& h, TreeWsCL& ws) {
     const bool ohh = flags & 1, use8 = flags & 2, use7 = flags & 4, alt8 = flags & 8, noRep = flags & 16,
                noZRep = flags & 32, noZRep2 = flags & 64, noRepZeros = flags & 128;
     const int nL = t.nL, n = t.nL + t.nD;
@@ -251,7 +250,7 @@ __device__ inline int hdr_rewrite(const Tab& t, int flags, Hdr& h, TreeWsCL& ws)
 // replaceRLERunsWithLiteralsIfSmaller (:321-332) via replaceWithLiteralsIfSmaller (:222-296): a run is
 // replaced by `run` plain lengths when those cost less (prune: no more) than the run code; only when
 // the repeated value has a header code.  In-place expansion from the back.
-__device__ inline void hdr_replace_runs(Hdr& h, bool prune) {
+D4_DEV void hdr_replace_runs(Hdr& h, bool prune) {
     int newNp = 0, saved = 0;
     bool any = false;
     for (int i = 0; i < h.np; i++) {
@@ -291,24 +290,24 @@ __device__ inline void hdr_replace_runs(Hdr& h, bool prune) {
 
 // recodeHeader (:579-629): new header code from the existing pairs; numCodelenLens is NOT reset
 // (SURVEY.md H8), only trimmed further.
-__device__ inline int hdr_recode(Hdr& h, TreeWsCL& ws) {
+D4_DEV int hdr_recode(Hdr& h, TreeWsCL& ws) {
     if (hdr_build_code(h, ws)) return 1;
     hdr_trim(h);
     h.bits = 5 + 5 + 4 + h.ncl * 3 + hdr_pairs_bits(h);
     return 0;
 }
 // recodeHeaderToLessRLEMatches (:632-635)
-__device__ inline int hdr_recode_less(Hdr& h, TreeWsCL& ws) {
+D4_DEV int hdr_recode_less(Hdr& h, TreeWsCL& ws) {
     hdr_replace_runs(h, true);
     return hdr_recode(h, ws);
 }
 // optimiseHeader (:471-476)
-__device__ inline void hdr_optimise(Hdr& h) {
+D4_DEV void hdr_optimise(Hdr& h) {
     h.bits -= hdr_trim(h);
     hdr_replace_runs(h, false);
 }
 // optimiseBlockDynBlock (DeflateStream.java:184-198): one header strategy trial
-__device__ inline int hdr_trial(const Tab& t, int flags, Hdr& h, TreeWsCL& ws) {
+D4_DEV int hdr_trial(const Tab& t, int flags, Hdr& h, TreeWsCL& ws) {
     if (hdr_rewrite(t, flags & 0xFF, h, ws)) return 1;
     if (flags & 0x100) { if (hdr_recode_less(h, ws)) return 1; }
     hdr_optimise(h);

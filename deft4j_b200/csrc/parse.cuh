@@ -185,9 +185,12 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
     __shared__ uint64_t s_pos;
 
     if (t == 0) {
+        // the fixed litlen CODES are those of the 288-entry RFC table (HuffmanTable.java:183-186 skips two
+        // code values), although the reference's table object has 286 entries
         uint8_t L[MAX_LL], D[MAX_D];
         fixed_lens(L, D);
-        build_dectab(L, 286, s_fixlit);
+        L[286] = L[287] = 8;
+        build_dectab(L, 288, s_fixlit);
         build_dectab(D, 30, s_fixdst);
         s_status = ST_OK;
         s_pos = 0;
@@ -422,7 +425,16 @@ k_emit(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, c
         return;
     }
     __shared__ DecTab s_lit, s_dst;
-    if (t == 0) build_dectab(b.tab.L, b.tab.nL, s_lit);
+    if (t == 0) {
+        if (b.type == 1) {
+            uint8_t L[MAX_LL], D[MAX_D];
+            fixed_lens(L, D);
+            L[286] = L[287] = 8;
+            build_dectab(L, 288, s_lit);
+        } else {
+            build_dectab(b.tab.L, b.tab.nL, s_lit);
+        }
+    }
     if (t == 32) build_dectab(b.tab.D, b.tab.nD, s_dst);
     __syncthreads();
     const uint64_t symb = sd.sym_base + b.sym_base, outb = sd.out_base + b.out_base;

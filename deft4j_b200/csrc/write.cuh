@@ -90,7 +90,11 @@ k_write(const StreamState* __restrict__ streams, const uint32_t* __restrict__ bl
     for (int k = tid; k < MAX_LL; k += WR_NT) W.L[k] = b.cand.tab.L[k];
     if (tid < MAX_D) W.D[tid] = b.cand.tab.D[tid];
     __syncthreads();
-    if (tid == 0) build_codes(W.L, b.cand.tab.nL, W.codeL);
+    // FIXED: codes of the 288-entry RFC table (see parse.cuh); lengths of 286/287 are only used for codes
+    if (tid == 0) {
+        if (type == 1) { W.L[286] = 8; W.L[287] = 8; }
+        build_codes(W.L, type == 1 ? 288 : b.cand.tab.nL, W.codeL);
+    }
     if (tid == 32) build_codes(W.D, b.cand.tab.nD, W.codeD);
     if (tid == 64 && type == 2) build_codes(b.cand.hdr.CL, 19, W.codeCL);
     __syncthreads();

@@ -129,6 +129,15 @@ int  deft4cu_device_batch_fetch(deft4cu_device_batch* b, deft4cu_result* results
 int  deft4cu_device_batch_timings(const deft4cu_device_batch* b, float* ms, uint32_t n);
 void deft4cu_device_batch_free(deft4cu_device_batch* b);
 
+/* ------------------------------------------------------------------------------------------------
+ * Parity-debug instrumentation (tests and scripts only): while armed, the candidate enumerator logs every
+ * candidate the selection callback of DeflateStream.optimiseBlock (DeflateStream.java:349-368) compares, as
+ * {candidate index within the call, size in bits} pairs ({-1, incumbent size} opens each call), so a
+ * divergence from the oracle can be located.  Meaningful for one block at a time.
+ * ---------------------------------------------------------------------------------------------- */
+int  deft4cu_debug_trace_begin(uint32_t cap_pairs);
+int  deft4cu_debug_trace_end(int64_t* dst_pairs, uint32_t cap_pairs, uint32_t* n_pairs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,15 @@
 namespace {
 
 ora_stats g_stats;
+// candidate trace (ora_trace_begin): {index within the optimiseBlock call, size}; {-1, incumbent} opens a call
+int64_t* g_trace = nullptr;
+size_t g_trace_cap = 0, g_trace_n = 0;
+long g_trace_idx = 0;
+void tracePut(long idx, long sz) {
+    if (!g_trace) return;
+    if (g_trace_n < g_trace_cap) { g_trace[2 * g_trace_n] = idx; g_trace[2 * g_trace_n + 1] = sz; }
+    g_trace_n++;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Constants (deflate/Constants.java:9-128): the RFC 1951 tables.
@@ -1241,10 +1250,13 @@ BlockP optimiseBlock(const BlockP& toOptimise, long position) {  // :343-490
     g_stats.optimise_block_calls++;
     BlockP smallest = toOptimise;
     long smallestSize = getSizeBits(*toOptimise, position);
+    tracePut(-1, smallestSize);
+    g_trace_idx = 0;
     Callback callback = [&](const BlockP& cand) {
         g_stats.candidates++;
         if (!cand) { fprintf(stderr, "oracle: null candidate (reference would throw)\n"); abort(); }
         long newSize = getSizeBits(*cand, position);
+        tracePut(g_trace_idx++, newSize);
         if (newSize < smallestSize) { smallest = cand; smallestSize = newSize; }
     };
     BlockP optimised = optimiseBlockNormal(toOptimise);
@@ -1517,6 +1529,9 @@ int ora_optimise_stream(const uint8_t* data, size_t len, int merge, uint8_t** ou
 }
 void ora_free_buf(uint8_t* p) { free(p); }
 
+void ora_trace_begin(int64_t* buf, size_t cap_pairs) { g_trace = buf; g_trace_cap = cap_pairs; g_trace_n = 0; }
+size_t ora_trace_end(void) { g_trace = nullptr; return g_trace_n; }
+
 void ora_huffman_tree(const int32_t* freq, int n, int limit, int32_t* code_out, int32_t* len_out) {
     std::vector<int> f(freq, freq + n);
     TableP t = buildTree(f, limit);
@@ -1531,6 +1546,30 @@ int ora_pack_code_lengths(const int32_t* lit, int nlit, const int32_t* dist, int
          flags & 128);
     for (size_t i = 0; i < lengths.size() && (int)i < cap; i++) dst[i] = lengths[i];
     return (int)lengths.size();
+}
+// One header-strategy trial (DeflateStream.optimiseBlockDynBlock, :184-198) on a bare dynamic block that has
+// only its two code-length tables: rewriteHeader(flags) [+ recodeHeaderToLessRLEMatches] + optimiseHeader.
+// ops: bit8 of flags = prune.  After the trial, `post_ops` (0 none, 1 recodeHeader, 2 recodeHeaderToLessRLEMatches,
+// 3 optimiseHeader) is applied once more so those mutators can be pinned on a realistic header too.
+int64_t ora_header_trial(const int32_t* lit, int nlit, const int32_t* dist, int ndist, int flags, int post_op,
+                         int32_t* pairs_out, int32_t* np_out, int32_t* cl_out, int32_t* ncl_out) {
+    Stream st;
+    auto b = std::make_shared<Block>(&st, DYNAMIC, nullptr);
+    b->litlenDec = ofCodelens(std::vector<int>(lit, lit + nlit));
+    b->distDec = ofCodelens(std::vector<int>(dist, dist + ndist));
+    b->litlens = std::make_shared<std::vector<LitLen>>();
+    b->rlePairs = std::make_shared<std::vector<Pair>>();
+    BlockP o = optimiseBlockDynBlock(b, flags & 1, flags & 2, flags & 4, flags & 8, flags & 16, flags & 32, flags & 64,
+                                     flags & 256, flags & 128);
+    if (post_op == 1) recodeHeader(*o);
+    else if (post_op == 2) recodeHeaderToLessRLEMatches(*o);
+    else if (post_op == 3) optimiseHeader(*o);
+    int n = 0;
+    for (const Pair& p : *o->rlePairs) { pairs_out[2 * n] = p.dist; pairs_out[2 * n + 1] = p.sym; n++; }
+    *np_out = n;
+    for (int i = 0; i < 19; i++) cl_out[i] = o->codeLenDec->codeLen[i];
+    *ncl_out = o->numCodelenLens;
+    return o->dynamicHeaderSizeBits;
 }
 void ora_get_stats(ora_stats* o) { *o = g_stats; }
 void ora_reset_stats(void) { memset(&g_stats, 0, sizeof g_stats); }

@@ -69,6 +69,18 @@ void ora_huffman_tree(const int32_t* freq, int n, int limit, int32_t* code_out, 
 int  ora_pack_code_lengths(const int32_t* lit, int nlit, const int32_t* dist, int ndist, int flags,
                            int32_t* dst, int cap);
 
+/* One header-strategy trial (DeflateStream.optimiseBlockDynBlock, DeflateStream.java:184-198) on a bare dynamic
+ * block holding only the two code-length tables; flags as above plus bit8 = prune.  post_op applies one more
+ * mutator afterwards: 0 none, 1 recodeHeader, 2 recodeHeaderToLessRLEMatches, 3 optimiseHeader.
+ * Returns dynamicHeaderSizeBits; pairs_out = {run, sym} per RLE pair (cap 320), cl_out = 19 header code lengths. */
+int64_t ora_header_trial(const int32_t* lit, int nlit, const int32_t* dist, int ndist, int flags, int post_op,
+                         int32_t* pairs_out, int32_t* np_out, int32_t* cl_out, int32_t* ncl_out);
+
+/* candidate trace for locating divergences: while armed, every candidate the selection callback of
+ * optimiseBlock compares is logged as {index within the call, size}; {-1, incumbent size} opens a call. */
+void   ora_trace_begin(int64_t* buf_pairs, size_t cap_pairs);
+size_t ora_trace_end(void);
+
 /* counters for the last ora_optimise call (instrumentation for DESIGN.md sizing) */
 typedef struct ora_stats {
     uint64_t optimise_block_calls, candidates, header_rewrites, tree_builds_small, tree_builds_big,

@@ -1,0 +1,38 @@
+"""Per-kernel-family device time of one batch built from golden files (replicated R times)."""
+import ctypes as C, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle_lib import OracleDeflateStream
+from conftest import read_golden
+from deft4j_b200 import _native as N
+from deft4j_b200.container import getContainerForBytes
+
+raws = []
+class Capture(OracleDeflateStream):
+    def parse(self, src):
+        from deft4j_b200.container._io import ByteReader
+        data = src.remaining() if isinstance(src, ByteReader) else bytes(src)
+        ok = super().parse(src)
+        raws.append(data[:self.consumed])
+        return ok
+
+rep = int(sys.argv[1])
+merge = int(sys.argv[2])
+for nm in sys.argv[3:]:
+    data = read_golden(nm)
+    getContainerForBytes(data, nm, Capture).read(data)
+bufs = raws * rep
+L = N.lib()
+ptrs, lens = N.make_ptr_arrays(bufs)
+h = C.c_void_p()
+assert L.deft4cu_device_batch_create(ptrs, lens, len(bufs), C.byref(h)) == 0
+for it in range(2):
+    launches = C.c_uint64(0)
+    t0 = time.time()
+    rc = L.deft4cu_device_batch_run(h, merge, C.byref(launches), None)
+    dt = time.time() - t0
+    ms = (C.c_float * 8)()
+    L.deft4cu_device_batch_timings(h, ms, 8)
+    tot = sum(len(b) for b in bufs)
+    print("rc %d streams %d bytes %d wall %.3fs launches %d  %.3f MB/s  ms: count %.1f emit %.1f lz %.1f opt %.1f finish %.1f write %.1f sums %.1f" % (
+        rc, len(bufs), tot, dt, launches.value, tot / dt / 1e6, *list(ms)[:7]))

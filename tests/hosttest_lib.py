@@ -1,0 +1,52 @@
+"""ctypes binding of deft4j_b200/libdeft4cu_hosttest.so — huff.cuh compiled as host code (TEST INFRASTRUCTURE)."""
+import ctypes as C
+import os
+import subprocess
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "deft4j_b200", "libdeft4cu_hosttest.so")
+_SRC = os.path.join(_ROOT, "deft4j_b200", "csrc")
+_lib = None
+
+
+def build():
+    srcs = [os.path.join(_SRC, f) for f in ("hosttest.cu", "huff.cuh", "common.cuh")]
+    if (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs if os.path.exists(s)):
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        subprocess.check_call([nvcc, "-O2", "-std=c++17", "--shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
+                               "-o", _SO, os.path.join(_SRC, "hosttest.cu")], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.host_huff_tree.argtypes = [C.POINTER(C.c_uint32), C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+        L.host_header_trial.restype = C.c_longlong
+        L.host_header_trial.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int,
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        _lib = L
+    return _lib
+
+
+def huff_tree(freq, limit):
+    n = len(freq)
+    f = (C.c_uint32 * n)(*freq)
+    lens = (C.c_uint8 * n)()
+    rc = lib().host_huff_tree(f, n, limit, lens)
+    return rc, list(lens)
+
+
+def header_trial(lit, dist, flags, post_op=0):
+    a = (C.c_uint8 * len(lit))(*lit)
+    b = (C.c_uint8 * len(dist))(*dist)
+    pairs = (C.c_int32 * 700)()
+    np_, ncl = C.c_int32(0), C.c_int32(0)
+    cl = (C.c_int32 * 19)()
+    bits = lib().host_header_trial(a, len(lit), b, len(dist), flags, post_op, pairs, C.byref(np_), cl, C.byref(ncl))
+    return bits, [(pairs[2 * i], pairs[2 * i + 1]) for i in range(np_.value)], list(cl), ncl.value
+
+
+def trial_flags():
+    return [lib().host_trial_flags(k) for k in range(56)]

@@ -177,3 +177,18 @@ def stats():
     s = Stats()
     lib().ora_get_stats(C.byref(s))
     return {n: getattr(s, n) for n, _ in Stats._fields_}
+
+
+def header_trial(lit, dist, flags, post_op=0):
+    """optimiseBlockDynBlock on a bare dynamic block (see ora_header_trial)."""
+    L = lib()
+    L.ora_header_trial.restype = C.c_int64
+    L.ora_header_trial.argtypes = [C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    a = (C.c_int32 * len(lit))(*lit)
+    b = (C.c_int32 * len(dist))(*dist)
+    pairs = (C.c_int32 * 700)()
+    np_, ncl = C.c_int32(0), C.c_int32(0)
+    cl = (C.c_int32 * 19)()
+    bits = L.ora_header_trial(a, len(lit), b, len(dist), flags, post_op, pairs, C.byref(np_), cl, C.byref(ncl))
+    return bits, [(pairs[2 * i], pairs[2 * i + 1]) for i in range(np_.value)], list(cl), ncl.value
