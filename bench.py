@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — the `deft4j optimise -m NONE` hot path on B200 (BASELINE.json metric: input MB/s optimised).
+
+A step = one pass of the whole path (parse -> optimise -> write -> checksums) over one batch of synthetic input.
+
+  value  : whole-job MB/s of input deflate with the inputs already resident in HBM (deft4cu_device_batch_run)
+  e2e    : the same through the reference-facing batch entry of the C ABI (deft4cu_optimise_batch) with pinned HOST
+           buffers in and host buffers out, host<->device copies inside the timed region
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+
+Launch: `python bench.py --gpus N --steps K --warmup W` (N=1) or under torch.distributed.run with N ranks (one
+process per GPU; streams are sharded by rank, C2's single stream is replicated per rank: no data-path collective).
+`--impl reference` times the CPU restatement of the reference (oracle/, the reference itself is Java and this image
+has no JVM) with every host core on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+import zlib
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "input MB/s optimised (-m NONE)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--size-mib", type=float, default=float(os.environ.get("DEFT4CU_BENCH_MIB", "1024")),
+                    help="C2: size of the single raw deflate stream per GPU (BASELINE config: 1024)")
+    ap.add_argument("--count", type=int, default=0, help="C3/C4: streams per GPU (default 12500 / 1250)")
+    ap.add_argument("--merge", type=int, default=-1, help="mergeBlocks; default: 0 for C2 (see DESIGN.md), 1 otherwise")
+    ap.add_argument("--sample-seconds", type=float, default=20.0, help="CPU baseline budget")
+    return ap.parse_args()
+
+
+def workload_config(a):
+    merge = a.merge if a.merge >= 0 else (0 if a.workload == "c2" else 1)
+    if a.workload == "c2":
+        name = ("single %d MiB raw deflate stream per GPU, zlib level 6 dynamic blocks over synthetic Zipf text "
+                "(BASELINE configs[1]), --no-merge-blocks" % a.size_mib)
+    elif a.workload == "c3":
+        a.count = a.count or 12500
+        name = "%d synthetic 256x256 RGBA PNG IDAT streams per GPU (BASELINE configs[2]), merge blocks" % a.count
+    else:
+        a.count = a.count or 1250
+        name = "%d ZIP-entry deflate payloads per GPU mixing stored/fixed/dynamic (BASELINE configs[3]), merge blocks" % a.count
+    return name, merge
+
+
+def make_streams(a, rank):
+    import workloads as W
+    if a.workload == "c2":
+        return [W.c2_stream(int(a.size_mib * (1 << 20)), seed=0xDEF7 + rank)]
+    if a.workload == "c3":
+        return W.c3_streams(a.count, first=rank * a.count)
+    return W.c4_streams(a.count, seed=4 + rank)
+
+
+# ---- CPU baseline: the oracle on every host core, one process per stream -------------------------------------------
+def _oracle_job(args):
+    raw, merge = args
+    import oracle_lib
+    s = oracle_lib.OracleDeflateStream()
+    assert s.parse(raw)
+    t0 = time.perf_counter()
+    s.optimise(bool(merge))
+    s.asBytes()
+    return time.perf_counter() - t0
+
+
+def cpu_sample_streams(a, cores, per_stream_seconds):
+    """A bounded sample of the workload: `cores` independent streams of the same kind, each sized for about
+    per_stream_seconds of single-thread oracle time (the oracle runs ~45 KB/s of C2 input per core)."""
+    import workloads as W
+    if a.workload == "c2":
+        text_bytes = int(45e3 * 2.4 * per_stream_seconds)
+        out = []
+        for k in range(cores):
+            co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
+            out.append(co.compress(W.c2_text(text_bytes, seed=0xBA5E + k)) + co.flush())
+        return out, "%d independent C2-style streams of %d KiB text each (one per core)" % (cores, text_bytes >> 10)
+    if a.workload == "c3":
+        n = max(cores, int(cores * per_stream_seconds / 1.5))
+        return W.c3_streams(n, first=5_000_000), "%d C3 PNG IDAT streams" % n
+    n = max(cores, int(cores * per_stream_seconds / 0.8))
+    return W.c4_streams(n, seed=99), "%d C4 entry payloads" % n
+
+
+def run_cpu_baseline(a, merge, budget_s):
+    import oracle_lib
+    oracle_lib.build()
+    cores = os.cpu_count() or 1
+    streams, what = cpu_sample_streams(a, cores, budget_s)
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_oracle_job, [(s, merge) for s in streams], chunksize=1)
+    dt = time.perf_counter() - t0
+    total = sum(len(s) for s in streams)
+    return {"value": total / dt / 1e6, "unit": "MB/s", "cores": cores, "kind": "port",
+            "sample": "%s, %.2f MB of input deflate in %.1f s; the reference is Java (no JVM in this image), so this is "
+                      "the C++ restatement (oracle/), which is faster than the JVM original" % (what, total / 1e6, dt)}
+
+
+# ---- clocks -------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- the two arms ----------------------------------------------------------------------------------------------------
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name, merge = workload_config(a)
+    # K+W bounded samples; each is the whole CPU budget divided over the steps
+    per = max(2.0, a.sample_seconds / max(1, a.steps))
+    vals = []
+    base = None
+    for i in range(a.warmup + a.steps):
+        if i < a.warmup and i > 0:
+            continue  # one warm-up sample is enough to page the library in
+        base = run_cpu_baseline(a, merge, per)
+        if i >= a.warmup:
+            vals.append(base["value"])
+    v = sum(vals) / len(vals)
+    base["value"] = v
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "MB/s", "n_gpus": a.gpus, "steps": a.steps,
+                      "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "u8", "data": "synthetic", "config": {"workload": name, "merge_blocks": bool(merge)},
+                      "cpu_baseline": base,
+                      "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    os.environ["DEFT4CU_DEVICE"] = str(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from deft4j_b200 import _native as N
+    L = N.lib()
+    name, merge = workload_config(a)
+    t_gen = time.time()
+    streams = make_streams(a, rank)
+    t_gen = time.time() - t_gen
+    in_bytes = sum(len(s) for s in streams)
+    n = len(streams)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.item()
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------------------------
+    ptrs, lens = N.make_ptr_arrays(streams)
+    h = C.c_void_p()
+    rc = L.deft4cu_device_batch_create(ptrs, lens, n, C.byref(h))
+    assert rc == 0, N.last_error()
+    stream = torch.cuda.Stream()
+    launches = C.c_uint64(0)
+    fam = [0.0] * 8
+
+    def step():
+        rc = L.deft4cu_device_batch_run(h, merge, C.byref(launches), C.c_void_p(stream.cuda_stream))
+        assert rc == 0, N.last_error()
+
+    with torch.cuda.stream(stream):
+        for _ in range(a.warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        total_launches = 0
+        for _ in range(a.steps):
+            step()
+            total_launches += launches.value
+            ms = (C.c_float * 8)()
+            L.deft4cu_device_batch_timings(h, ms, 8)
+            fam = [x + y for x, y in zip(fam, ms)]
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    res = (N.Result * n)()
+    assert L.deft4cu_device_batch_fetch(h, res) == 0
+    out_bytes = sum(r.out_len for r in res)
+    unc_bytes = sum(r.uncompressed_len for r in res)
+    saved_bits = sum(r.saved_bits for r in res)
+    assert all(r.status == 0 for r in res)
+    L.deft4cu_free_results(res, n)
+    L.deft4cu_device_batch_free(h)
+    total_in = sum_over_ranks(in_bytes)
+    value = total_in * a.steps / (dev_ms / 1e3) / 1e6
+
+    # ---- e2e: pinned host buffers through the batch entry of the C ABI ---------------------------------------------
+    pinned = [torch.frombuffer(bytearray(s), dtype=torch.uint8).pin_memory() for s in streams]
+    pp = (C.c_char_p * n)(*[C.cast(t.data_ptr(), C.c_char_p) for t in pinned])
+    e2e_res = (N.Result * n)()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(a.steps):
+        rc = L.deft4cu_optimise_batch(pp, lens, n, merge, e2e_res)
+        assert rc == 0, N.last_error()
+        d2h = sum(r.out_len for r in e2e_res) + C.sizeof(N.Result) * n
+        L.deft4cu_free_results(e2e_res, n)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    if world > 1:
+        dist.barrier()
+    e2e_value = total_in * a.steps / e2e_s / 1e6
+
+    # ---- roofline of the dominant kernel (k_opt_blocks, the candidate enumerator) ------------------------------------
+    peak, peak_src = peaks()
+    algo_bytes = in_bytes + out_bytes + 2 * unc_bytes          # A = C_in + C_out + 2 U per pass
+    opt_ms = fam[3] / a.steps
+    achieved = algo_bytes / (opt_ms / 1e3) / 1e9 if opt_ms > 0 else 0.0
+    names = ["parse_count", "emit", "lz77", "optimise", "finish_merge", "write", "checksums"]
+    roofline = {"bound": "hbm", "kernel": "k_opt_blocks", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": opt_ms,
+                "family_ms_per_step": {k: v / a.steps for k, v in zip(names, fam)}}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            roofline["traffic_note"] = json.load(f)
+    except Exception:
+        pass
+
+    if rank == 0:
+        base = run_cpu_baseline(a, merge, a.sample_seconds) if world == 1 else None
+        line = {"metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": name, "merge_blocks": bool(merge), "streams_per_gpu": n,
+                           "input_bytes_per_gpu": in_bytes, "uncompressed_bytes_per_gpu": unc_bytes,
+                           "saved_bits_per_gpu": saved_bits, "l2": "inputs larger than L2" if in_bytes > (126 << 20) else
+                           "inputs smaller than L2; every step re-parses from HBM-resident input after the previous step's "
+                           "multi-GB intermediates passed through L2",
+                           "datagen_s": round(t_gen, 1)},
+                "clocks": clocks, "gpu_launches": total_launches,
+                "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h},
+                "roofline": roofline}
+        if base:
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

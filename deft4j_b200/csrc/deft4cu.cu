@@ -135,8 +135,8 @@ k_checksums(const uint8_t* __restrict__ out, const uint64_t* __restrict__ off, c
 class Batch {
    public:
     uint32_t n = 0;
-    cudaStream_t cs = nullptr;
-    bool own_stream = false;
+    cudaStream_t cs = nullptr;      // stream every kernel and copy of this batch is issued on
+    cudaStream_t own_cs = nullptr;  // created by upload(); cs may later be redirected to a caller's stream
     uint64_t launches = 0;
     float ms[8] = {0};
 
@@ -176,7 +176,7 @@ class Batch {
     bool have_sums = false;
     bool parsed = false;
 
-    ~Batch() { release_all(); if (own_stream && cs) cudaStreamDestroy(cs); }
+    ~Batch() { release_all(); if (own_cs) cudaStreamDestroy(own_cs); }
 
     void release_model() {
         dfree(d_descs, cs); dfree(d_infos, cs); dfree(d_blocks, cs); dfree(d_chunks, cs);
@@ -193,7 +193,7 @@ class Batch {
 
     int upload(const uint8_t* const* in, const uint64_t* len, uint32_t count) {
         n = count;
-        if (!cs) { D4_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking)); own_stream = true; }
+        if (!own_cs) { D4_CUDA_CHECK(cudaStreamCreateWithFlags(&own_cs, cudaStreamNonBlocking)); cs = own_cs; }
         in_len.assign(len, len + n);
         in_off.resize(n);
         uint64_t off = 0;
@@ -832,7 +832,8 @@ int deft4cu_device_batch_create(const uint8_t* const* in, const uint64_t* in_len
 }
 int deft4cu_device_batch_run(deft4cu_device_batch* db, uint32_t flags, uint64_t* launches, void* cuda_stream) {
     Batch& b = *db->batch;
-    (void)cuda_stream;
+    // run on the caller's stream when one is given (bench.py brackets the steps with events on that stream)
+    b.cs = cuda_stream ? (cudaStream_t)cuda_stream : b.own_cs;
     b.launches = 0;
     int rc = b.parse();
     if (rc) return rc;

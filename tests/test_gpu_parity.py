@@ -1,0 +1,253 @@
+"""Parity tests proper (run on the B200): the CUDA path, called through the C ABI (ctypes -> libdeft4cu.so),
+against the CPU oracle and the reference's committed golden files.  Integer/byte work: the bar is bit-exact.
+"""
+import io
+import zlib
+
+import pytest
+
+import workloads as W
+from conftest import GOLDEN_PAIRS, UNPAIRED_INPUTS, read_golden
+
+pytestmark = pytest.mark.gpu
+
+INFO_FIELDS = ("type", "size_bits", "position", "uncompressed_len", "n_symbols", "n_rle_pairs", "num_litlen_lens",
+               "num_dist_lens", "num_codelen_lens", "litlen_size_bits", "header_size_bits")
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import deft4j_b200
+    from deft4j_b200 import _native
+    _native.lib()  # raises when the CUDA library or a device is missing: no fallback
+    return deft4j_b200
+
+
+def assert_same_model(g, o, symbols=True):
+    assert g.blockCount() == o.blockCount()
+    for i in range(o.blockCount()):
+        a, b = g.blockInfo(i), o.blockInfo(i)
+        for f in INFO_FIELDS:
+            if f in ("num_litlen_lens", "num_dist_lens", "num_codelen_lens") and b.type != 2:
+                continue
+            assert getattr(a, f) == getattr(b, f), (i, f, getattr(a, f), getattr(b, f))
+        if a.type != 0 and symbols:
+            assert g.blockSymbols(i) == o.blockSymbols(i), i
+            if a.type == 2:
+                for w in (0, 1, 2):
+                    assert g.blockCodelens(i, w) == o.blockCodelens(i, w), (i, w)
+                assert g.blockRlePairs(i) == o.blockRlePairs(i), i
+
+
+def compare_stream(gpu, oracle, raw, merge, check_model=True):
+    g = gpu.DeflateStream()
+    o = oracle.OracleDeflateStream()
+    okg, oko = g.parse(raw + b"TRAILER"), o.parse(raw + b"TRAILER")
+    assert okg == oko
+    if not oko:
+        return None
+    assert g.consumed == o.consumed
+    assert g.getSizeBits() == o.getSizeBits()
+    data = o.getUncompressedData()
+    assert g.getUncompressedData() == data
+    assert g.getChecksums() == (zlib.crc32(data) & 0xffffffff, zlib.adler32(data) & 0xffffffff, len(data))
+    if check_model:
+        assert_same_model(g, o)
+    sg, so = g.optimise(merge), o.optimise(merge)
+    assert sg == so
+    out = g.asBytes()
+    assert out == o.asBytes()
+    assert g.getSizeBits() == o.getSizeBits()
+    if check_model:
+        assert_same_model(g, o)
+    assert zlib.decompress(out, -15) == data
+    return sg
+
+
+# ---- C1: the reference's own fixtures --------------------------------------------------------------------------
+@pytest.mark.parametrize("inp,gold,merge", GOLDEN_PAIRS, ids=[p[0] for p in GOLDEN_PAIRS])
+def test_reference_golden_pairs(gpu, inp, gold, merge):
+    """`deft4j optimise -m NONE` on the repo's fixtures with runTestOpt.sh's flags: container bytes and the
+    saved-bits log lines identical to the reference's committed outputs."""
+    from deft4j_b200.container import getContainerForBytes
+    data = read_golden(inp)
+    cont = getContainerForBytes(data, inp, gpu.DeflateStream)
+    assert cont.read(data)
+    log = io.StringIO()
+    cont.optimise(merge, log)
+    assert cont.write() == read_golden(gold)
+    ref_log = [l for l in read_golden(gold + ".txt").decode().splitlines() if "bits saved" in l]
+    assert log.getvalue().strip().splitlines() == ref_log
+
+
+@pytest.mark.parametrize("inp", [p[0] for p in GOLDEN_PAIRS] + UNPAIRED_INPUTS)
+def test_parse_model_matches_oracle(gpu, oracle, inp):
+    """Decode parity on every fixture: block list, per-symbol LitLen records, code tables, header RLE pairs,
+    bit sizes, decoded bytes, CRC-32/Adler-32 (computed on the device)."""
+    from deft4j_b200.container import getContainerForBytes
+    data = read_golden(inp)
+    cg = getContainerForBytes(data, inp, gpu.DeflateStream)
+    co = getContainerForBytes(data, inp, oracle.OracleDeflateStream)
+    assert cg.read(data) and co.read(data)
+    assert len(cg.getDeflateStreams()) == len(co.getDeflateStreams())
+    for g, o in zip(cg.getDeflateStreams(), co.getDeflateStreams()):
+        assert_same_model(g, o)
+        d = o.getUncompressedData()
+        assert g.getUncompressedData() == d
+        assert g.getChecksums() == (zlib.crc32(d) & 0xffffffff, zlib.adler32(d) & 0xffffffff, len(d))
+
+
+@pytest.mark.parametrize("inp", ["ban.txt.gz", "lz.txt.gz", "deflate-store.txt.gz", "deflate-fixed.txt.zz",
+                                 "deflate-dynamic.txt.gz", "asyoulik/asyoulik-zopfli-extopt.txt.gz"])
+def test_unpaired_fixtures_match_oracle(gpu, oracle, inp):
+    from deft4j_b200.container import getContainerForBytes
+    data = read_golden(inp)
+    cg = getContainerForBytes(data, inp, gpu.DeflateStream)
+    co = getContainerForBytes(data, inp, oracle.OracleDeflateStream)
+    assert cg.read(data) and co.read(data)
+    assert cg.optimise(True, None) == co.optimise(True, None)
+    assert cg.write() == co.write()
+
+
+# ---- C2..C5 at sizes the oracle finishes in seconds ---------------------------------------------------------------
+def _deflate(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, wbits=-15, memlevel=8):
+    co = zlib.compressobj(level, zlib.DEFLATED, wbits, memlevel, strategy)
+    return co.compress(data) + co.flush()
+
+
+@pytest.mark.parametrize("merge", [False, True])
+def test_c2_text_stream(gpu, oracle, merge):
+    raw = _deflate(W.c2_text(200_000))
+    assert compare_stream(gpu, oracle, raw, merge) > 0
+
+
+def test_c3_png_idat_streams(gpu, oracle):
+    for raw in W.c3_streams(3):
+        compare_stream(gpu, oracle, raw, True, check_model=False)
+
+
+def test_c4_entry_mix(gpu, oracle):
+    for raw in W.c4_streams(12, seed=44):
+        compare_stream(gpu, oracle, raw, True, check_model=False)
+
+
+def test_c5_adversarial(gpu, oracle):
+    streams = [s for s in W.c5_streams() if len(s) < 200_000]
+    assert len(streams) >= 10
+    for raw in streams:
+        compare_stream(gpu, oracle, raw, True, check_model=False)
+
+
+@pytest.mark.parametrize("name", sorted(W.handmade_streams()))
+@pytest.mark.parametrize("merge", [False, True])
+def test_handmade_shapes(gpu, oracle, name, merge):
+    """distance 32768 / length 258, the 284+31 spelling of 258 (H9), empty blocks mid-stream (H6), stored blocks
+    around 65535 (H5/H12), lone EOB, empty stored block."""
+    compare_stream(gpu, oracle, W.handmade_streams()[name], merge)
+
+
+@pytest.mark.parametrize("level,strategy", [(0, 0), (1, 0), (9, 0), (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)])
+def test_zlib_flavours(gpu, oracle, level, strategy):
+    compare_stream(gpu, oracle, _deflate(W.c2_text(70_000, seed=level * 10 + strategy + 1), level, strategy), True,
+                   check_model=False)
+
+
+def test_sync_flush_empty_stored_blocks(gpu, oracle):
+    """Z_SYNC_FLUSH / Z_FULL_FLUSH leave empty stored blocks mid-stream: the reference's loop stops at the first one
+    it removes."""
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    t = W.c2_text(30_000, seed=9)
+    raw = co.compress(t[:10_000]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(t[10_000:20_000]) + \
+        co.flush(zlib.Z_FULL_FLUSH) + co.compress(t[20_000:]) + co.flush()
+    for merge in (False, True):
+        compare_stream(gpu, oracle, raw, merge)
+
+
+# ---- parse failures and edge inputs --------------------------------------------------------------------------------
+@pytest.mark.parametrize("raw", [b"", b"\x07", b"\x01\x05\x00\x00\x00", bytes([0x03, 0x02, 0x00]) + b"\0" * 4,
+                                 b"\x05", b"\xff" * 40], ids=["empty", "btype3", "len_nlen", "dist_before_start",
+                                                             "truncated_dynamic", "garbage"])
+def test_parse_failures(gpu, oracle, raw):
+    g, o = gpu.DeflateStream(), oracle.OracleDeflateStream()
+    assert o.parse(raw) is False
+    assert g.parse(raw) is False
+
+
+def test_truncated_stream_fails(gpu, oracle):
+    raw = _deflate(W.c2_text(20_000))
+    for cut in (len(raw) // 2, len(raw) - 1, 5):
+        g, o = gpu.DeflateStream(), oracle.OracleDeflateStream()
+        assert o.parse(raw[:cut]) is False
+        assert g.parse(raw[:cut]) is False
+
+
+# ---- the entry points of include/deft4cu.h -----------------------------------------------------------------------
+def test_batch_entry_matches_handles(gpu, oracle):
+    streams = W.c4_streams(9, seed=7) + [b"\x07", W.handmade_streams()["edge284"]]
+    res = gpu.optimise_batch(streams, True)
+    for raw, r in zip(streams, res):
+        o = oracle.OracleDeflateStream()
+        if not o.parse(raw):
+            assert r["status"] == 1
+            continue
+        assert r["status"] == 0 and r["consumed"] == o.consumed
+        before = o.getSizeBits()
+        assert r["size_bits_in"] == before
+        assert r["saved_bits"] == o.optimise(True)
+        assert r["out"] == o.asBytes()
+        assert r["size_bits_out"] == o.getSizeBits()
+        d = o.getUncompressedData()
+        assert (r["uncompressed_len"], r["crc32"], r["adler32"]) == (len(d), zlib.crc32(d) & 0xffffffff, zlib.adler32(d) & 0xffffffff)
+
+
+def test_facade_identity_semantics(gpu):
+    """Deft.optimiseDeflateStream returns the SAME array when nothing is saved or the stream does not parse (Deft.java:25-33)."""
+    already = gpu.Deft.optimiseDeflateStream(_deflate(W.c2_text(30_000)), True)
+    assert gpu.Deft.optimiseDeflateStream(already, True) is already
+    junk = b"\x07junk"
+    assert gpu.Deft.optimiseDeflateStream(junk, True) is junk
+    raw = _deflate(W.c2_text(30_000))
+    out = gpu.Deft.optimiseDeflateStream(raw, True)
+    assert out is not raw and len(out) <= len(raw) and zlib.decompress(out, -15) == zlib.decompress(raw, -15)
+    assert gpu.Deft.getSizeBitsFallback(junk) == len(junk) * 8
+    assert len(raw) * 8 - 8 < gpu.Deft.getSizeBitsFallback(raw) <= len(raw) * 8
+
+
+def test_parse_batch_and_partial_optimise(gpu, oracle):
+    streams = W.c3_streams(4, first=100)
+    hs = gpu.DeflateStream.parse_batch(streams)
+    assert all(h is not None for h in hs)
+    saved = gpu.DeflateStream.optimise_batch(hs[1:3], True)
+    for k, raw in enumerate(streams):
+        o = oracle.OracleDeflateStream()
+        assert o.parse(raw)
+        if k in (1, 2):
+            assert o.optimise(True) == saved[k - 1]
+        assert hs[k].asBytes() == o.asBytes()
+
+
+# ---- full-size properties (no oracle: size-independent invariants) ----------------------------------------------------
+def test_c2_large_stream_properties(gpu):
+    """16 MiB single stream (about 650 dynamic blocks), mergeBlocks=false like the benchmark: the rewritten stream
+    inflates to the same bytes, is no larger, and the device checksums match zlib's."""
+    raw = W.c2_stream(16 << 20)
+    data = zlib.decompress(raw, -15)
+    r = gpu.optimise_batch([raw], False)[0]
+    assert r["status"] == 0 and r["consumed"] == len(raw)
+    assert zlib.decompress(r["out"], -15) == data
+    assert r["size_bits_out"] == r["size_bits_in"] - r["saved_bits"]
+    assert 0 < r["saved_bits"] and len(r["out"]) < len(raw)
+    assert (r["uncompressed_len"], r["crc32"], r["adler32"]) == (len(data), zlib.crc32(data) & 0xffffffff, zlib.adler32(data) & 0xffffffff)
+    # a second pass over the rewritten stream never grows it and still round-trips (on the samples the oracle
+    # can finish it saves exactly 0: every block already sits at the enumerator's fix point)
+    r2 = gpu.optimise_batch([r["out"]], False)[0]
+    assert r2["saved_bits"] >= 0 and len(r2["out"]) <= len(r["out"]) and zlib.decompress(r2["out"], -15) == data
+
+
+def test_c3_batch_properties(gpu):
+    streams = W.c3_streams(300, first=1000)
+    res = gpu.optimise_batch(streams, True)
+    for raw, r in zip(streams, res):
+        assert r["status"] == 0
+        assert zlib.decompress(r["out"], -15) == zlib.decompress(raw, -15)
+        assert len(r["out"]) <= len(raw)

@@ -1,0 +1,229 @@
+"""Synthetic workloads of BASELINE.json's configs, shared by bench.py and the tests.
+
+Everything is generated from fixed seeds with numpy + the system zlib (the compressor that *produces* the
+input streams is not part of the measured path).
+
+  C2  single raw deflate stream, zlib level 6 (dynamic blocks) over Zipf-distributed synthetic text
+  C3  batch of 256x256 RGBA PNG IDAT streams (zlib level 6 over adaptively filtered synthetic images)
+  C4  stream mix of stored / fixed / dynamic entries (the payloads of the ZIP config)
+  C5  adversarial streams: len-258 / dist-1 and dist-32768 matches, RLE-heavy headers
+"""
+import zlib
+
+import numpy as np
+
+VOCAB = 20000
+
+
+def _vocab(seed=0xDEF7):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(2, 10, VOCAB)
+    table = rng.integers(97, 123, (VOCAB, 10), dtype=np.uint8)
+    table[np.arange(VOCAB), lens] = 32  # the separating space
+    p = 1.0 / np.arange(1, VOCAB + 1)
+    return table, (lens + 1).astype(np.int64), p / p.sum(), rng
+
+
+def text_chunks(seed=0xDEF7, words_per_chunk=1 << 18):
+    """Endless generator of text chunks (bytes): 20 000-word vocabulary, Zipf(1.0) draws, single spaces."""
+    table, wl, p, rng = _vocab(seed)
+    cdf = np.cumsum(p)
+    while True:
+        idx = np.searchsorted(cdf, rng.random(words_per_chunk)).clip(0, VOCAB - 1)
+        l = wl[idx]
+        ends = np.cumsum(l)
+        total = int(ends[-1])
+        starts = ends - l
+        rows = np.repeat(idx, l)
+        cols = np.arange(total, dtype=np.int64) - np.repeat(starts, l)
+        yield table[rows, cols].tobytes()
+
+
+def c2_stream(target_bytes, seed=0xDEF7):
+    """ONE raw deflate stream (zlib.compressobj(6, DEFLATED, -15, 8)) of at least target_bytes."""
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
+    parts, n = [], 0
+    # ~2.6 bytes of text per compressed byte; feed text until the compressor has emitted enough
+    for chunk in text_chunks(seed):
+        out = co.compress(chunk)
+        parts.append(out)
+        n += len(out)
+        if n >= target_bytes:
+            break
+    parts.append(co.flush())
+    return b"".join(parts)
+
+
+def c2_text(nbytes, seed=0xDEF7):
+    parts, n = [], 0
+    for chunk in text_chunks(seed, 1 << 16):
+        parts.append(chunk)
+        n += len(chunk)
+        if n >= nbytes:
+            break
+    return b"".join(parts)[:nbytes]
+
+
+def _png_filtered(index, w=256, h=256):
+    """Filtered scanlines (Sub filter on gradients / None on flats) of a synthetic RGBA image: a mix of flat
+    regions, linear gradients and 5 % uniform noise; 262 400 bytes."""
+    rng = np.random.default_rng(index)
+    img = np.zeros((h, w, 4), dtype=np.uint8)
+    # flat regions
+    for _ in range(6):
+        x0, y0 = rng.integers(0, w), rng.integers(0, h)
+        x1, y1 = rng.integers(x0, w + 1), rng.integers(y0, h + 1)
+        img[y0:y1, x0:x1] = rng.integers(0, 256, 4, dtype=np.uint8)
+    # linear gradients
+    for _ in range(3):
+        y0 = rng.integers(0, h - 16)
+        y1 = rng.integers(y0 + 8, h + 1)
+        g = (np.arange(w) * rng.integers(1, 4) + rng.integers(0, 256)) & 255
+        img[y0:y1, :, rng.integers(0, 3)] = g.astype(np.uint8)[None, :]
+    img[..., 3] = 255
+    # 5 % noise
+    m = rng.random((h, w)) < 0.05
+    img[m] = rng.integers(0, 256, (int(m.sum()), 4), dtype=np.uint8)
+    raw = img.reshape(h, w * 4)
+    sub = raw.copy()
+    sub[:, 4:] = raw[:, 4:] - raw[:, :-4]
+    # adaptive choice per line: minimum sum of absolute differences heuristic between None and Sub
+    cost_none = np.minimum(raw, 256 - raw.astype(np.int16)).sum(1)
+    cost_sub = np.minimum(sub, 256 - sub.astype(np.int16)).sum(1)
+    use_sub = cost_sub < cost_none
+    lines = np.where(use_sub[:, None], sub, raw)
+    out = np.empty((h, w * 4 + 1), dtype=np.uint8)
+    out[:, 0] = use_sub.astype(np.uint8)
+    out[:, 1:] = lines
+    return out.tobytes()
+
+
+def c3_streams(count, first=0):
+    """Raw deflate payloads of `count` PNG IDAT streams (the zlib wrapper is the container's business)."""
+    out = []
+    for i in range(first, first + count):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
+        out.append(co.compress(_png_filtered(i)) + co.flush())
+    return out
+
+
+def c4_streams(count, seed=4):
+    """Method-8 entry payloads: k%3==0 stored (level 0), ==1 Z_FIXED level 6, ==2 default level 6; payload sizes
+    log-uniform 1 KiB..256 KiB of C2 text."""
+    rng = np.random.default_rng(seed)
+    text = c2_text(4 << 20, seed=seed)
+    out = []
+    for k in range(count):
+        n = int(np.exp(rng.uniform(np.log(1024), np.log(256 * 1024))))
+        off = int(rng.integers(0, len(text) - n))
+        payload = text[off:off + n]
+        if k % 3 == 0:
+            co = zlib.compressobj(0, zlib.DEFLATED, -15, 8)
+        elif k % 3 == 1:
+            co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_FIXED)
+        else:
+            co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
+        out.append(co.compress(payload) + co.flush())
+    return out
+
+
+def c5_streams(scale=1):
+    """Adversarial streams (scaled: `scale` MiB per long-match stream)."""
+    rng = np.random.default_rng(5)
+    n = scale << 20
+    period = rng.integers(0, 256, 32768, dtype=np.uint8).tobytes()
+    sparse = rng.choice(np.array([0, 255], dtype=np.uint8), 1 << 16).tobytes()
+    two = rng.choice(np.array([7, 9], dtype=np.uint8), 1 << 15, p=[0.9, 0.1]).tobytes()
+    datas = [b"\x41" * n, (period * (n // 32768 + 1))[:n], sparse, two, bytes(range(256)) * 64]
+    out = []
+    for d in datas:
+        for level, strat in ((6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_RLE)):
+            co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strat)
+            out.append(co.compress(d) + co.flush())
+    return out
+
+
+# ---- hand-made streams (fixed-code blocks) for shapes zlib never emits -----------------------------------------
+_LEN_BASE = [3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258]
+_LEN_EB = [0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0]
+_DIST_BASE = [1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097,
+              6145, 8193, 12289, 16385, 24577]
+_DIST_EB = [0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13]
+
+
+class BitWriter:
+    def __init__(self):
+        self.acc, self.n, self.out = 0, 0, bytearray()
+
+    def bits(self, value, count):  # LSB first
+        self.acc |= value << self.n
+        self.n += count
+        while self.n >= 8:
+            self.out.append(self.acc & 255)
+            self.acc >>= 8
+            self.n -= 8
+
+    def code(self, code, length):  # Huffman codes go MSB first
+        self.bits(int(format(code, "0%db" % length)[::-1], 2), length)
+
+    def align(self):
+        if self.n:
+            self.bits(0, 8 - self.n)
+
+    def done(self):
+        self.align()
+        return bytes(self.out)
+
+
+def _fixed_litlen(bw, sym):
+    if sym <= 143: bw.code(0x30 + sym, 8)
+    elif sym <= 255: bw.code(0x190 + sym - 144, 9)
+    elif sym <= 279: bw.code(sym - 256, 7)
+    else: bw.code(0xC0 + sym - 280, 8)
+
+
+def fixed_block(bw, symbols, final):
+    """symbols: int literal | (length, distance) | (258, distance, 'edge') for the symbol-284+31 spelling of 258."""
+    bw.bits(1 if final else 0, 1)
+    bw.bits(1, 2)
+    for s in symbols:
+        if isinstance(s, int):
+            _fixed_litlen(bw, s)
+            continue
+        length, dist = s[0], s[1]
+        if len(s) > 2:
+            _fixed_litlen(bw, 284); bw.bits(31, 5)
+        else:
+            i = max(k for k in range(29) if _LEN_BASE[k] <= length and (k < 28 or length == 258))
+            if length == 258: i = 28
+            _fixed_litlen(bw, 257 + i); bw.bits(length - _LEN_BASE[i], _LEN_EB[i])
+        d = max(k for k in range(30) if _DIST_BASE[k] <= dist)
+        bw.code(d, 5); bw.bits(dist - _DIST_BASE[d], _DIST_EB[d])
+    _fixed_litlen(bw, 256)
+
+
+def stored_block(bw, data, final):
+    bw.bits(1 if final else 0, 1)
+    bw.bits(0, 2)
+    bw.align()
+    bw.bits(len(data), 16); bw.bits(len(data) ^ 0xffff, 16)
+    bw.out += data
+
+
+def handmade_streams():
+    """Shapes outside zlib's repertoire: distance 32768 / length 258, the 284+31 edge case, empty blocks mid-stream
+    (SURVEY.md H6), stored blocks around 65535 (H5/H12), a lone EOB."""
+    rng = np.random.default_rng(55)
+    out = {}
+    base = [int(x) for x in rng.integers(0, 256, 32768)]
+    bw = BitWriter(); fixed_block(bw, base + [(258, 32768)] * 130 + [(3, 1), (258, 1)], True); out["dist32768_len258"] = bw.done()
+    bw = BitWriter(); fixed_block(bw, [65, 66, 67] + [(258, 3, "edge")] * 40 + [(258, 3)] * 3, True); out["edge284"] = bw.done()
+    bw = BitWriter()
+    fixed_block(bw, [72, 105, 32] * 20, False); stored_block(bw, b"", False); fixed_block(bw, [(30, 60), 33], False)
+    fixed_block(bw, [], False); fixed_block(bw, [10] * 50, True); out["empty_blocks_midstream"] = bw.done()
+    bw = BitWriter(); stored_block(bw, bytes(base[:3000]) * 10, False); stored_block(bw, bytes(base) + bytes(base[:2766]), False)
+    stored_block(bw, b"xyz" * 11000, False); stored_block(bw, b"tail", True); out["stored_around_65535"] = bw.done()
+    bw = BitWriter(); fixed_block(bw, [], True); out["lone_eob"] = bw.done()
+    bw = BitWriter(); stored_block(bw, b"", True); out["empty_stored_only"] = bw.done()
+    bw = BitWriter(); fixed_block(bw, [0] + [(258, 1)] * 300, False); fixed_block(bw, [(258, 1)] * 300 + [255], True); out["rle_two_fixed"] = bw.done()
+    return out
