@@ -238,14 +238,14 @@ def run_ours(a):
     fam = [0.0] * 8
 
     def step():
-        rc = L.deft4cu_device_batch_run(h, merge, C.byref(launches), C.c_void_p(stream.cuda_stream))
+        rc = L.deft4cu_device_batch_run(h, merge, C.byref(launches), None if os.environ.get('D4_OWN') else C.c_void_p(stream.cuda_stream))
         assert rc == 0, N.last_error()
 
     with torch.cuda.stream(stream):
         for _ in range(a.warmup):
             step()
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
+        sampler = ClockSampler(local) if rank == 0 and not os.environ.get('D4_NOSAMPLER') else None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         total_launches = 0

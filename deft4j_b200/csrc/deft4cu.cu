@@ -23,6 +23,7 @@ namespace d4 {
 
 static int g_device = -1;
 static int g_sms = 148;
+static bool g_sync_debug = getenv("D4_SYNC") != nullptr;
 static std::mutex g_mu;
 
 static int ensure_init() {
@@ -35,6 +36,13 @@ static int ensure_init() {
         kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                     \
         launches++;                                                              \
         D4_CUDA_CHECK(cudaGetLastError());                                       \
+        if (g_sync_debug) {                                                      \
+            cudaError_t se_ = cudaStreamSynchronize(stream);                     \
+            if (se_ != cudaSuccess) {                                            \
+                set_error(std::string(#kern) + " faulted: " + cudaGetErrorString(se_)); \
+                return DEFT4CU_ERR_CUDA;                                         \
+            }                                                                    \
+        }                                                                        \
     } while (0)
 
 template <typename T>
@@ -215,8 +223,8 @@ class Batch {
         infos.assign(n, StreamInfo{});
         D4_CUDA_CHECK(dalloc(&d_descs, (size_t)n + 1, cs));
         D4_CUDA_CHECK(dalloc(&d_infos, n, cs));
-        D4_CUDA_CHECK(dalloc(&d_gerr, 1, cs));
-        D4_CUDA_CHECK(cudaMemsetAsync(d_gerr, 0, sizeof(int), cs));
+        D4_CUDA_CHECK(dalloc(&d_gerr, 8, cs));
+        D4_CUDA_CHECK(cudaMemsetAsync(d_gerr, 0, 8 * sizeof(int), cs));
         std::vector<uint64_t> bcap(n), ccap(n);
         for (uint32_t i = 0; i < n; i++) {
             bcap[i] = in_len[i] / 4096 + 8;
@@ -403,6 +411,11 @@ class Batch {
             D4_CUDA_CHECK(dalloc(&sc.masks, (size_t)grid * NCAND * sc.maxwords, cs));
             D4_CUDA_CHECK(dalloc(&sc.memoH, (size_t)grid * MEMO_H, cs));
             D4_CUDA_CHECK(dalloc(&sc.memoT, (size_t)grid * MEMO_T, cs));
+            if (getenv("D4_POISON")) {
+                cudaMemsetAsync(sc.masks, 0xFF, sizeof(uint32_t) * (size_t)grid * NCAND * sc.maxwords, cs);
+                cudaMemsetAsync(sc.memoH, 0xFF, sizeof(MemoHEntry) * (size_t)grid * MEMO_H, cs);
+                cudaMemsetAsync(sc.memoT, 0xFF, sizeof(Tab) * (size_t)grid * MEMO_T, cs);
+            }
             LAUNCH(k_opt_blocks, grid, ENG_NT, cs, d_jobs, (uint32_t)jobs.size(), d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, d_counter, d_gerr);
             dfree(sc.masks, cs); dfree(sc.memoH, cs); dfree(sc.memoT, cs);
             dfree(d_jobs, cs); dfree(d_counter, cs);
@@ -420,16 +433,26 @@ class Batch {
             if (merge) { dfree(sc.masks, cs); dfree(sc.memoH, cs); dfree(sc.memoT, cs); }
         }
         cudaEventRecord(ev[2], cs);
-        int gerr = 0;
+        int gerrv[8] = {0};
         D4_CUDA_CHECK(cudaMemcpyAsync(sstate.data(), d_sstate, sizeof(StreamState) * n, cudaMemcpyDeviceToHost, cs));
-        D4_CUDA_CHECK(cudaMemcpyAsync(&gerr, d_gerr, sizeof(int), cudaMemcpyDeviceToHost, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(gerrv, d_gerr, sizeof(gerrv), cudaMemcpyDeviceToHost, cs));
         D4_CUDA_CHECK(cudaStreamSynchronize(cs));
         float t;
         cudaEventElapsedTime(&t, ev[0], ev[1]); ms[3] = t;
         cudaEventElapsedTime(&t, ev[1], ev[2]); ms[4] = t;
         for (auto& e : ev) cudaEventDestroy(e);
+        const int gerr = gerrv[0];
+        if (gerr == 13 || gerr == 14) {
+            char msg[256];
+            snprintf(msg, sizeof msg, gerr == 14 ? "engine verify: job %d opcode %d slot %d claims payload %d, true %d (cta %d candIndex %d of %zu)" : "engine self-check: block %d round %d winner idx %d claims payload %d, true %d (cta %d job %d of %zu)",
+                     gerrv[1], gerrv[2], gerrv[3], gerrv[4], gerrv[5], gerrv[6], gerrv[7], jobs.size());
+            set_error(msg);
+            return DEFT4CU_ERR_CUDA;
+        }
         if (gerr) {
-            set_error("optimiser hit an internal limit (tree node pool / round cap)");
+            set_error(gerr == ERR_ROUNDS ? "optimiser hit an internal limit: more than 64 optimiseBlock rounds on one block"
+                                         : "optimiser: a Huffman tree could not be balanced (the reference throws here)");
+            D4_CUDA_CHECK(cudaMemsetAsync(d_gerr, 0, sizeof(int), cs));
             for (uint32_t i = 0; i < n; i++) if (sstate[i].selected) sstate[i].status = ST_UNSUPPORTED;
             return DEFT4CU_ERR_UNSUPPORTED;
         }
@@ -460,13 +483,19 @@ class Batch {
             LAUNCH(k_write, (unsigned)nblk_total, WR_NT, cs, d_sstate, d_blk_stream, d_bs, d_sym, d_symout, d_out, d_maskpool, d_dst_off,
                    (unsigned long long*)d_dst, d_gerr);
         cudaEventRecord(ev[1], cs);
-        int gerr = 0;
-        D4_CUDA_CHECK(cudaMemcpyAsync(&gerr, d_gerr, sizeof(int), cudaMemcpyDeviceToHost, cs));
+        int gerr[8] = {0};
+        D4_CUDA_CHECK(cudaMemcpyAsync(gerr, d_gerr, sizeof(gerr), cudaMemcpyDeviceToHost, cs));
         D4_CUDA_CHECK(cudaStreamSynchronize(cs));
         float t;
         cudaEventElapsedTime(&t, ev[0], ev[1]); ms[5] = t;
         for (auto& e : ev) cudaEventDestroy(e);
-        if (gerr) { set_error("writer and cost model disagree on a block size"); return DEFT4CU_ERR_WRITE; }
+        if (gerr[0]) {
+            char msg[200];
+            snprintf(msg, sizeof msg, "writer and cost model disagree (code %d) on block %d: wrote %d bits, model says %d (%s)",
+                     gerr[0], gerr[1], gerr[2], gerr[3], gerr[4] == 1 ? "header" : "block");
+            set_error(msg);
+            return DEFT4CU_ERR_WRITE;
+        }
         return DEFT4CU_OK;
     }
 
@@ -532,6 +561,15 @@ int deft4cu_init(int device) {
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if (getenv("D4_DEBUG_LIMITS")) {
+        size_t st = 0, hp = 0;
+        cudaDeviceGetLimit(&st, cudaLimitStackSize);
+        cudaDeviceGetLimit(&hp, cudaLimitMallocHeapSize);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, k_opt_blocks);
+        fprintf(stderr, "[deft4cu] stack limit %zu heap %zu; k_opt_blocks local %zu regs %d smem %zu\n", st, hp, fa.localSizeBytes, fa.numRegs, fa.sharedSizeBytes);
+        if (getenv("D4_STACK")) { cudaDeviceSetLimit(cudaLimitStackSize, atoi(getenv("D4_STACK"))); }
     }
     g_device = device;
     return DEFT4CU_OK;

@@ -29,6 +29,7 @@
 namespace d4 {
 
 constexpr int ENG_NT = 256;
+constexpr int ERR_TREE = 11, ERR_ROUNDS = 12, ERR_WRITER = 2;  // internal-limit codes reported through gerr
 
 // parity-debug instrumentation (deft4cu_debug_trace): when armed, every candidate the selection callback sees
 // is logged as (candidate index, size) and the header-strategy memo is bypassed so all 56 trials are logged
@@ -93,6 +94,12 @@ struct EngSmem {
 
 enum { C_B = 0, C_BEST, C_O, C_H, C_E, C_X, C_CHK, C_T, C_Y, C_B1, C_B2, C_B3, C_B4, C_PP, C_CHK2, C_TMP };
 
+#ifdef D4_VERIFY
+#define D4V(c, op) verify(c, op)
+#else
+#define D4V(c, op)
+#endif
+
 struct Eng {
     EngSmem* S;
     BlkView v;
@@ -114,6 +121,7 @@ struct Eng {
         uint32_t* md = mask(dst);
         for (uint32_t k = tid; k < v.nwords; k += ENG_NT) md[k] = ms[k];
         __syncthreads();
+        D4V(dst, 7);
     }
 
     // ---- selection callback (DeflateStream.java:349-368) ------------------------------------------
@@ -176,6 +184,7 @@ struct Eng {
         __syncthreads();
         if (tid == 0) cd.payload -= (long long)S->red;
         __syncthreads();
+        D4V(c, prune ? 2 : 1);
     }
 
     // removeDistLitLeastExpensive(mode) on candidate c (in place); no-op unless DYNAMIC
@@ -224,6 +233,7 @@ struct Eng {
             }
         }
         __syncthreads();
+        D4V(c, 3 + mode);
     }
 
     // histogram of candidate c's symbol list into S->hist
@@ -286,6 +296,27 @@ struct Eng {
         return r | 1ull;
     }
 
+#ifdef D4_VERIFY
+    int* vgerr = nullptr;
+    int vjob = -1;
+    // debug: payload of candidate c recomputed from its mask and tables; first mismatch is recorded
+    __device__ __noinline__ void verify(int c, int opcode) {
+        __syncthreads();
+        uint32_t save[2] = {0, 0};
+        // pass_hist/hist_payload clobber S->hist and S->red only
+        pass_hist(c);
+        long long t = hist_payload(S->c[c].tab);
+        if (tid == 0 && t != S->c[c].payload) {
+            if (atomicMax(vgerr, 14) < 13) {
+                vgerr[1] = vjob; vgerr[2] = opcode; vgerr[3] = c; vgerr[4] = (int)S->c[c].payload; vgerr[5] = (int)t;
+                vgerr[6] = (int)blockIdx.x; vgerr[7] = (int)S->candIndex;
+            }
+        }
+        (void)save;
+        __syncthreads();
+    }
+#endif
+
     // ---- recodeHuffman (:670-743) on candidate c: tables from the histogram, payload, default header
     __device__ __noinline__ void op_recode(int c) {
         pass_hist(c);
@@ -313,6 +344,7 @@ struct Eng {
             uint32_t* d = (uint32_t*)&S->c[c];
             for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
             __syncthreads();
+            D4V(c, 5);
             return;
         }
         Cand& cd = S->c[c];
@@ -321,7 +353,7 @@ struct Eng {
             int nl = 286;
             while (nl > 0 && S->hist[nl - 1] == 0) nl--;
             cd.tab.nL = (uint16_t)nl;
-            if (huff_tree<290, 584>(S->hist, nl, 15, cd.tab.L, S->tl)) S->err = ST_UNSUPPORTED;
+            if (huff_tree<290, 584>(S->hist, nl, 15, cd.tab.L, S->tl)) S->err = ERR_TREE;
             for (int k = nl; k < MAX_LL; k++) cd.tab.L[k] = 0;
         }
         if (tid == 32) {
@@ -335,7 +367,7 @@ struct Eng {
             else if (nz <= 1) { cd.tab.nD = (uint16_t)nd; cd.tab.D[nd - 1] = 1; }  // handleOne
             else {
                 cd.tab.nD = (uint16_t)nd;
-                if (huff_tree<32, 68>(df, nd, 15, cd.tab.D, S->td)) S->err = ST_UNSUPPORTED;
+                if (huff_tree<32, 68>(df, nd, 15, cd.tab.D, S->td)) S->err = ERR_TREE;
             }
         }
         __syncthreads();
@@ -345,7 +377,7 @@ struct Eng {
         if (tid == 0) {
             cd.payload = pay;
             TreeWsCL ws;
-            if (hdr_rewrite(cd.tab, FLAGS_DEFAULT, cd.hdr, ws)) S->err = ST_UNSUPPORTED;
+            if (hdr_rewrite(cd.tab, FLAGS_DEFAULT, cd.hdr, ws)) S->err = ERR_TREE;
         }
         __syncthreads();
         // store in the memo (FIFO replacement)
@@ -366,6 +398,7 @@ struct Eng {
             for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
         }
         __syncthreads();
+        D4V(c, 6);
     }
     // recodeHuffmanLessMatches (:655-658)
     __device__ void op_recode_less(int c) { pass_replace(c, true); op_recode(c); }
@@ -405,11 +438,11 @@ struct Eng {
         return op_optimise(dst) > 0;
     }
     __device__ void op_recode_header(int c) {
-        if (tid == 0 && S->c[c].tab.type == 2) { TreeWsCL ws; if (hdr_recode(S->c[c].hdr, ws)) S->err = ST_UNSUPPORTED; }
+        if (tid == 0 && S->c[c].tab.type == 2) { TreeWsCL ws; if (hdr_recode(S->c[c].hdr, ws)) S->err = ERR_TREE; }
         __syncthreads();
     }
     __device__ void op_recode_header_less(int c) {
-        if (tid == 0 && S->c[c].tab.type == 2) { TreeWsCL ws; if (hdr_recode_less(S->c[c].hdr, ws)) S->err = ST_UNSUPPORTED; }
+        if (tid == 0 && S->c[c].tab.type == 2) { TreeWsCL ws; if (hdr_recode_less(S->c[c].hdr, ws)) S->err = ERR_TREE; }
         __syncthreads();
     }
 
@@ -449,7 +482,7 @@ struct Eng {
             if (j < nb * 56 && s_hit[j / 56] < 0) {
                 Hdr h;
                 TreeWsCL ws;
-                if (hdr_trial(S->c[C_B1 + j / 56].tab, c_trial_flags[j % 56], h, ws)) S->err = ST_UNSUPPORTED;
+                if (hdr_trial(S->c[C_B1 + j / 56].tab, c_trial_flags[j % 56], h, ws)) S->err = ERR_TREE;
                 S->trialBits[j] = h.bits;
             }
         }
@@ -466,7 +499,11 @@ struct Eng {
         }
         __syncthreads();
         for (int b = 0; b < nb; b++) {
-            if (s_hit[b] < 0) {  // insert
+            // every thread must read the flag before thread 0 overwrites it below (a late reader would skip the two
+            // barriers inside and leave the CTA one barrier out of step)
+            const bool miss = s_hit[b] < 0;
+            __syncthreads();
+            if (miss) {  // insert
                 int slot;
                 if (tid == 0) {
                     slot = S->memoT_next;
@@ -502,7 +539,7 @@ struct Eng {
                 copy(C_BEST, C_B1 + b);
                 if (tid == 0) {
                     TreeWsCL ws;
-                    if (hdr_trial(S->c[C_BEST].tab, c_trial_flags[arg], S->c[C_BEST].hdr, ws)) S->err = ST_UNSUPPORTED;
+                    if (hdr_trial(S->c[C_BEST].tab, c_trial_flags[arg], S->c[C_BEST].hdr, ws)) S->err = ERR_TREE;
                 }
             }
             __syncthreads();

@@ -15,7 +15,7 @@
 
 namespace d4 {
 
-constexpr int MAXR = 16;  // optimiseBlock rounds logged per block
+constexpr int MAXR = 64;  // optimiseBlock rounds logged per block
 
 struct BlkState {
     Cand cand;            // cand.tab.type: 0 STORED, 1 FIXED, 2 DYNAMIC
@@ -129,6 +129,9 @@ k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __rest
         e.v.n = b.n_sym;
         e.v.nwords = (b.n_sym + 31) / 32;
         e.v.ulen = b.out_len;
+#ifdef D4_VERIFY
+        e.vgerr = gerr; e.vjob = (int)job;
+#endif
         eng_load(e, b, nullptr);
         RoundLog& lg = logs[jobs[job]];
         int r = 0;
@@ -139,9 +142,20 @@ k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __rest
             }
             const bool improved = S.bestSize < S.sizeI;
             __syncthreads();
+            if (improved && !S.bestStored) {  // self-check: the winner's payload recomputed from its symbol list
+                e.pass_hist(C_BEST);
+                const long long truePay = e.hist_payload(S.c[C_BEST].tab);
+                if (truePay != S.c[C_BEST].payload && tid == 0) {
+                    if (atomicMax(gerr, 13) < 13) {
+                        gerr[1] = (int)jobs[job]; gerr[2] = r; gerr[3] = (int)S.bestIndex;
+                        gerr[4] = (int)S.c[C_BEST].payload; gerr[5] = (int)truePay; gerr[6] = (int)blockIdx.x; gerr[7] = (int)job;
+                    }
+                }
+                __syncthreads();
+            }
             r++;
             if (!improved) break;
-            if (r >= MAXR) { if (tid == 0) S.err = ST_UNSUPPORTED; break; }
+            if (r >= MAXR) { if (tid == 0) S.err = ERR_ROUNDS; break; }
             e.copy(C_B, C_BEST);
         }
         __syncthreads();

@@ -119,7 +119,9 @@ k_write(const StreamState* __restrict__ streams, const uint32_t* __restrict__ bl
                     put_bits(dw, p, (unsigned long long)(run - off), sz); p += sz;
                 }
             }
-            if ((long long)(p - pos0 - 3) != (long long)h.bits) atomicMax(gerr, 2);  // model/writer disagree
+            if ((long long)(p - pos0 - 3) != (long long)h.bits) {  // model/writer disagree
+                if (atomicMax(gerr, 2) == 0) { gerr[1] = (int)blockIdx.x; gerr[2] = (int)(p - pos0 - 3); gerr[3] = h.bits; gerr[4] = 1; }
+            }
         }
         W.base = p;
     }
@@ -196,7 +198,9 @@ k_write(const StreamState* __restrict__ streams, const uint32_t* __restrict__ bl
         __syncthreads();
     }
     if (tid == 0) {
-        if ((long long)(W.base - pos0 - 3) != b.size_bits) atomicMax(gerr, 2);
+        if ((long long)(W.base - pos0 - 3) != b.size_bits) {
+            if (atomicMax(gerr, 2) == 0) { gerr[1] = (int)blockIdx.x; gerr[2] = (int)(W.base - pos0 - 3); gerr[3] = (int)b.size_bits; gerr[4] = 2; }
+        }
     }
 }
 

@@ -25,6 +25,8 @@ def golden_raws(nm):
 
 
 merge = int(sys.argv[1])
+if os.environ.get('D4_TORCH'):
+    import torch; torch.cuda.init(); torch.zeros(1, device='cuda')
 bufs = []
 for spec in sys.argv[2:]:
     kind, arg = spec.split(":")
@@ -41,7 +43,7 @@ L = N.lib()
 ptrs, lens = N.make_ptr_arrays(bufs)
 h = C.c_void_p()
 assert L.deft4cu_device_batch_create(ptrs, lens, len(bufs), C.byref(h)) == 0
-for it in range(2):
+for it in range(int(os.environ.get("D4_ITERS", "2"))):
     launches = C.c_uint64(0)
     t0 = time.time()
     rc = L.deft4cu_device_batch_run(h, merge, C.byref(launches), None)
