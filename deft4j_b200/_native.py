@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeft4cu.so")
+# DEFT4CU_LIB selects another build of the same ABI (tests use the small-pool stress build)
+LIB_PATH = os.environ.get("DEFT4CU_LIB") or os.path.join(_HERE, "libdeft4cu.so")
 
 OK, ERR_PARSE, ERR_WRITE, ERR_UNSUPPORTED, ERR_CUDA, ERR_ARG = 0, 1, 2, 3, 4, 5
 MERGE_BLOCKS = 1

@@ -372,6 +372,23 @@ class Batch {
         return DEFT4CU_OK;
     }
 
+    // per-CTA engine scratch (mask pool, interned tables, recode cache, pass memo values)
+    cudaError_t alloc_scratch(EngScratch& sc, unsigned grid) {
+        cudaError_t e;
+        if ((e = dalloc(&sc.masks, (size_t)grid * (MAXM + NCAND) * sc.maxwords, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.tabs, (size_t)grid * MAXT, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.recode, (size_t)grid * MAXM, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.pvals, (size_t)grid * MEMO_P, cs)) != cudaSuccess) return e;
+        if (getenv("D4_POISON")) {
+            cudaMemsetAsync(sc.masks, 0xFF, sizeof(uint32_t) * (size_t)grid * (MAXM + NCAND) * sc.maxwords, cs);
+            cudaMemsetAsync(sc.tabs, 0xFF, sizeof(Tab) * (size_t)grid * MAXT, cs);
+            cudaMemsetAsync(sc.recode, 0xFF, sizeof(Cand) * (size_t)grid * MAXM, cs);
+            cudaMemsetAsync(sc.pvals, 0xFF, sizeof(PVal) * (size_t)grid * MEMO_P, cs);
+        }
+        return cudaSuccess;
+    }
+    void free_scratch(EngScratch& sc) { dfree(sc.masks, cs); dfree(sc.tabs, cs); dfree(sc.recode, cs); dfree(sc.pvals, cs); }
+
     // ---- optimise: phase A over blocks, then per-stream replay/merge/layout ----------------------------
     int optimise(uint32_t flags, const std::vector<uint8_t>& selected) {
         cudaEvent_t ev[3];
@@ -408,29 +425,26 @@ class Batch {
             unsigned grid = (unsigned)std::min<uint64_t>(jobs.size(), (uint64_t)g_sms * perSM);
             EngScratch sc;
             sc.maxwords = (maxsym + 31) / 32 + 1;
-            D4_CUDA_CHECK(dalloc(&sc.masks, (size_t)grid * NCAND * sc.maxwords, cs));
-            D4_CUDA_CHECK(dalloc(&sc.memoH, (size_t)grid * MEMO_H, cs));
-            D4_CUDA_CHECK(dalloc(&sc.memoT, (size_t)grid * MEMO_T, cs));
-            if (getenv("D4_POISON")) {
-                cudaMemsetAsync(sc.masks, 0xFF, sizeof(uint32_t) * (size_t)grid * NCAND * sc.maxwords, cs);
-                cudaMemsetAsync(sc.memoH, 0xFF, sizeof(MemoHEntry) * (size_t)grid * MEMO_H, cs);
-                cudaMemsetAsync(sc.memoT, 0xFF, sizeof(Tab) * (size_t)grid * MEMO_T, cs);
-            }
+            D4_CUDA_CHECK(alloc_scratch(sc, grid));
             LAUNCH(k_opt_blocks, grid, ENG_NT, cs, d_jobs, (uint32_t)jobs.size(), d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, d_counter, d_gerr);
-            dfree(sc.masks, cs); dfree(sc.memoH, cs); dfree(sc.memoT, cs);
+            free_scratch(sc);
             dfree(d_jobs, cs); dfree(d_counter, cs);
         }
         cudaEventRecord(ev[1], cs);
         {
             EngScratch sc{};
             sc.maxwords = (maxstream + 31) / 32 + 2;
-            if (merge) {
-                D4_CUDA_CHECK(dalloc(&sc.masks, (size_t)n * NCAND * sc.maxwords, cs));
-                D4_CUDA_CHECK(dalloc(&sc.memoH, (size_t)n * MEMO_H, cs));
-                D4_CUDA_CHECK(dalloc(&sc.memoT, (size_t)n * MEMO_T, cs));
-            }
-            if (n) LAUNCH(k_finish, n, ENG_NT, cs, d_sstate, d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, merge, d_gerr);
-            if (merge) { dfree(sc.masks, cs); dfree(sc.memoH, cs); dfree(sc.memoT, cs); }
+            int perSM = 0;
+            D4_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_finish, ENG_NT, 0));
+            if (perSM < 1) perSM = 1;
+            const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)g_sms * perSM);
+            unsigned* d_counter = nullptr;
+            D4_CUDA_CHECK(dalloc(&d_counter, 1, cs));
+            D4_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, 4, cs));
+            if (merge) D4_CUDA_CHECK(alloc_scratch(sc, grid));
+            if (n) LAUNCH(k_finish, grid, ENG_NT, cs, d_sstate, n, d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, merge, d_counter, d_gerr);
+            if (merge) free_scratch(sc);
+            dfree(d_counter, cs);
         }
         cudaEventRecord(ev[2], cs);
         int gerrv[8] = {0};
@@ -451,6 +465,7 @@ class Batch {
         }
         if (gerr) {
             set_error(gerr == ERR_ROUNDS ? "optimiser hit an internal limit: more than 64 optimiseBlock rounds on one block"
+                      : gerr == ERR_POOL ? "optimiser: internal table pool overflow"
                                          : "optimiser: a Huffman tree could not be balanced (the reference throws here)");
             D4_CUDA_CHECK(cudaMemsetAsync(d_gerr, 0, sizeof(int), cs));
             for (uint32_t i = 0; i < n; i++) if (sstate[i].selected) sstate[i].status = ST_UNSUPPORTED;

@@ -13,11 +13,16 @@
 //   pass_hist    : the histogram loop of recodeHuffman   (:671-681); payload = hist . (len + extra bits)
 // Small serial work (Huffman trees, header model) runs in single threads (huff.cuh).
 //
-// Two exact shortcuts (pure-function memoisation; neither changes any candidate's size or the order in
-// which candidates are compared):
-//   * recodeHuffman's result (tables, payload, default header) depends only on the histogram -> cache.
+// Exact shortcuts (pure-function memoisation; none changes any candidate's size or the order in which
+// candidates are compared).  The enumeration revisits the same (symbol list, code tables) states many
+// times (e.g. recoded(e) inside addOptimisedRecoded(post(e)) is the seed of the next Run), so states
+// are hash-consed into ids and every O(n) pass is a function of ids:
+//   * masks are immutable and live in a per-CTA pool; a candidate holds a mask id `mid`; Tabs are interned
+//     into `tabid`s.  replace/least passes are memoised on (mid, tabid, op) -> (mid', payload delta);
+//     recodeHuffman's result (tables, payload, default header) depends only on the mask -> cached per mid.
+//     When a pool fills up, everything not referenced by a candidate slot is dropped (flush_all).
 //   * the 56 header-strategy trials of a base depend only on (Tab, payload) and their sizes are
-//     payload + f(Tab, strategy) -> the first-minimum strategy per Tab is cached, and the
+//     payload + f(Tab, strategy) -> the first-minimum strategy per tabid is cached, and the
 //     addOptimisedRecoded(prune) sweep (DeflateStream.java:431) is skipped: it re-evaluates candidates
 //     with exactly the sizes of the sweep on `post` (:418) — both are copies of the same block that
 //     differ only in the header, which every base/trial discards — so under the strict `<` of the
@@ -41,14 +46,25 @@ __device__ __forceinline__ void trace_put(long long idx, long long sz) {
     if (k < g_trace_cap) { g_trace[2 * k] = idx; g_trace[2 * k + 1] = sz; }
 }
 constexpr int NCAND = 16;
-constexpr int MEMO_H = 192;   // histogram -> recode result
-constexpr int MEMO_T = 192;   // Tab -> best header strategy
+#ifdef D4_SMALL_POOLS           // stress build: forces the pool-overflow path (flush_all) on ordinary inputs
+constexpr int MAXM = 20, MAXT = 20, MEMO_P = 64;
+#else
+constexpr int MAXM = 256;     // distinct symbol-list masks kept per block
+constexpr int MAXT = 256;     // distinct code tables kept per block
+constexpr int MEMO_P = 1024;  // pass memo slots (open addressing, kept under 3/4 full)
+#endif
+constexpr int ERR_POOL = 15;
+constexpr int TRIAL_UNSET = (int)0x80000000;
 
 struct Cand {
     Tab tab;
     Hdr hdr;
     long long payload;  // litlenSizeBits
+    uint16_t mid;       // mask id (engine-internal: index into the CTA's mask pool)
+    uint16_t tabid;     // interned Tab id (engine-internal)
+    uint32_t pad2;
 };
+struct PVal { uint32_t mid; uint32_t pad; long long delta; };
 __device__ __forceinline__ long long cand_size(const Cand& c) { return c.payload + (c.tab.type == 2 ? c.hdr.bits : 0); }
 
 struct BlkView {
@@ -58,11 +74,6 @@ struct BlkView {
     uint32_t n;       // symbols (including a NOP left by a merge)
     uint32_t nwords;  // mask words
     uint64_t ulen;    // decoded length
-};
-
-struct MemoHEntry {   // global scratch
-    uint32_t hist[320];
-    Cand result;
 };
 
 struct EngSmem {
@@ -80,14 +91,19 @@ struct EngSmem {
     int bestStored;
     long long sizeI, sizeC1, restMin;
     unsigned candIndex, bestIndex;
-    // memo tables
-    unsigned long long memoH_hash[MEMO_H];
-    int memoH_n, memoH_next;
-    unsigned long long memoT_hash[MEMO_T];
-    int memoT_bits[MEMO_T];
-    unsigned char memoT_arg[MEMO_T];
-    int memoT_n, memoT_next;
-    int tmpIdx;
+    // pools and memo tables
+    unsigned long long maskHash[MAXM];
+    unsigned char recodeValid[MAXM];
+    int nMasks;
+    unsigned long long tabHash[MAXT];
+    int tabTrialBits[MAXT];
+    unsigned char tabTrialArg[MAXT];
+    int nTabs, fixedTab;
+    unsigned long long pkey[MEMO_P];
+    int nP;
+    int remap[NCAND], uniq[NCAND];
+    unsigned long long uh[NCAND];
+    int tmpIdx, redAny2;
     int trialBits[4 * 56];
     unsigned long long hred[ENG_NT / 32];
 };
@@ -103,23 +119,22 @@ enum { C_B = 0, C_BEST, C_O, C_H, C_E, C_X, C_CHK, C_T, C_Y, C_B1, C_B2, C_B3, C
 struct Eng {
     EngSmem* S;
     BlkView v;
-    uint32_t* masks;      // NCAND slots of maxwords
+    uint32_t* masks;      // (MAXM + NCAND) slots of maxwords: the mask pool + the evacuation area of flush_all
     uint32_t maxwords;
-    MemoHEntry* memoH;    // MEMO_H entries
-    Tab* memoT;           // MEMO_T entries
+    Tab* tabs;            // MAXT interned code tables
+    Cand* recode;         // MAXM: recodeHuffman result per mask id
+    PVal* pvals;          // MEMO_P pass memo values
     int tid;
 
-    __device__ uint32_t* mask(int c) const { return masks + (size_t)c * maxwords; }
+    __device__ uint32_t* maskp(int id) const { return masks + (size_t)id * maxwords; }
 
-    // ---- candidate copy (DeflateBlockHuffman.copy, :1174-1205, with value semantics) -------------
+    // ---- candidate copy (DeflateBlockHuffman.copy, :1174-1205, with value semantics; masks are immutable
+    //      pool entries, so a copy shares its source's mask id) --------------------------------------------
     __device__ __noinline__ void copy(int dst, int src) {
         if (dst == src) return;
         const uint32_t* s = (const uint32_t*)&S->c[src];
         uint32_t* d = (uint32_t*)&S->c[dst];
         for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
-        const uint32_t* ms = mask(src);
-        uint32_t* md = mask(dst);
-        for (uint32_t k = tid; k < v.nwords; k += ENG_NT) md[k] = ms[k];
         __syncthreads();
         D4V(dst, 7);
     }
@@ -136,6 +151,157 @@ struct Eng {
             S->candIndex++;
         }
         if (better) copy(C_BEST, c); else __syncthreads();
+    }
+
+    __device__ __noinline__ unsigned long long hash_words(const uint32_t* p, int nwords32) {
+        unsigned long long h = 0;
+        for (int k = tid; k < nwords32; k += ENG_NT) {
+            unsigned long long x = (unsigned long long)p[k] + 0x9E3779B97F4A7C15ull * (unsigned long long)(k + 1);
+            x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+            h += x;
+        }
+        for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+        if ((tid & 31) == 0) S->hred[tid >> 5] = h;
+        __syncthreads();
+        unsigned long long r = 0;
+        for (int k = 0; k < ENG_NT / 32; k++) r += S->hred[k];
+        __syncthreads();
+        return r | 1ull;
+    }
+
+    // ---- pools --------------------------------------------------------------------------------------------
+    // start of a new block (new symbol view): everything is forgotten
+    __device__ __noinline__ void begin_block() {
+        __syncthreads();
+        for (int k = tid; k < MEMO_P; k += ENG_NT) S->pkey[k] = 0;
+        for (int k = tid; k < MAXM; k += ENG_NT) S->recodeValid[k] = 0;
+        if (tid < NCAND) { S->c[tid].mid = 0; S->c[tid].tabid = 0; S->c[tid].pad2 = 0; }
+        if (tid == 0) { S->nMasks = 0; S->nTabs = 0; S->nP = 0; S->fixedTab = -1; }
+        __syncthreads();
+    }
+
+    // Tab of candidate c -> S->c[c].tabid (hash-consed; a hash hit is confirmed by a full comparison)
+    __device__ __noinline__ void intern_tab(int c) {
+        const uint32_t* q = (const uint32_t*)&S->c[c].tab;
+        const unsigned long long h = hash_words(q, (int)(sizeof(Tab) / 4));
+        if (tid == 0) { S->tmpIdx = -1; S->redAny2 = 0; }
+        __syncthreads();
+        const int nT = S->nTabs;
+        for (int k = tid; k < nT; k += ENG_NT)
+            if (S->tabHash[k] == h) atomicMax(&S->tmpIdx, k);
+        __syncthreads();
+        int hit = S->tmpIdx;
+        if (hit >= 0) {
+            const uint32_t* a = (const uint32_t*)&tabs[hit];
+            bool diff = false;
+            for (int k = tid; k < (int)(sizeof(Tab) / 4); k += ENG_NT) diff |= a[k] != q[k];
+            if (diff) S->redAny2 = 1;
+            __syncthreads();
+            if (S->redAny2) hit = -1;
+        }
+        __syncthreads();
+        if (hit < 0) {
+            if (tid == 0) {
+                int slot = S->nTabs;
+                if (slot >= MAXT) { S->err = ERR_POOL; slot = MAXT - 1; } else S->nTabs = slot + 1;
+                S->tabHash[slot] = h;
+                S->tabTrialBits[slot] = TRIAL_UNSET;
+                S->tmpIdx = slot;
+            }
+            __syncthreads();
+            hit = S->tmpIdx;
+            uint32_t* a = (uint32_t*)&tabs[hit];
+            for (int k = tid; k < (int)(sizeof(Tab) / 4); k += ENG_NT) a[k] = q[k];
+        }
+        if (tid == 0) S->c[c].tabid = (uint16_t)hit;
+        __syncthreads();
+    }
+
+    // the mask just written into pool slot nMasks -> its id (an equal older mask wins, so equal symbol lists
+    // reached along different paths share their memo entries)
+    __device__ __noinline__ int intern_mask() {
+        const int fresh = S->nMasks;
+        const uint32_t* q = maskp(fresh);
+        const unsigned long long h = hash_words(q, (int)v.nwords);
+        if (tid == 0) { S->tmpIdx = -1; S->redAny2 = 0; }
+        __syncthreads();
+        for (int k = tid; k < fresh; k += ENG_NT)
+            if (S->maskHash[k] == h) atomicMax(&S->tmpIdx, k);
+        __syncthreads();
+        int hit = S->tmpIdx;
+        if (hit >= 0) {
+            const uint32_t* a = maskp(hit);
+            bool diff = false;
+            for (uint32_t k = tid; k < v.nwords; k += ENG_NT) diff |= a[k] != q[k];
+            if (diff) S->redAny2 = 1;
+            __syncthreads();
+            if (S->redAny2) hit = -1;
+        }
+        __syncthreads();
+        if (hit < 0) {
+            hit = fresh;
+            if (tid == 0) { S->maskHash[fresh] = h; S->recodeValid[fresh] = 0; S->nMasks = fresh + 1; }
+        }
+        __syncthreads();
+        return hit;
+    }
+
+    // a pool is full: keep only what the candidate slots reference
+    __device__ __noinline__ void flush_all() {
+        __syncthreads();
+        if (tid == 0) {
+            int nu = 0;
+            for (int c = 0; c < NCAND; c++) {
+                const int m = S->c[c].mid;
+                int k = 0;
+                while (k < nu && S->uniq[k] != m) k++;
+                if (k == nu) { S->uniq[nu] = m; S->uh[nu] = S->maskHash[m]; nu++; }
+                S->remap[c] = k;
+            }
+            S->tmpIdx = nu;
+        }
+        __syncthreads();
+        const int nu = S->tmpIdx;
+        for (int k = 0; k < nu; k++) {
+            const uint32_t* s = maskp(S->uniq[k]);
+            uint32_t* d = maskp(MAXM + k);
+            for (uint32_t w = tid; w < v.nwords; w += ENG_NT) d[w] = s[w];
+        }
+        __syncthreads();
+        for (int k = 0; k < nu; k++) {
+            const uint32_t* s = maskp(MAXM + k);
+            uint32_t* d = maskp(k);
+            for (uint32_t w = tid; w < v.nwords; w += ENG_NT) d[w] = s[w];
+        }
+        if (tid < NCAND) S->c[tid].mid = (uint16_t)S->remap[tid];
+        if (tid < nu) S->maskHash[tid] = S->uh[tid];
+        for (int k = tid; k < MAXM; k += ENG_NT) S->recodeValid[k] = 0;
+        for (int k = tid; k < MEMO_P; k += ENG_NT) S->pkey[k] = 0;
+        __syncthreads();
+        if (tid == 0) { S->nMasks = nu; S->nTabs = 0; S->nP = 0; S->fixedTab = -1; }
+        __syncthreads();
+        for (int c = 0; c < NCAND; c++) intern_tab(c);
+    }
+    // every op creates at most one mask, one Tab and one memo entry
+    __device__ __forceinline__ void maybe_flush() {
+        const bool need = S->nMasks >= MAXM || S->nTabs >= MAXT || S->nP >= MEMO_P * 3 / 4;
+        if (need) flush_all();
+    }
+
+    // pass memo (thread 0 only): slot of `key`, or -1 - (insert position)
+    __device__ __forceinline__ int pm_find(unsigned long long key) const {
+        unsigned long long x = key;
+        x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+        unsigned h = (unsigned)x & (MEMO_P - 1);
+        while (true) {
+            const unsigned long long k = S->pkey[h];
+            if (k == key) return (int)h;
+            if (k == 0) return -1 - (int)h;
+            h = (h + 1) & (MEMO_P - 1);
+        }
+    }
+    __device__ __forceinline__ unsigned long long pm_key(int mid, int tabid, int op) const {
+        return (1ull << 63) | ((unsigned long long)op << 32) | ((unsigned long long)tabid << 16) | (unsigned long long)mid;
     }
 
     // ---- CTA-wide passes ----------------------------------------------------------------------------
@@ -158,10 +324,22 @@ struct Eng {
 
     // replaceBackrefsWithLiteralsIfSmaller(prune) on candidate c (in place)
     __device__ __noinline__ void pass_replace(int c, bool prune) {
+        maybe_flush();
         Cand& cd = S->c[c];
-        uint32_t* m = mask(c);
-        if (tid == 0) S->red = 0;
+        const int mid = cd.mid;
+        const unsigned long long key = pm_key(mid, cd.tabid, prune ? 1 : 0);
+        if (tid == 0) { S->tmpIdx = pm_find(key); S->red = 0; S->redAny = 0; }
         __syncthreads();
+        int slot = S->tmpIdx;
+        if (slot >= 0) {
+            if (tid == 0) { const PVal pv = pvals[slot]; cd.mid = (uint16_t)pv.mid; cd.payload -= pv.delta; }
+            __syncthreads();
+            D4V(c, prune ? 2 : 1);
+            return;
+        }
+        slot = -1 - slot;
+        const uint32_t* m = maskp(mid);
+        uint32_t* md = maskp(S->nMasks);
         long long saved = 0;
         const int lane = tid & 31;
         for (uint32_t base = (tid >> 5) * 32; base < v.n; base += ENG_NT) {
@@ -177,12 +355,24 @@ struct Eng {
                 }
             }
             unsigned bal = __ballot_sync(0xffffffffu, rep);
-            if (lane == 0 && bal) m[base >> 5] = word | bal;
+            if (lane == 0) {
+                md[base >> 5] = word | bal;
+                if (bal) S->redAny = 1;
+            }
         }
         for (int d = 16; d > 0; d >>= 1) saved += __shfl_xor_sync(0xffffffffu, saved, d);
         if (lane == 0 && saved) atomicAdd(&S->red, (unsigned long long)saved);
         __syncthreads();
-        if (tid == 0) cd.payload -= (long long)S->red;
+        int newmid = mid;
+        if (S->redAny) newmid = intern_mask();
+        if (tid == 0) {
+            PVal pv; pv.mid = (uint32_t)newmid; pv.pad = 0; pv.delta = (long long)S->red;
+            pvals[slot] = pv;
+            S->pkey[slot] = key;
+            S->nP++;
+            cd.mid = (uint16_t)newmid;
+            cd.payload -= pv.delta;
+        }
         __syncthreads();
         D4V(c, prune ? 2 : 1);
     }
@@ -191,10 +381,23 @@ struct Eng {
     __device__ __noinline__ void pass_least(int c, int mode) {
         Cand& cd = S->c[c];
         if (cd.tab.type != 2) return;
-        uint32_t* m = mask(c);
+        maybe_flush();
+        const int mid = cd.mid;
+        const unsigned long long key = pm_key(mid, cd.tabid, 2 + mode);
+        if (tid == 0) S->tmpIdx = pm_find(key);
         if (tid < 32) { S->leastSum[tid] = 0; S->leastCnt[tid] = 0; }
         if (tid == 0) { S->leastBlocked = 0; S->leastSeen = 0; }
         __syncthreads();
+        int slot = S->tmpIdx;
+        __syncthreads();
+        if (slot >= 0) {
+            if (tid == 0) { const PVal pv = pvals[slot]; cd.mid = (uint16_t)pv.mid; cd.payload -= pv.delta; }
+            __syncthreads();
+            D4V(c, 3 + mode);
+            return;
+        }
+        slot = -1 - slot;
+        const uint32_t* m = maskp(mid);
         for (uint32_t i = tid; i < v.n; i += ENG_NT) {
             uint32_t s = v.sym[i];
             if (sym_is_match(s) && !((m[i >> 5] >> (i & 31)) & 1)) {
@@ -215,11 +418,13 @@ struct Eng {
                 }
             }
             S->tmpIdx = rem;
-            cd.payload += remSize;
+            S->red = (unsigned long long)(long long)remSize;
         }
         __syncthreads();
         const int rem = S->tmpIdx;
+        int newmid = mid;
         if (rem >= 0) {
+            uint32_t* md = maskp(S->nMasks);
             const int lane = tid & 31;
             for (uint32_t base = (tid >> 5) * 32; base < v.n; base += ENG_NT) {
                 uint32_t i = base + lane;
@@ -229,16 +434,26 @@ struct Eng {
                     rep = sym_is_match(s) && (sym_lensym(s) - 257 == rem);
                 }
                 unsigned bal = __ballot_sync(0xffffffffu, rep);
-                if (lane == 0 && bal) m[base >> 5] |= bal;
+                if (lane == 0) md[base >> 5] = m[base >> 5] | bal;
             }
+            __syncthreads();
+            newmid = intern_mask();
+        }
+        if (tid == 0) {
+            PVal pv; pv.mid = (uint32_t)newmid; pv.pad = 0; pv.delta = -(long long)S->red;
+            pvals[slot] = pv;
+            S->pkey[slot] = key;
+            S->nP++;
+            cd.mid = (uint16_t)newmid;
+            cd.payload -= pv.delta;
         }
         __syncthreads();
         D4V(c, 3 + mode);
     }
 
-    // histogram of candidate c's symbol list into S->hist
-    __device__ __noinline__ void pass_hist(int c) {
-        const uint32_t* m = mask(c);
+    // histogram of the symbol list with mask `mid` into S->hist
+    __device__ __noinline__ void pass_hist(int mid) {
+        const uint32_t* m = maskp(mid);
         for (int k = tid; k < 320; k += ENG_NT) S->hist[k] = 0;
         __syncthreads();
         for (uint32_t i = tid; i < v.n; i += ENG_NT) {
@@ -280,31 +495,14 @@ struct Eng {
         return r;
     }
 
-    __device__ __noinline__ unsigned long long hash_words(const uint32_t* p, int nwords32) {
-        unsigned long long h = 0;
-        for (int k = tid; k < nwords32; k += ENG_NT) {
-            unsigned long long x = (unsigned long long)p[k] + 0x9E3779B97F4A7C15ull * (unsigned long long)(k + 1);
-            x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
-            h += x;
-        }
-        for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
-        if ((tid & 31) == 0) S->hred[tid >> 5] = h;
-        __syncthreads();
-        unsigned long long r = 0;
-        for (int k = 0; k < ENG_NT / 32; k++) r += S->hred[k];
-        __syncthreads();
-        return r | 1ull;
-    }
-
 #ifdef D4_VERIFY
     int* vgerr = nullptr;
     int vjob = -1;
     // debug: payload of candidate c recomputed from its mask and tables; first mismatch is recorded
     __device__ __noinline__ void verify(int c, int opcode) {
         __syncthreads();
-        uint32_t save[2] = {0, 0};
         // pass_hist/hist_payload clobber S->hist and S->red only
-        pass_hist(c);
+        pass_hist(S->c[c].mid);
         long long t = hist_payload(S->c[c].tab);
         if (tid == 0 && t != S->c[c].payload) {
             if (atomicMax(vgerr, 14) < 13) {
@@ -312,42 +510,26 @@ struct Eng {
                 vgerr[6] = (int)blockIdx.x; vgerr[7] = (int)S->candIndex;
             }
         }
-        (void)save;
         __syncthreads();
     }
 #endif
 
-    // ---- recodeHuffman (:670-743) on candidate c: tables from the histogram, payload, default header
+    // ---- recodeHuffman (:670-743) on candidate c: tables from the histogram, payload, default header.
+    //      The result is a function of the symbol list alone -> cached per mask id.
     __device__ __noinline__ void op_recode(int c) {
-        pass_hist(c);
-        unsigned long long h = hash_words(S->hist, 320);
-        // memo lookup (exact: the histogram is compared in full on a hash hit)
-        if (tid == 0) S->tmpIdx = -1;
-        __syncthreads();
-        for (int k = tid; k < S->memoH_n; k += ENG_NT)
-            if (S->memoH_hash[k] == h) atomicMax(&S->tmpIdx, k);
-        __syncthreads();
-        int hit = S->tmpIdx;
-        if (hit >= 0) {
-            if (tid == 0) S->redAny = 0;
-            __syncthreads();
-            const uint32_t* mh = memoH[hit].hist;
-            bool diff = false;
-            for (int k = tid; k < 320; k += ENG_NT) diff |= (mh[k] != S->hist[k]);
-            if (diff) S->redAny = 1;
-            __syncthreads();
-            if (S->redAny) hit = -1;
-            __syncthreads();
-        }
-        if (hit >= 0) {
-            const uint32_t* s = (const uint32_t*)&memoH[hit].result;
+        maybe_flush();
+        Cand& cd = S->c[c];
+        const int mid = cd.mid;
+        if (S->recodeValid[mid]) {
+            const uint32_t* s = (const uint32_t*)&recode[mid];
             uint32_t* d = (uint32_t*)&S->c[c];
+            __syncthreads();
             for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
             __syncthreads();
             D4V(c, 5);
             return;
         }
-        Cand& cd = S->c[c];
+        pass_hist(mid);
         // trailing zero-frequency trimming + the distance special cases (:683-740)
         if (tid == 0) {
             int nl = 286;
@@ -371,7 +553,7 @@ struct Eng {
             }
         }
         __syncthreads();
-        if (tid == 0) cd.tab.type = 2;
+        if (tid == 0) { cd.tab.type = 2; cd.tab.pad[0] = cd.tab.pad[1] = cd.tab.pad[2] = 0; }
         __syncthreads();
         long long pay = hist_payload(cd.tab);
         if (tid == 0) {
@@ -380,22 +562,12 @@ struct Eng {
             if (hdr_rewrite(cd.tab, FLAGS_DEFAULT, cd.hdr, ws)) S->err = ERR_TREE;
         }
         __syncthreads();
-        // store in the memo (FIFO replacement)
-        int slot;
-        if (tid == 0) {
-            slot = S->memoH_next;
-            S->memoH_next = (slot + 1) % MEMO_H;
-            if (S->memoH_n < MEMO_H) S->memoH_n++;
-            S->memoH_hash[slot] = h;
-            S->tmpIdx = slot;
-        }
-        __syncthreads();
-        slot = S->tmpIdx;
-        for (int k = tid; k < 320; k += ENG_NT) memoH[slot].hist[k] = S->hist[k];
+        intern_tab(c);
         {
             const uint32_t* s = (const uint32_t*)&S->c[c];
-            uint32_t* d = (uint32_t*)&memoH[slot].result;
+            uint32_t* d = (uint32_t*)&recode[mid];
             for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
+            if (tid == 0) S->recodeValid[mid] = 1;
         }
         __syncthreads();
         D4V(c, 6);
@@ -403,22 +575,49 @@ struct Eng {
     // recodeHuffmanLessMatches (:655-658)
     __device__ void op_recode_less(int c) { pass_replace(c, true); op_recode(c); }
 
-    // recodeToFixedHuffman (:637-653)
+    // recodeToFixedHuffman (:637-653); the fixed-code payload is a function of the symbol list alone
     __device__ __noinline__ void op_to_fixed(int c) {
         Cand& cd = S->c[c];
         if (cd.tab.type == 1) return;
-        pass_hist(c);
+        __syncthreads();  // every thread has read the type before thread 0 rewrites it below
+        maybe_flush();
+        const int mid = cd.mid;
+        const unsigned long long key = pm_key(mid, 0xFFFF, 4);
         if (tid == 0) {
+            S->tmpIdx = pm_find(key);
             cd.tab.type = 1; cd.tab.nL = 286; cd.tab.nD = 30;
+            cd.tab.pad[0] = cd.tab.pad[1] = cd.tab.pad[2] = 0;
             fixed_lens(cd.tab.L, cd.tab.D);
             for (int k = 286; k < MAX_LL; k++) cd.tab.L[k] = 0;
             for (int k = 30; k < MAX_D; k++) cd.tab.D[k] = 0;
             cd.hdr.np = 0; cd.hdr.ncl = 0; cd.hdr.bits = 0;
         }
         __syncthreads();
-        long long pay = hist_payload(cd.tab);
-        if (tid == 0) cd.payload = pay;
+        int slot = S->tmpIdx;
         __syncthreads();
+        if (slot >= 0) {
+            if (tid == 0) cd.payload = pvals[slot].delta;
+        } else {
+            slot = -1 - slot;
+            pass_hist(mid);
+            long long pay = hist_payload(cd.tab);
+            if (tid == 0) {
+                cd.payload = pay;
+                PVal pv; pv.mid = (uint32_t)mid; pv.pad = 0; pv.delta = pay;
+                pvals[slot] = pv;
+                S->pkey[slot] = key;
+                S->nP++;
+            }
+        }
+        __syncthreads();
+        if (S->fixedTab >= 0) {
+            if (tid == 0) cd.tabid = (uint16_t)S->fixedTab;
+            __syncthreads();
+        } else {
+            intern_tab(c);
+            if (tid == 0) S->fixedTab = cd.tabid;
+            __syncthreads();
+        }
     }
 
     // DeflateBlockHuffman.optimise (:460-469): returns bits saved
@@ -448,38 +647,16 @@ struct Eng {
 
     // ---- the 56 header strategy trials of up to 4 bases (addOptimisedRecoded, :277-316) -------------
     // bases are candidates C_B1.. (nb of them).  For each base the first-minimum strategy is looked up
-    // in / added to the Tab memo, then the virtual candidates are fed to the selection callback in the
-    // reference's order; only a winning trial is materialised.
+    // in / added to the per-tabid memo, then the virtual candidates are fed to the selection callback in
+    // the reference's order; only a winning trial is materialised.
     __device__ __noinline__ void trials(int nb) {
-        // memo lookup per base
-        __shared__ int s_hit[4];
-        __shared__ unsigned long long s_hash[4];
-        for (int b = 0; b < nb; b++) {
-            unsigned long long h = hash_words((const uint32_t*)&S->c[C_B1 + b].tab, (int)(sizeof(Tab) / 4));
-            if (tid == 0) { s_hash[b] = h; s_hit[b] = -1; }
-            __syncthreads();
-            for (int k = tid; k < S->memoT_n; k += ENG_NT)
-                if (S->memoT_hash[k] == h) atomicMax(&s_hit[b], k);
-            __syncthreads();
-            int hit = s_hit[b];
-            if (g_trace) { hit = -1; __syncthreads(); if (tid == 0) s_hit[b] = -1; __syncthreads(); }
-            if (hit >= 0) {
-                if (tid == 0) S->redAny = 0;
-                __syncthreads();
-                const uint32_t* a = (const uint32_t*)&memoT[hit];
-                const uint32_t* q = (const uint32_t*)&S->c[C_B1 + b].tab;
-                bool diff = false;
-                for (int k = tid; k < (int)(sizeof(Tab) / 4); k += ENG_NT) diff |= a[k] != q[k];
-                if (diff) S->redAny = 1;
-                __syncthreads();
-                if (S->redAny && tid == 0) s_hit[b] = -1;
-                __syncthreads();
-            }
-        }
+        __shared__ int s_miss[4];
+        if (tid < nb) s_miss[tid] = (S->tabTrialBits[S->c[C_B1 + tid].tabid] == TRIAL_UNSET) || g_trace != nullptr;
+        __syncthreads();
         // evaluate the misses: thread j -> (base j / 56, strategy j % 56)
         {
             int j = tid;
-            if (j < nb * 56 && s_hit[j / 56] < 0) {
+            if (j < nb * 56 && s_miss[j / 56]) {
                 Hdr h;
                 TreeWsCL ws;
                 if (hdr_trial(S->c[C_B1 + j / 56].tab, c_trial_flags[j % 56], h, ws)) S->err = ERR_TREE;
@@ -491,42 +668,19 @@ struct Eng {
             for (int b = 0; b < nb; b++)
                 for (int k = 0; k < 56; k++) trace_put(S->candIndex + b * 56 + k, S->c[C_B1 + b].payload + S->trialBits[b * 56 + k]);
         __syncthreads();
-        if (tid < nb && s_hit[tid] < 0) {
+        if (tid < nb && s_miss[tid]) {
             int best = 0x7fffffff, arg = 0;
             for (int k = 0; k < 56; k++) { int bts = S->trialBits[tid * 56 + k]; if (bts < best) { best = bts; arg = k; } }
-            S->trialBits[tid * 56] = best;
-            S->trialBits[tid * 56 + 1] = arg;
+            const int t = S->c[C_B1 + tid].tabid;   // two bases with one Tab write the same values
+            S->tabTrialBits[t] = best;
+            S->tabTrialArg[t] = (unsigned char)arg;
         }
         __syncthreads();
-        for (int b = 0; b < nb; b++) {
-            // every thread must read the flag before thread 0 overwrites it below (a late reader would skip the two
-            // barriers inside and leave the CTA one barrier out of step)
-            const bool miss = s_hit[b] < 0;
-            __syncthreads();
-            if (miss) {  // insert
-                int slot;
-                if (tid == 0) {
-                    slot = S->memoT_next;
-                    S->memoT_next = (slot + 1) % MEMO_T;
-                    if (S->memoT_n < MEMO_T) S->memoT_n++;
-                    S->memoT_hash[slot] = s_hash[b];
-                    S->memoT_bits[slot] = S->trialBits[b * 56];
-                    S->memoT_arg[slot] = (unsigned char)S->trialBits[b * 56 + 1];
-                    s_hit[b] = slot;
-                }
-                __syncthreads();
-                slot = s_hit[b];
-                const uint32_t* q = (const uint32_t*)&S->c[C_B1 + b].tab;
-                uint32_t* a = (uint32_t*)&memoT[slot];
-                for (int k = tid; k < (int)(sizeof(Tab) / 4); k += ENG_NT) a[k] = q[k];
-                __syncthreads();
-            }
-        }
         // selection in reference order: base b's 56 candidates; the first minimum is the only one that
         // can replace the incumbent
         for (int b = 0; b < nb; b++) {
-            const int slot = s_hit[b];
-            const int bits = S->memoT_bits[slot], arg = S->memoT_arg[slot];
+            const int t = S->c[C_B1 + b].tabid;
+            const int bits = S->tabTrialBits[t], arg = S->tabTrialArg[t];
             const long long sz = S->c[C_B1 + b].payload + bits;
             const bool better = sz < S->bestSize;
             __syncthreads();

@@ -76,10 +76,11 @@ __global__ void k_init_state(const BlockRec* __restrict__ recs, const StreamDesc
     b.size_bits = (long long)(r.end_bit - r.hdr_bit) - 3;
 }
 
-struct EngScratch {
-    uint32_t* masks;      // per CTA: NCAND * maxwords
-    MemoHEntry* memoH;    // per CTA: MEMO_H
-    Tab* memoT;           // per CTA: MEMO_T
+struct EngScratch {       // global scratch, one slice per CTA
+    uint32_t* masks;      // (MAXM + NCAND) * maxwords
+    Tab* tabs;            // MAXT
+    Cand* recode;         // MAXM
+    PVal* pvals;          // MEMO_P
     uint32_t maxwords;
 };
 
@@ -87,21 +88,32 @@ __device__ inline void eng_init(Eng& e, EngSmem* S, const EngScratch& sc, int ct
     e.S = S;
     e.tid = threadIdx.x;
     e.maxwords = sc.maxwords;
-    e.masks = sc.masks + (size_t)cta * NCAND * sc.maxwords;
-    e.memoH = sc.memoH + (size_t)cta * MEMO_H;
-    e.memoT = sc.memoT + (size_t)cta * MEMO_T;
-    if (threadIdx.x == 0) { S->memoH_n = 0; S->memoH_next = 0; S->memoT_n = 0; S->memoT_next = 0; S->err = 0; }
+    e.masks = sc.masks + (size_t)cta * (MAXM + NCAND) * sc.maxwords;
+    e.tabs = sc.tabs + (size_t)cta * MAXT;
+    e.recode = sc.recode + (size_t)cta * MAXM;
+    e.pvals = sc.pvals + (size_t)cta * MEMO_P;
+    if (threadIdx.x == 0) S->err = 0;
+    __syncthreads();
+}
+
+// the mask in pool slot 0 (written by the caller) becomes mask id 0 of a new block, held by C_B
+__device__ inline void eng_adopt_mask0(Eng& e) {
+    __syncthreads();
+    const unsigned long long h = e.hash_words(e.maskp(0), (int)e.v.nwords);
+    if (e.tid == 0) { e.S->maskHash[0] = h; e.S->recodeValid[0] = 0; e.S->nMasks = 1; e.S->c[C_B].mid = 0; }
     __syncthreads();
 }
 
 // load BlkState b into candidate slot C_B with the given mask source (pool words, or nullptr = zeros)
 __device__ inline void eng_load(Eng& e, const BlkState& b, const uint32_t* maskSrc) {
+    e.begin_block();
     const uint32_t* s = (const uint32_t*)&b.cand;
     uint32_t* d = (uint32_t*)&e.S->c[C_B];
     for (int k = e.tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
-    uint32_t* m = e.mask(C_B);
+    uint32_t* m = e.maskp(0);
     for (uint32_t k = e.tid; k < e.v.nwords; k += ENG_NT) m[k] = maskSrc ? maskSrc[k] : 0u;
-    __syncthreads();
+    eng_adopt_mask0(e);
+    e.intern_tab(C_B);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -143,7 +155,7 @@ k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __rest
             const bool improved = S.bestSize < S.sizeI;
             __syncthreads();
             if (improved && !S.bestStored) {  // self-check: the winner's payload recomputed from its symbol list
-                e.pass_hist(C_BEST);
+                e.pass_hist(S.c[C_BEST].mid);
                 const long long truePay = e.hist_payload(S.c[C_BEST].tab);
                 if (truePay != S.c[C_BEST].payload && tid == 0) {
                     if (atomicMax(gerr, 13) < 13) {
@@ -164,7 +176,7 @@ k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __rest
             const uint32_t* s = (const uint32_t*)&S.c[C_B];
             uint32_t* d = (uint32_t*)&b.cand;
             for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
-            const uint32_t* m = e.mask(C_B);
+            const uint32_t* m = e.maskp(S.c[C_B].mid);
             uint32_t* pm = maskpool + b.mask_off;
             for (uint32_t k = tid; k < e.v.nwords; k += ENG_NT) pm[k] = m[k];
             if (tid == 0) b.nrounds = r;
@@ -178,20 +190,15 @@ k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __rest
 // --------------------------------------------------------------------------------------------------
 // k_finish: replay + merge + layout, one CTA per stream
 // --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ENG_NT)
-k_finish(StreamState* __restrict__ streams, BlkState* __restrict__ bs, const RoundLog* __restrict__ logs,
-         uint32_t* __restrict__ sym, const uint32_t* __restrict__ symout, const uint8_t* __restrict__ out,
-         uint32_t* __restrict__ maskpool, EngScratch sc, int merge, int* __restrict__ gerr) {
-    __shared__ EngSmem S;
+__device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __restrict__ bs, const RoundLog* __restrict__ logs,
+                              uint32_t* __restrict__ sym, const uint32_t* __restrict__ symout, const uint8_t* __restrict__ out,
+                              uint32_t* __restrict__ maskpool, int merge, int* __restrict__ gerr) {
     __shared__ long long s_pos, s_saved;
     __shared__ int s_cur, s_next, s_do, s_first;
-    StreamState& st = streams[blockIdx.x];
     if (!st.selected || st.status != ST_OK) return;
     const int tid = threadIdx.x;
     BlkState* B = bs + st.blk_base;
     const uint32_t nb = st.n_blocks;
-    Eng e;
-    if (merge) eng_init(e, &S, sc, blockIdx.x);
 
     // ---- replay of DeflateStream.optimise (:496-566) with the real bit position --------------------
     if (tid == 0) {
@@ -304,7 +311,8 @@ k_finish(StreamState* __restrict__ streams, BlkState* __restrict__ bs, const Rou
                 e.v.n = nA + nB;
                 e.v.nwords = (nA + nB + 31) / 32;
                 e.v.ulen = c.out_len + nx.out_len;
-                uint32_t* m = e.mask(C_B);
+                e.begin_block();
+                uint32_t* m = e.maskp(0);
                 for (uint32_t k = tid; k < e.v.nwords; k += ENG_NT) m[k] = 0;
                 __syncthreads();
                 const uint32_t* ma = maskpool + c.mask_off;
@@ -314,7 +322,7 @@ k_finish(StreamState* __restrict__ streams, BlkState* __restrict__ bs, const Rou
                 for (uint32_t i = tid; i < nB; i += ENG_NT)
                     if ((mb[i >> 5] >> (i & 31)) & 1) atomicOr(&m[(nA + i) >> 5], 1u << ((nA + i) & 31));
                 if (tid == 0) { S.c[C_B].tab.type = 2; S.c[C_B].payload = 0; S.c[C_B].hdr.bits = 0; }
-                __syncthreads();
+                eng_adopt_mask0(e);
                 e.op_to_fixed(C_B);  // both halves recoded to the fixed code; payload from the histogram
                 const long long pos = s_pos;
                 e.optimise_block(stored_size(e.v.ulen, pos));
@@ -331,7 +339,7 @@ k_finish(StreamState* __restrict__ streams, BlkState* __restrict__ bs, const Rou
                         const uint32_t* s = (const uint32_t*)&S.c[C_BEST];
                         uint32_t* d = (uint32_t*)&c.cand;
                         for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
-                        const uint32_t* bm = e.mask(C_BEST);
+                        const uint32_t* bm = e.maskp(S.c[C_BEST].mid);
                         uint32_t* pm = maskpool + c.mask_off;
                         for (uint32_t k = tid; k < e.v.nwords; k += ENG_NT) pm[k] = bm[k];
                     }
@@ -359,7 +367,7 @@ k_finish(StreamState* __restrict__ streams, BlkState* __restrict__ bs, const Rou
             }
             __syncthreads();
         }
-        if (S.err && tid == 0) atomicMax(gerr, S.err);
+        if (S.err && tid == 0) { atomicMax(gerr, S.err); S.err = 0; }
     }
     __syncthreads();
 
@@ -380,6 +388,25 @@ k_finish(StreamState* __restrict__ streams, BlkState* __restrict__ bs, const Rou
         if (last >= 0) B[last].bfinal = 1;
         st.total_bits = (uint64_t)size;
         st.saved_bits = s_saved;
+    }
+}
+
+// streams are taken from a queue by a grid sized to the machine, so the engine scratch is per CTA, not per stream
+__global__ void __launch_bounds__(ENG_NT)
+k_finish(StreamState* __restrict__ streams, uint32_t nstreams, BlkState* __restrict__ bs, const RoundLog* __restrict__ logs,
+         uint32_t* __restrict__ sym, const uint32_t* __restrict__ symout, const uint8_t* __restrict__ out,
+         uint32_t* __restrict__ maskpool, EngScratch sc, int merge, unsigned* __restrict__ counter, int* __restrict__ gerr) {
+    __shared__ EngSmem S;
+    __shared__ uint32_t s_job;
+    Eng e;
+    if (merge) eng_init(e, &S, sc, blockIdx.x);
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_job = atomicAdd(counter, 1u);
+        __syncthreads();
+        const uint32_t job = s_job;
+        if (job >= nstreams) break;
+        finish_stream(S, e, streams[job], bs, logs, sym, symout, out, maskpool, merge, gerr);
     }
 }
 

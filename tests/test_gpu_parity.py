@@ -251,3 +251,40 @@ def test_c3_batch_properties(gpu):
         assert r["status"] == 0
         assert zlib.decompress(r["out"], -15) == zlib.decompress(raw, -15)
         assert len(r["out"]) <= len(raw)
+
+
+# ---- engine pool overflow: the same library built with tiny pools (-DD4_SMALL_POOLS) -----------------------------
+_SMALLPOOL_SCRIPT = r"""
+import io, sys, zlib
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+import workloads as W, oracle_lib
+from conftest import GOLDEN_PAIRS, read_golden
+import deft4j_b200
+from deft4j_b200.container import getContainerForBytes
+for inp, gold, merge in GOLDEN_PAIRS:
+    data = read_golden(inp)
+    cont = getContainerForBytes(data, inp, deft4j_b200.DeflateStream)
+    assert cont.read(data)
+    cont.optimise(merge, io.StringIO())
+    assert cont.write() == read_golden(gold), inp
+co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
+raw = co.compress(W.c2_text(300000)) + co.flush()
+for merge in (False, True):
+    r = deft4j_b200.optimise_batch([raw], merge)[0]
+    o = oracle_lib.OracleDeflateStream(); assert o.parse(raw)
+    assert r["saved_bits"] == o.optimise(merge) and r["out"] == o.asBytes()
+print("SMALLPOOLS-OK")
+"""
+
+
+def test_engine_pool_overflow_path(gpu):
+    """The engine's hash-consed mask/table pools and pass memo are flushed when full; with pools of 20 entries
+    every block of the fixtures overflows them many times, and the output must not change."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "deft4j_b200", "libdeft4cu_smallpools.so")
+    assert os.path.exists(lib), "run __graft_entry__.build()"
+    env = dict(os.environ, DEFT4CU_LIB=lib)
+    p = subprocess.run([sys.executable, "-c", _SMALLPOOL_SCRIPT % {"root": root, "tests": os.path.join(root, "tests")}],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "SMALLPOOLS-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
