@@ -129,16 +129,30 @@ struct ChunkRec {
     uint32_t n;           // symbols in the chunk
 };
 
-struct StreamDesc {
-    uint64_t in_off, in_len;        // bytes in the batch input buffer
+// A stream is parsed by one or more "walkers": the input is cut into segments, walker j of a stream
+// starts at the first plausible block header inside segment j (k_find; walker 0 at bit 0) and walks
+// blocks until it reaches a block boundary at or beyond its segment's end.  The host then follows the
+// chain from walker 0: a walker is valid iff its predecessor ended exactly where it started; a missing
+// or wrong start is re-walked from the known position (deft4cu.cu, Batch::parse).
+constexpr uint64_t BIT_NONE = ~0ull;
+struct StreamDesc {                 // one per walker
+    uint64_t in_off, in_len;        // the whole stream: bytes in the batch input buffer
+    uint64_t start_bit, stop_bit;   // first block header of this walker (BIT_NONE: nothing to do); segment end
     uint64_t blk_base, blk_cap;     // BlockRec slots
     uint64_t chunk_base, chunk_cap; // ChunkRec slots
     uint64_t sym_base, out_base;    // pool bases (filled before emit)
+    uint64_t stream_out_base;       // pool offset of the stream's first decoded byte
+    uint32_t walker0, nseg;         // the walkers of this stream are [walker0, walker0 + nseg)
+    uint32_t spec;                  // 1: speculative start (from k_find); 0: known block boundary
+    uint32_t pad;
 };
-struct StreamInfo {                 // result of the count pass
+struct StreamInfo {                 // result of the count pass (per walker); the host aggregates per stream
     int32_t status;
     uint32_t n_blocks;
     uint64_t n_syms, out_len, consumed, n_chunks, total_bits;
+    uint64_t end_bit;               // walker: bit position where it stopped (next block header / end of stream)
+    uint32_t final_seen;            // walker: stopped at BFINAL
+    uint32_t pad;
 };
 
 // ---- little bit reader ----------------------------------------------------------------------------

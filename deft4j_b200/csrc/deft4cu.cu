@@ -214,54 +214,164 @@ class Batch {
         return DEFT4CU_OK;
     }
 
-    // ---- parse: count, emit, LZ77 resolve, model init ------------------------------------------------
+    // ---- parse: find block boundaries, count (walkers), emit, LZ77 resolve, model init ---------------------
+    std::vector<StreamDesc> wdescs;     // per walker (device copy: d_descs)
+    std::vector<StreamInfo> winfos;     // per walker
+    std::vector<uint32_t> chain;        // valid walkers, stream after stream, in stream order
+    std::vector<uint32_t> chain_off;    // n + 1 offsets into chain
+    uint32_t parse_rewalks = 0, parse_walkers = 0;
+
     int parse() {
         release_model();
         cudaEvent_t ev[4];
         for (auto& e : ev) cudaEventCreate(&e);
         descs.assign(n + 1, StreamDesc{});
         infos.assign(n, StreamInfo{});
-        D4_CUDA_CHECK(dalloc(&d_descs, (size_t)n + 1, cs));
-        D4_CUDA_CHECK(dalloc(&d_infos, n, cs));
         D4_CUDA_CHECK(dalloc(&d_gerr, 8, cs));
         D4_CUDA_CHECK(cudaMemsetAsync(d_gerr, 0, 8 * sizeof(int), cs));
-        std::vector<uint64_t> bcap(n), ccap(n);
+        // ---- walkers: one per segment of each stream -------------------------------------------------------
+        uint64_t seg_bytes = 128 << 10;
+        if (const char* e = getenv("D4_SEG_BYTES")) seg_bytes = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
+        const uint64_t seg_bits = seg_bytes * 8;
+        const uint64_t spec_max_bits = 4 * seg_bits + (1 << 20);
+        wdescs.clear();
+        std::vector<uint32_t> w0(n), spec_list, all_list;
         for (uint32_t i = 0; i < n; i++) {
-            bcap[i] = in_len[i] / 4096 + 8;
-            ccap[i] = in_len[i] * 8 / CHUNK_BITS + bcap[i] + 8;
+            const uint32_t nseg = in_len[i] <= seg_bytes ? 1u : (uint32_t)((in_len[i] + seg_bytes - 1) / seg_bytes);
+            w0[i] = (uint32_t)wdescs.size();
+            for (uint32_t j = 0; j < nseg; j++) {
+                StreamDesc d{};
+                d.in_off = in_off[i]; d.in_len = in_len[i];
+                d.start_bit = j == 0 ? 0 : BIT_NONE;
+                d.stop_bit = nseg == 1 ? BIT_NONE : (uint64_t)(j + 1) * seg_bits;
+                d.walker0 = w0[i]; d.nseg = nseg; d.spec = j == 0 ? 0 : 1;
+                if (nseg == 1) { d.blk_cap = in_len[i] / 4096 + 8; d.chunk_cap = in_len[i] * 8 / CHUNK_BITS + d.blk_cap + 8; }
+                else { d.blk_cap = seg_bytes / 2048 + 8; d.chunk_cap = 4 * seg_bits / CHUNK_BITS + d.blk_cap + 8; }
+                if (j) spec_list.push_back((uint32_t)wdescs.size());
+                all_list.push_back((uint32_t)wdescs.size());
+                wdescs.push_back(d);
+            }
         }
+        const uint32_t W = (uint32_t)wdescs.size();
+        parse_walkers = W; parse_rewalks = 0;
+        std::vector<uint32_t> wstream(W);
+        for (uint32_t i = 0; i < n; i++) for (uint32_t j = 0; j < wdescs[w0[i]].nseg; j++) wstream[w0[i] + j] = i;
+        winfos.assign(W, StreamInfo{});
+        uint32_t* d_list = nullptr;
+        D4_CUDA_CHECK(dalloc(&d_descs, (size_t)W, cs));
+        D4_CUDA_CHECK(dalloc(&d_infos, (size_t)W, cs));
+        D4_CUDA_CHECK(dalloc(&d_list, (size_t)W, cs));
         cudaEventRecord(ev[0], cs);
-        for (int attempt = 0; attempt < 2; attempt++) {
+        if (!spec_list.empty()) {
+            D4_CUDA_CHECK(cudaMemcpyAsync(d_descs, wdescs.data(), sizeof(StreamDesc) * W, cudaMemcpyHostToDevice, cs));
+            D4_CUDA_CHECK(cudaMemcpyAsync(d_list, spec_list.data(), 4 * spec_list.size(), cudaMemcpyHostToDevice, cs));
+            LAUNCH(k_find, (unsigned)spec_list.size(), FIND_NT, cs, d_in, d_descs, d_list, seg_bits);
+            // the candidate starts come back to the host: the chain below compares them with the true boundaries
+            std::vector<StreamDesc> tmp(W);
+            D4_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), d_descs, sizeof(StreamDesc) * W, cudaMemcpyDeviceToHost, cs));
+            D4_CUDA_CHECK(cudaStreamSynchronize(cs));
+            for (uint32_t w : spec_list) wdescs[w].start_bit = tmp[w].start_bit;
+        }
+        chain.clear(); chain_off.assign(n + 1, 0);
+        std::vector<std::vector<uint32_t>> chains(n);
+        std::vector<uint8_t> trunc(n, 0);
+        for (int attempt = 0;; attempt++) {
             uint64_t bt = 0, ct = 0;
-            for (uint32_t i = 0; i < n; i++) {
-                descs[i].in_off = in_off[i]; descs[i].in_len = in_len[i];
-                descs[i].blk_base = bt; descs[i].blk_cap = bcap[i]; bt += bcap[i];
-                descs[i].chunk_base = ct; descs[i].chunk_cap = ccap[i]; ct += ccap[i];
+            for (uint32_t w = 0; w < W; w++) {
+                wdescs[w].blk_base = bt; bt += wdescs[w].blk_cap;
+                wdescs[w].chunk_base = ct; ct += wdescs[w].chunk_cap;
             }
             dfree(d_blocks, cs); dfree(d_chunks, cs);
             D4_CUDA_CHECK(dalloc(&d_blocks, bt, cs));
             D4_CUDA_CHECK(dalloc(&d_chunks, ct, cs));
-            D4_CUDA_CHECK(cudaMemcpyAsync(d_descs, descs.data(), sizeof(StreamDesc) * (n + 1), cudaMemcpyHostToDevice, cs));
-            if (n) LAUNCH(k_count, n, PARSE_NT, cs, d_in, d_descs, d_infos, d_blocks, d_chunks);
-            D4_CUDA_CHECK(cudaMemcpyAsync(infos.data(), d_infos, sizeof(StreamInfo) * n, cudaMemcpyDeviceToHost, cs));
+            D4_CUDA_CHECK(cudaMemcpyAsync(d_descs, wdescs.data(), sizeof(StreamDesc) * W, cudaMemcpyHostToDevice, cs));
+            D4_CUDA_CHECK(cudaMemcpyAsync(d_list, all_list.data(), 4 * (size_t)W, cudaMemcpyHostToDevice, cs));
+            if (W) LAUNCH(k_count, W, PARSE_NT, cs, d_in, d_descs, d_infos, d_blocks, d_chunks, d_list, seg_bits, spec_max_bits);
+            D4_CUDA_CHECK(cudaMemcpyAsync(winfos.data(), d_infos, sizeof(StreamInfo) * W, cudaMemcpyDeviceToHost, cs));
             D4_CUDA_CHECK(cudaStreamSynchronize(cs));
-            bool again = false;
-            for (uint32_t i = 0; i < n; i++) {
-                if (infos[i].status != ST_OK) continue;
-                if (infos[i].n_blocks > bcap[i] || infos[i].n_chunks > ccap[i]) {
-                    again = true;
-                    bcap[i] = infos[i].n_blocks; ccap[i] = infos[i].n_chunks;
+            // ---- follow every stream's chain from walker 0; re-walk what was guessed wrong ---------------------
+            std::vector<uint32_t> cur(n), pending;
+            std::vector<uint8_t> fin(n, 0);
+            for (uint32_t i = 0; i < n; i++) { chains[i].assign(1, w0[i]); cur[i] = w0[i]; }
+            bool overflow = false;
+            while (true) {
+                pending.clear();
+                for (uint32_t i = 0; i < n; i++) {
+                    if (fin[i]) continue;
+                    while (true) {
+                        const StreamInfo& wi = winfos[cur[i]];
+                        const StreamDesc& wd = wdescs[cur[i]];
+                        if (wi.n_blocks > wd.blk_cap || wi.n_chunks > wd.chunk_cap) { overflow = true; fin[i] = 1; break; }
+                        if (wi.status != ST_OK || wi.final_seen) { fin[i] = 1; break; }
+                        if (wi.end_bit + 3 > in_len[i] * 8) { fin[i] = 2; break; }  // no room for another block header (:81-84)
+                        uint64_t j = wi.end_bit / seg_bits;
+                        if (j >= wd.nseg) j = wd.nseg - 1;
+                        const uint32_t nx = w0[i] + (uint32_t)j;
+                        if (nx <= cur[i]) {  // cannot happen (a walker stops at or past its segment end); refuse rather than loop
+                            set_error("parse chain did not advance");
+                            return DEFT4CU_ERR_CUDA;
+                        }
+                        chains[i].push_back(nx);
+                        cur[i] = nx;
+                        if (wdescs[nx].start_bit == wi.end_bit && winfos[nx].status != ST_NONE && winfos[nx].status != ST_ABORT)
+                            continue;  // guessed right
+                        wdescs[nx].start_bit = wi.end_bit;
+                        wdescs[nx].spec = 0;
+                        pending.push_back(nx);
+                        break;
+                    }
                 }
+                if (pending.empty()) break;
+                parse_rewalks += (uint32_t)pending.size();
+                for (uint32_t w : pending)
+                    D4_CUDA_CHECK(cudaMemcpyAsync(d_descs + w, &wdescs[w], sizeof(StreamDesc), cudaMemcpyHostToDevice, cs));
+                D4_CUDA_CHECK(cudaMemcpyAsync(d_list, pending.data(), 4 * pending.size(), cudaMemcpyHostToDevice, cs));
+                LAUNCH(k_count, (unsigned)pending.size(), PARSE_NT, cs, d_in, d_descs, d_infos, d_blocks, d_chunks, d_list, seg_bits, spec_max_bits);
+                for (uint32_t w : pending)
+                    D4_CUDA_CHECK(cudaMemcpyAsync(&winfos[w], d_infos + w, sizeof(StreamInfo), cudaMemcpyDeviceToHost, cs));
+                D4_CUDA_CHECK(cudaStreamSynchronize(cs));
             }
-            if (!again) break;
-            if (attempt == 1) { set_error("block/chunk capacity retry failed"); return DEFT4CU_ERR_CUDA; }
+            for (uint32_t i = 0; i < n; i++) trunc[i] = fin[i] == 2;
+            if (!overflow) break;
+            if (attempt == 3) { set_error("block/chunk capacity retry failed"); return DEFT4CU_ERR_CUDA; }
+            // record slots ran out somewhere on a chain: size every walker that has run for what it reported (the
+            // starts found so far are kept, so the next attempt follows the same chain without guessing again)
+            for (uint32_t w = 0; w < W; w++) {
+                if (winfos[w].status == ST_NONE) continue;
+                wdescs[w].blk_cap = std::max<uint64_t>(wdescs[w].blk_cap, winfos[w].n_blocks + 8);
+                wdescs[w].chunk_cap = std::max<uint64_t>(wdescs[w].chunk_cap, 2 * winfos[w].n_chunks + 8);
+            }
         }
+        // ---- per-stream totals -------------------------------------------------------------------------------
+        for (uint32_t i = 0; i < n; i++) {
+            StreamInfo& si = infos[i];
+            si = StreamInfo{};
+            si.status = ST_OK;
+            for (uint32_t w : chains[i]) {
+                const StreamInfo& wi = winfos[w];
+                si.n_blocks += wi.n_blocks; si.n_syms += wi.n_syms; si.out_len += wi.out_len; si.n_chunks += wi.n_chunks;
+                si.end_bit = wi.end_bit;
+                if (wi.status != ST_OK) { si.status = wi.status >= ST_NONE ? ST_PARSE : wi.status; break; }
+            }
+            if (trunc[i] && si.status == ST_OK) si.status = ST_PARSE;
+            if (si.out_len > 0xF0000000ull && si.status == ST_OK) si.status = ST_UNSUPPORTED;
+            si.total_bits = si.end_bit;
+            si.consumed = (si.end_bit + 7) >> 3;
+            chain_off[i] = (uint32_t)chain.size();
+            if (si.status == ST_OK) chain.insert(chain.end(), chains[i].begin(), chains[i].end());
+        }
+        chain_off[n] = (uint32_t)chain.size();
+        dfree(d_list, cs);
         cudaEventRecord(ev[1], cs);
-        // pool bases
+        // pool bases: streams back to back, inside a stream its valid walkers in chain order
         uint64_t sb = 0, ob = 0;
         for (uint32_t i = 0; i < n; i++) {
             descs[i].sym_base = sb; descs[i].out_base = ob;
-            if (infos[i].status == ST_OK) { sb += infos[i].n_syms; ob += infos[i].out_len; }
+            for (uint32_t c = chain_off[i]; c < chain_off[i + 1]; c++) {
+                StreamDesc& wd = wdescs[chain[c]];
+                wd.sym_base = sb; wd.out_base = ob; wd.stream_out_base = descs[i].out_base;
+                sb += winfos[chain[c]].n_syms; ob += winfos[chain[c]].out_len;
+            }
         }
         descs[n].sym_base = sb; descs[n].out_base = ob;
         nsym_total = sb; nout_total = ob;
@@ -270,7 +380,7 @@ class Batch {
             set_error("decoded size of the batch exceeds 4 GiB; split the batch");
             return DEFT4CU_ERR_UNSUPPORTED;
         }
-        D4_CUDA_CHECK(cudaMemcpyAsync(d_descs, descs.data(), sizeof(StreamDesc) * (n + 1), cudaMemcpyHostToDevice, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(d_descs, wdescs.data(), sizeof(StreamDesc) * W, cudaMemcpyHostToDevice, cs));
         D4_CUDA_CHECK(dalloc(&d_sym, sb, cs));
         D4_CUDA_CHECK(dalloc(&d_symout, sb, cs));
         D4_CUDA_CHECK(dalloc(&d_out, ob + 16, cs));
@@ -280,8 +390,8 @@ class Batch {
         std::vector<uint64_t> sblk_base(n);
         for (uint32_t i = 0; i < n; i++) {
             sblk_base[i] = blk_stream.size();
-            if (infos[i].status != ST_OK) continue;
-            for (uint32_t k = 0; k < infos[i].n_blocks; k++) { jobs.push_back(EmitJob{i, k}); blk_stream.push_back(i); }
+            for (uint32_t c = chain_off[i]; c < chain_off[i + 1]; c++)
+                for (uint32_t k = 0; k < winfos[chain[c]].n_blocks; k++) { jobs.push_back(EmitJob{chain[c], k}); blk_stream.push_back(i); }
         }
         nblk_total = jobs.size();
         EmitJob* d_jobs = nullptr;
@@ -327,8 +437,12 @@ class Batch {
         summ.resize(nblk_total);
         if (nblk_total) LAUNCH(k_blk_summary, (unsigned)((nblk_total + 255) / 256), 256, cs, d_blocks, d_summ, nblk_total);
         D4_CUDA_CHECK(cudaMemcpyAsync(summ.data(), d_summ, sizeof(BlkSummary) * nblk_total, cudaMemcpyDeviceToHost, cs));
-        D4_CUDA_CHECK(cudaMemcpyAsync(infos.data(), d_infos, sizeof(StreamInfo) * n, cudaMemcpyDeviceToHost, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(winfos.data(), d_infos, sizeof(StreamInfo) * W, cudaMemcpyDeviceToHost, cs));
         D4_CUDA_CHECK(cudaStreamSynchronize(cs));
+        // k_emit flags a match that reaches before the start of its stream on the walker that saw it
+        for (uint32_t i = 0; i < n; i++)
+            for (uint32_t c = chain_off[i]; c < chain_off[i + 1]; c++)
+                if (winfos[chain[c]].status != ST_OK && infos[i].status == ST_OK) infos[i].status = ST_PARSE;
         dfree(d_summ, cs); dfree(d_jobs, cs); dfree(d_chunks, cs);
         // model
         mask_offs.resize(nblk_total);
@@ -360,7 +474,7 @@ class Batch {
         D4_CUDA_CHECK(cudaMemsetAsync(d_maskpool, 0, (mo + 2) * 4, cs));
         D4_CUDA_CHECK(cudaMemcpyAsync(d_moffs, mask_offs.data(), 8 * nblk_total, cudaMemcpyHostToDevice, cs));
         D4_CUDA_CHECK(cudaMemcpyAsync(d_blk_stream, blk_stream.data(), 4 * nblk_total, cudaMemcpyHostToDevice, cs));
-        if (nblk_total) LAUNCH(k_init_state, (unsigned)((nblk_total + 127) / 128), 128, cs, d_blocks, d_descs, d_blk_stream, d_moffs, d_bs, nblk_total);
+        if (nblk_total) LAUNCH(k_init_state, (unsigned)((nblk_total + 127) / 128), 128, cs, d_blocks, d_moffs, d_bs, nblk_total);
         D4_CUDA_CHECK(cudaStreamSynchronize(cs));
         dfree(d_moffs, cs);
         float t;

@@ -51,21 +51,19 @@ __device__ __forceinline__ long long blk_size(const BlkState& b, long long align
     return b.cand.tab.type == 0 ? stored_size(b.out_len, alignment) : cand_size(b.cand);
 }
 
-__global__ void k_init_state(const BlockRec* __restrict__ recs, const StreamDesc* __restrict__ descs,
-                             const uint32_t* __restrict__ blk_stream, const uint64_t* __restrict__ mask_offs,
+__global__ void k_init_state(const BlockRec* __restrict__ recs, const uint64_t* __restrict__ mask_offs,
                              BlkState* __restrict__ bs, uint64_t nblk) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nblk) return;
     const BlockRec& r = recs[i];
-    const StreamDesc& sd = descs[blk_stream[i]];
     BlkState& b = bs[i];
     b.cand.tab = r.tab;
     b.cand.tab.type = r.type;
     b.cand.tab.pad[0] = b.cand.tab.pad[1] = b.cand.tab.pad[2] = 0;
     b.cand.hdr = r.hdr;
     b.cand.payload = r.payload_bits;
-    b.sym_off = sd.sym_base + r.sym_base;
-    b.out_off = sd.out_base + r.out_base;
+    b.sym_off = r.sym_base;   // pool indices (rebased by k_compact_blocks)
+    b.out_off = r.out_base;
     b.mask_off = mask_offs[i];
     b.out_len = r.out_len;
     b.n_sym = r.n_sym;

@@ -162,19 +162,162 @@ __device__ inline uint32_t parse_dynamic_header(const uint8_t* in, uint64_t pos,
     return (uint32_t)(p - pos);
 }
 
-// status codes shared with the host (mirror DEFT4CU_*)
-constexpr int ST_OK = 0, ST_PARSE = 1, ST_UNSUPPORTED = 3;
+// status codes shared with the host (mirror DEFT4CU_*); ST_NONE / ST_ABORT only ever describe speculative walkers
+constexpr int ST_OK = 0, ST_PARSE = 1, ST_UNSUPPORTED = 3, ST_NONE = 100, ST_ABORT = 101;
+
+// --------------------------------------------------------------------------------------------------
+// k_find: block boundaries inside a stream, found on the device.  One CTA per speculative walker scans
+// its segment for the first bit position that holds a well-formed dynamic block header: BTYPE = 2,
+// HLIT <= 29, HDIST <= 29, a COMPLETE code-length code (Kraft sum exactly 1), code lengths that decode
+// to exactly HLIT + HDIST entries, an end-of-block code, a complete litlen code and a complete (or
+// empty / single-code) distance code.  The test only has to be a good guess: a walker's result is used
+// only if the chain from bit 0 ends exactly at its start, and a boundary the test misses (fixed or
+// stored blocks, incomplete codes the reference accepts) is re-walked from the known
+// position.  Stage 1 (cheap, every bit position) runs on all threads; survivors are queued in shared
+// memory and stage 2 (full header decode) is spread over the warps.
+// --------------------------------------------------------------------------------------------------
+constexpr int FIND_NT = 256;
+constexpr int FIND_TILE = FIND_NT * 8;   // bit positions per tile
+
+__device__ __forceinline__ uint64_t funnel128(uint64_t lo, uint64_t hi, int k) {  // bits [k, k+64) of hi:lo, 0 <= k < 64
+    return k ? ((lo >> k) | (hi << (64 - k))) : lo;
+}
+
+__device__ inline bool find_full_check(const uint8_t* in, uint64_t p, uint64_t total_bits) {
+    uint64_t w = peek_bits(in, p);
+    const int nL = (int)((w >> 3) & 31) + 257, nD = (int)((w >> 8) & 31) + 1, ncl = (int)((w >> 13) & 15) + 4;
+    uint64_t q = p + 17;
+    if (q + 3ull * ncl > total_bits) return false;
+    uint64_t cw = peek_bits(in, q);
+    uint8_t cl[19];
+    for (int i = 0; i < 19; i++) cl[i] = 0;
+    for (int i = 0; i < ncl; i++) cl[c_codelen_order[i]] = (uint8_t)((cw >> (3 * i)) & 7);
+    q += 3ull * ncl;
+    // canonical decode by length (<= 7 bits)
+    int count[8], first[8], offs[8];
+    uint8_t symtab[19];
+    for (int l = 0; l < 8; l++) count[l] = 0;
+    for (int s = 0; s < 19; s++) count[cl[s]]++;
+    count[0] = 0;
+    int code = 0, off = 0;
+    for (int l = 1; l < 8; l++) { code = (code + count[l - 1]) << 1; first[l] = code; offs[l] = off; off += count[l]; }
+    {
+        int fill[8];
+        for (int l = 0; l < 8; l++) fill[l] = offs[l];
+        for (int s = 0; s < 19; s++) if (cl[s]) symtab[fill[cl[s]]++] = (uint8_t)s;
+    }
+    const int combined = nL + nD;
+    int i = 0, prev = -1, len256 = 0, nzL = 0, nzD = 0;
+    uint32_t kl = 0, kd = 0;  // Kraft sums in units of 2^-15
+    while (i < combined) {
+        if (q >= total_bits) return false;
+        w = peek_bits(in, q);
+        int c = 0, l = 0, sym = -1;
+        for (l = 1; l <= 7; l++) {
+            c = (c << 1) | (int)(w & 1);
+            w >>= 1;
+            int idx = c - first[l];
+            if (idx >= 0 && idx < count[l]) { sym = symtab[offs[l] + idx]; break; }
+        }
+        if (sym < 0) return false;
+        q += l;
+        int run = 1, val = sym;
+        if (sym == 16) { if (prev < 0) return false; run = (int)(w & 3) + 3; q += 2; val = prev; }
+        else if (sym == 17) { run = (int)(w & 7) + 3; q += 3; val = 0; }
+        else if (sym == 18) { run = (int)(w & 127) + 11; q += 7; val = 0; }
+        if (i + run > combined) return false;
+        if (val) {
+            for (int k = 0; k < run; k++) {
+                const int idx = i + k;
+                if (idx < nL) { kl += 32768u >> val; nzL++; if (idx == 256) len256 = val; }
+                else { kd += 32768u >> val; nzD++; }
+            }
+            if (kl > 32768u || kd > 32768u) return false;
+        }
+        i += run;
+        prev = val;
+    }
+    if (q > total_bits) return false;
+    if (!len256) return false;
+    if (!(kl == 32768u || (nzL == 1 && kl == 16384u))) return false;
+    if (!(kd == 32768u || nzD == 0 || (nzD == 1 && kd == 16384u))) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(FIND_NT)
+k_find(const uint8_t* __restrict__ d_in, StreamDesc* __restrict__ descs, const uint32_t* __restrict__ list, uint64_t seg_bits) {
+    const uint32_t wid = list[blockIdx.x];
+    StreamDesc& sd = descs[wid];
+    const uint8_t* in = d_in + sd.in_off;
+    const uint64_t total_bits = sd.in_len * 8;
+    const uint64_t seg_begin = (uint64_t)(wid - sd.walker0) * seg_bits;
+    uint64_t seg_end = seg_begin + seg_bits;
+    if (seg_end > total_bits) seg_end = total_bits;
+    const int t = threadIdx.x;
+    __shared__ uint16_t s_q[FIND_TILE];
+    __shared__ unsigned s_n, s_best;
+    uint64_t found = BIT_NONE;
+    for (uint64_t tile = seg_begin; tile < seg_end && found == BIT_NONE; tile += FIND_TILE) {
+        if (t == 0) { s_n = 0; s_best = 0xFFFFFFFFu; }
+        __syncthreads();
+        {   // stage 1: 8 consecutive bit positions per thread out of one 128-bit window
+            const uint8_t* a = in + (tile >> 3) + t;
+            const uint64_t* al = (const uint64_t*)((uintptr_t)a & ~(uintptr_t)7);
+            const int sh = (int)((uintptr_t)a & 7) * 8;
+            const uint64_t x0 = __ldg(al), x1 = __ldg(al + 1), x2 = __ldg(al + 2);
+            const uint64_t lo = funnel128(x0, x1, sh), hi = funnel128(x1, x2, sh);
+#pragma unroll
+            for (int s8 = 0; s8 < 8; s8++) {
+                const uint64_t p = tile + (uint64_t)t * 8 + s8;
+                if (p >= seg_end || p + 17 + 12 > total_bits) continue;
+                const uint64_t w1 = funnel128(lo, hi, s8);
+                if (((w1 >> 1) & 3) != 2) continue;
+                if (((w1 >> 3) & 31) > 29 || ((w1 >> 8) & 31) > 29) continue;
+                const int ncl = (int)((w1 >> 13) & 15) + 4;
+                const uint64_t cw = funnel128(lo, hi, s8 + 17);
+                int kraft = 0;
+                for (int i = 0; i < ncl; i++) {
+                    const int v = (int)((cw >> (3 * i)) & 7);
+                    kraft += v ? (128 >> v) : 0;
+                }
+                if (kraft != 128) continue;
+                s_q[atomicAdd(&s_n, 1u)] = (uint16_t)(t * 8 + s8);
+            }
+        }
+        __syncthreads();
+        const unsigned cnt = s_n;
+        // stage 2: queue entry e -> lane e / 8 of warp e % 8, so few survivors land in different warps
+        for (unsigned e = (unsigned)(t & 31) * 8 + (unsigned)(t >> 5); e < cnt; e += FIND_NT) {
+            const unsigned rel = s_q[e];
+            if (rel < s_best && find_full_check(in, tile + rel, total_bits)) atomicMin(&s_best, rel);
+        }
+        __syncthreads();
+        if (s_best != 0xFFFFFFFFu) found = tile + s_best;
+        __syncthreads();
+    }
+    if (t == 0) sd.start_bit = found;
+}
 
 // --------------------------------------------------------------------------------------------------
 // k_count: one CTA per stream.
 // --------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PARSE_NT, 1)
 k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, StreamInfo* __restrict__ infos,
-        BlockRec* __restrict__ blocks, ChunkRec* __restrict__ chunks) {
-    const int sid = blockIdx.x, t = threadIdx.x;
+        BlockRec* __restrict__ blocks, ChunkRec* __restrict__ chunks, const uint32_t* __restrict__ list,
+        uint64_t seg_bits, uint64_t spec_max_bits) {
+    const int sid = (int)list[blockIdx.x], t = threadIdx.x;
     const StreamDesc sd = descs[sid];
     const uint8_t* in = d_in + sd.in_off;
     const uint64_t total_bits = sd.in_len * 8;
+    if (sd.start_bit == BIT_NONE) {  // speculative walker without a candidate header in its segment
+        if (t == 0) {
+            StreamInfo si;
+            si.status = ST_NONE; si.n_blocks = 0; si.n_syms = 0; si.out_len = 0; si.consumed = 0; si.n_chunks = 0;
+            si.total_bits = 0; si.end_bit = BIT_NONE; si.final_seen = 0; si.pad = 0;
+            infos[sid] = si;
+        }
+        return;
+    }
 
     __shared__ DecTab s_lit, s_dst, s_fixlit, s_fixdst;
     __shared__ BlockRec s_blk;
@@ -193,7 +336,7 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
         build_dectab(L, 288, s_fixlit);
         build_dectab(D, 30, s_fixdst);
         s_status = ST_OK;
-        s_pos = 0;
+        s_pos = sd.start_bit;
     }
     __syncthreads();
 
@@ -357,6 +500,9 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
                 blk_syms += wcnt; blk_out += wout;
                 if (stop < PARSE_NT) eob_seen = true;  // EOB (or error, handled by status)
                 if (win - data_bit > 0xFFFF0000ull || blk_syms > 0x7FFF0000u) { if (t == 0) s_status = ST_UNSUPPORTED; eob_seen = true; }
+                // a speculative walker that runs far past its segment is decoding garbage (or a block too long to
+                // be worth guessing): give up, the chain re-walks it from a known boundary if it is needed
+                if (sd.spec && !eob_seen && win > sd.stop_bit + spec_max_bits) { if (t == 0) s_status = ST_ABORT; eob_seen = true; }
                 __syncthreads();
                 if (s_status != ST_OK) break;
             }
@@ -387,6 +533,18 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
         out_total += s_blk.out_len;
         n_blocks++;
         done = s_final != 0;
+        if (!done && s_pos >= sd.stop_bit) {
+            // block boundary at or past the segment end: hand over to the walker of the segment the boundary is in.
+            // A walker on a known boundary keeps going when that walker did not start here (it would have to be
+            // re-walked anyway), as long as its record slots last.
+            done = true;
+            if (!sd.spec) {
+                uint64_t j = s_pos / seg_bits;
+                if (j >= sd.nseg) j = sd.nseg - 1;
+                const uint64_t nxt = descs[sd.walker0 + j].start_bit;
+                if (nxt != s_pos && (uint64_t)n_blocks * 2 < sd.blk_cap && n_chunks * 2 < sd.chunk_cap) done = false;
+            }
+        }
         if (out_total > 0xF0000000ull) { if (t == 0) s_status = ST_UNSUPPORTED; done = true; }
         __syncthreads();
     }
@@ -399,6 +557,9 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
         si.consumed = (s_pos + 7) >> 3;
         si.n_chunks = n_chunks;
         si.total_bits = s_pos;
+        si.end_bit = s_pos;
+        si.final_seen = (s_status == ST_OK && s_final != 0) ? 1u : 0u;
+        si.pad = 0;
         infos[sid] = si;
     }
 }
@@ -450,7 +611,7 @@ k_emit(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, c
             symout[si + k] = oo;
             // a match reaching before the start of its stream: the reference dereferences a null
             // prevBlock (DeflateBlock.java:175-181); reported as a parse failure
-            if (sym_is_match(u.packed) && (uint64_t)oo - sd.out_base < (uint64_t)sym_dist(u.packed))
+            if (sym_is_match(u.packed) && (uint64_t)oo - sd.stream_out_base < (uint64_t)sym_dist(u.packed))
                 infos[job.stream].status = ST_PARSE;
             oo += u.outlen;
         }
@@ -504,9 +665,12 @@ __global__ void k_compact_blocks(const StreamDesc* __restrict__ descs, const Blo
     int lane = threadIdx.x & 31;
     if (w >= n) return;
     const EmitJob job = jobs[w];
-    const uint32_t* s = (const uint32_t*)&blocks[descs[job.stream].blk_base + job.block];
+    const StreamDesc& sd = descs[job.stream];
+    const uint32_t* s = (const uint32_t*)&blocks[sd.blk_base + job.block];
     uint32_t* d = (uint32_t*)&dst[w];
     for (int k = lane; k < (int)(sizeof(BlockRec) / 4); k += 32) d[k] = s[k];
+    __syncwarp();
+    if (lane == 0) { dst[w].sym_base += sd.sym_base; dst[w].out_base += sd.out_base; }  // walker relative -> pool index
 }
 
 __global__ void k_lz_jump(uint32_t* __restrict__ ptr, uint64_t n, int* __restrict__ changed) {

@@ -288,3 +288,36 @@ def test_engine_pool_overflow_path(gpu):
     p = subprocess.run([sys.executable, "-c", _SMALLPOOL_SCRIPT % {"root": root, "tests": os.path.join(root, "tests")}],
                        env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "SMALLPOOLS-OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+
+
+# ---- intra-stream parallel parse: tiny segments force many walkers, wrong guesses and re-walks --------------------
+@pytest.mark.parametrize("seg", [64, 200, 1000, 4096])
+def test_segmented_parse_matches_oracle(gpu, oracle, seg, monkeypatch):
+    """The stream is cut into `seg`-byte segments (default 128 KiB), every segment's walker guesses its first block
+    boundary on the device and the host follows the chain from bit 0.  Whatever the guesses, the parsed model and
+    the optimised bytes must equal the single-walker result: dynamic blocks (found), fixed / stored blocks (never
+    guessed: re-walked), empty blocks, blocks spanning many segments, truncated streams."""
+    monkeypatch.setenv("D4_SEG_BYTES", str(seg))
+    from deft4j_b200.container import getContainerForBytes
+    streams = []
+    for inp in ["asyoulik/asyoulik-gzip.txt.gz", "apng/ball.png", "deflate-store-2.txt.gz", "deflate-fixed.txt.gz"]:
+        data = read_golden(inp)
+        co = getContainerForBytes(data, inp, oracle.OracleDeflateStream)
+        assert co.read(data)
+        streams += [s.asBytes() for s in co.getDeflateStreams()][:3]
+    streams += [_deflate(W.c2_text(150_000, seed=5), 1), _deflate(W.c2_text(60_000, seed=6), 6, zlib.Z_FIXED),
+                _deflate(W.c2_text(200_000, seed=7), 0), _deflate(W.c2_text(120_000, seed=8), 9)]
+    streams += list(W.handmade_streams().values())
+    streams += [s for s in W.c5_streams() if len(s) < 60_000][:6]
+    for raw in streams:
+        compare_stream(gpu, oracle, raw, False, check_model=True)
+    # truncated input: still a parse failure, never a hang or a wrong chain
+    raw = _deflate(W.c2_text(50_000, seed=11))
+    for cut in (len(raw) // 3, len(raw) - 2):
+        assert gpu.DeflateStream().parse(raw[:cut]) is False
+    # one batch with everything: walkers of different streams side by side
+    res = gpu.optimise_batch(streams, True)
+    monkeypatch.delenv("D4_SEG_BYTES")
+    ref = gpu.optimise_batch(streams, True)
+    for a, b in zip(res, ref):
+        assert (a["status"], a["saved_bits"], a["out"], a["crc32"]) == (b["status"], b["saved_bits"], b["out"], b["crc32"])
