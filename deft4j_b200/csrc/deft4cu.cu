@@ -18,6 +18,7 @@ static void set_error(const std::string& s) { g_err = s; }
 }  // namespace d4
 
 #include "write.cuh"
+#include "checksum.cuh"
 
 namespace d4 {
 
@@ -65,79 +66,6 @@ __global__ void k_blk_summary(const BlockRec* __restrict__ recs, BlkSummary* __r
     out[i].type = recs[i].type;
     out[i].n_sym = recs[i].n_sym;
     out[i].out_len = recs[i].out_len;
-}
-
-// CRC-32 / Adler-32 of the decoded bytes on the device (GZFile.java:130-145,
-// ZLibFile.java:42-51).  One CTA per stream; each thread folds a contiguous slice, slices are combined
-// with the standard length-aware combination (crc: multiply by x^(8*len) mod P; adler: closed form).
-__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b) {  // GF(2) polynomial product mod P (reflected)
-    uint32_t r = 0;
-    for (int i = 0; i < 32; i++) {
-        if (a & 0x80000000u) r ^= b;
-        a <<= 1;
-        b = (b >> 1) ^ ((b & 1) ? 0xEDB88320u : 0);
-    }
-    return r;
-}
-__device__ inline uint32_t crc_xpow8n(uint64_t n) {  // x^(8n) mod P
-    uint32_t r = 0x80000000u;  // x^0
-    uint32_t p = 0x00800000u;  // x^8
-    while (n) {
-        if (n & 1) r = crc_mulmod(r, p);
-        p = crc_mulmod(p, p);
-        n >>= 1;
-    }
-    return r;
-}
-struct Sums { uint32_t crc; uint32_t a, b; uint64_t len; };
-
-__global__ void __launch_bounds__(256)
-k_checksums(const uint8_t* __restrict__ out, const uint64_t* __restrict__ off, const uint64_t* __restrict__ len,
-            uint32_t* __restrict__ crc_out, uint32_t* __restrict__ adler_out) {
-    __shared__ uint32_t tab[256];
-    __shared__ Sums part[256];
-    const int tid = threadIdx.x;
-    {
-        uint32_t c = (uint32_t)tid;
-        for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1) ? 0xEDB88320u : 0);
-        tab[tid] = c;
-    }
-    __syncthreads();
-    const uint8_t* p = out + off[blockIdx.x];
-    const uint64_t n = len[blockIdx.x];
-    const uint64_t per = (n + 255) / 256;
-    uint64_t lo = per * tid, hi = lo + per;
-    if (lo > n) lo = n;
-    if (hi > n) hi = n;
-    uint32_t crc = 0;  // raw register (no pre/post inversion) of this slice
-    uint32_t a = 0, b = 0;
-    uint64_t k = lo;
-    while (k < hi) {
-        uint64_t stop = k + 5552 < hi ? k + 5552 : hi;
-        for (; k < stop; k++) {
-            uint8_t v = p[k];
-            crc = tab[(crc ^ v) & 0xff] ^ (crc >> 8);
-            a += v; b += a;
-        }
-        a %= 65521u; b %= 65521u;
-    }
-    part[tid].crc = crc; part[tid].a = a; part[tid].b = b; part[tid].len = hi - lo;
-    __syncthreads();
-    if (tid == 0) {
-        // crc of concatenation: raw(A|B) = raw(A) * x^(8|B|) + raw(B), with the initial 0xFFFFFFFF folded in
-        uint32_t c = 0xFFFFFFFFu;
-        uint32_t A = 1, Bs = 0;
-        for (int t = 0; t < 256; t++) {
-            uint64_t l = part[t].len;
-            if (!l) continue;
-            c = crc_mulmod(c, crc_xpow8n(l)) ^ part[t].crc;
-            uint32_t lm = (uint32_t)(l % 65521u);
-            Bs = (uint32_t)((Bs + (uint64_t)lm * A + part[t].b) % 65521u);
-            A = (A + part[t].a) % 65521u;
-        }
-        crc_out[blockIdx.x] = ~c;
-        adler_out[blockIdx.x] = (Bs << 16) | A;
-    }
 }
 
 class Batch {
@@ -630,18 +558,35 @@ class Batch {
 
     int checksums() {
         if (have_sums) return DEFT4CU_OK;
+        static std::once_flag once;
+        std::call_once(once, [] { k_crc_init<<<1, 1>>>(); cudaDeviceSynchronize(); });
         cudaEvent_t ev[2];
         for (auto& e : ev) cudaEventCreate(&e);
         std::vector<uint64_t> off(n), len(n);
-        for (uint32_t i = 0; i < n; i++) { off[i] = descs[i].out_base; len[i] = infos[i].status == ST_OK ? infos[i].out_len : 0; }
+        std::vector<CkJob> jobs;
+        for (uint32_t i = 0; i < n; i++) {
+            off[i] = descs[i].out_base; len[i] = infos[i].status == ST_OK ? infos[i].out_len : 0;
+            const uint64_t c0 = off[i] >> CK_CELL_LOG2, c1 = (off[i] + len[i]) >> CK_CELL_LOG2;
+            const uint64_t cells = c1 > c0 ? c1 - c0 : 0;
+            const uint32_t nj = (uint32_t)std::max<uint64_t>(1, (cells + CK_NT - 1) / CK_NT);
+            for (uint32_t c = 0; c < nj; c++) jobs.push_back(CkJob{i, c});
+        }
         uint64_t *d_off = nullptr, *d_len = nullptr;
         uint32_t *d_crc = nullptr, *d_ad = nullptr;
+        CkJob* d_jobs = nullptr;
+        CkAcc* d_acc = nullptr;
         D4_CUDA_CHECK(dalloc(&d_off, n, cs)); D4_CUDA_CHECK(dalloc(&d_len, n, cs));
         D4_CUDA_CHECK(dalloc(&d_crc, n, cs)); D4_CUDA_CHECK(dalloc(&d_ad, n, cs));
+        D4_CUDA_CHECK(dalloc(&d_jobs, jobs.size(), cs)); D4_CUDA_CHECK(dalloc(&d_acc, n, cs));
         D4_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), 8 * n, cudaMemcpyHostToDevice, cs));
         D4_CUDA_CHECK(cudaMemcpyAsync(d_len, len.data(), 8 * n, cudaMemcpyHostToDevice, cs));
+        D4_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(CkJob) * jobs.size(), cudaMemcpyHostToDevice, cs));
+        D4_CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(CkAcc) * std::max<uint32_t>(n, 1), cs));
         cudaEventRecord(ev[0], cs);
-        if (n) LAUNCH(k_checksums, n, 256, cs, d_out, d_off, d_len, d_crc, d_ad);
+        if (n) {
+            LAUNCH(k_checksum_cells, (unsigned)jobs.size(), CK_NT, cs, d_out, d_off, d_len, d_jobs, d_acc);
+            LAUNCH(k_checksum_final, (n * 32 + 255) / 256, 256, cs, d_len, d_acc, n, d_crc, d_ad);
+        }
         cudaEventRecord(ev[1], cs);
         crc.resize(n); adler.resize(n);
         D4_CUDA_CHECK(cudaMemcpyAsync(crc.data(), d_crc, 4 * n, cudaMemcpyDeviceToHost, cs));
@@ -650,7 +595,7 @@ class Batch {
         float t;
         cudaEventElapsedTime(&t, ev[0], ev[1]); ms[6] = t;
         for (auto& e : ev) cudaEventDestroy(e);
-        dfree(d_off, cs); dfree(d_len, cs); dfree(d_crc, cs); dfree(d_ad, cs);
+        dfree(d_off, cs); dfree(d_len, cs); dfree(d_crc, cs); dfree(d_ad, cs); dfree(d_jobs, cs); dfree(d_acc, cs);
         have_sums = true;
         return DEFT4CU_OK;
     }
