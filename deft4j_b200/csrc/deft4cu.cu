@@ -421,6 +421,12 @@ class Batch {
         if ((e = dalloc(&sc.tabs, (size_t)grid * MAXT, cs)) != cudaSuccess) return e;
         if ((e = dalloc(&sc.recode, (size_t)grid * MAXM, cs)) != cudaSuccess) return e;
         if ((e = dalloc(&sc.pvals, (size_t)grid * MEMO_P, cs)) != cudaSuccess) return e;
+        // cost arrays: as many per CTA as a 6 GiB budget allows (2 .. DCN_MAX)
+        const size_t maxn = (size_t)sc.maxwords * 32;
+        sc.dcn = (int)std::max<size_t>(2, std::min<size_t>(DCN_MAX, (6ull << 30) / (2 * maxn * grid)));
+        if ((e = dalloc(&sc.dc, (size_t)grid * sc.dcn * maxn, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.hists, (size_t)grid * (MAXM + NCAND) * 320, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.kind, (size_t)grid * maxn, cs)) != cudaSuccess) return e;
         if (getenv("D4_POISON")) {
             cudaMemsetAsync(sc.masks, 0xFF, sizeof(uint32_t) * (size_t)grid * (MAXM + NCAND) * sc.maxwords, cs);
             cudaMemsetAsync(sc.tabs, 0xFF, sizeof(Tab) * (size_t)grid * MAXT, cs);
@@ -429,7 +435,10 @@ class Batch {
         }
         return cudaSuccess;
     }
-    void free_scratch(EngScratch& sc) { dfree(sc.masks, cs); dfree(sc.tabs, cs); dfree(sc.recode, cs); dfree(sc.pvals, cs); }
+    void free_scratch(EngScratch& sc) {
+        dfree(sc.masks, cs); dfree(sc.tabs, cs); dfree(sc.recode, cs); dfree(sc.pvals, cs);
+        dfree(sc.dc, cs); dfree(sc.hists, cs); dfree(sc.kind, cs);
+    }
 
     // ---- optimise: phase A over blocks, then per-stream replay/merge/layout ----------------------------
     int optimise(uint32_t flags, const std::vector<uint8_t>& selected) {
@@ -679,6 +688,22 @@ int deft4cu_debug_trace_end(int64_t* dst, uint32_t cap, uint32_t* n) {
     cudaFree(g_trace_dev);
     g_trace_dev = nullptr;
     return DEFT4CU_OK;
+}
+
+// cycle counters of a -DD4_PROF build (engine.cuh g_prof); returns DEFT4CU_ERR_ARG in ordinary builds
+int deft4cu_debug_prof(uint64_t* dst, uint32_t n, int reset) {
+#ifdef D4_PROF
+    unsigned long long h[64];
+    D4_CUDA_CHECK(cudaDeviceSynchronize());
+    D4_CUDA_CHECK(cudaMemcpyFromSymbol(h, g_prof, sizeof(h)));
+    for (uint32_t i = 0; i < n && i < 64; i++) dst[i] = h[i];
+    if (reset) { memset(h, 0, sizeof h); D4_CUDA_CHECK(cudaMemcpyToSymbol(g_prof, h, sizeof(h))); }
+    return DEFT4CU_OK;
+#else
+    (void)dst; (void)n; (void)reset;
+    set_error("not a -DD4_PROF build");
+    return DEFT4CU_ERR_ARG;
+#endif
 }
 
 // ---- handle API ------------------------------------------------------------------------------------------

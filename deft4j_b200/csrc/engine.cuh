@@ -47,8 +47,9 @@ __device__ __forceinline__ void trace_put(long long idx, long long sz) {
 }
 constexpr int NCAND = 16;
 #ifdef D4_SMALL_POOLS           // stress build: forces the pool-overflow path (flush_all) on ordinary inputs
-constexpr int MAXM = 20, MAXT = 20, MEMO_P = 64;
+constexpr int MAXM = 20, MAXT = 20, MEMO_P = 64, DCN_MAX = 3;
 #else
+constexpr int DCN_MAX = 64;   // per-table literal-minus-match cost arrays kept per block (round-robin eviction)
 constexpr int MAXM = 256;     // distinct symbol-list masks kept per block
 constexpr int MAXT = 256;     // distinct code tables kept per block
 constexpr int MEMO_P = 1024;  // pass memo slots (open addressing, kept under 3/4 full)
@@ -86,6 +87,7 @@ struct EngSmem {
     int err;
     TreeWs<290, 584> tl;
     TreeWs<32, 68> td;
+    TreeWsCL wsCL;       // header-code tree workspace of thread 0 (local memory costs an L2 round trip per access)
     // selection state
     long long bestSize;
     int bestStored;
@@ -101,6 +103,9 @@ struct EngSmem {
     int nTabs, fixedTab;
     unsigned long long pkey[MEMO_P];
     int nP;
+    unsigned char tabDc[MAXT];        // tabid -> cost-array slot (0xFF: none)
+    unsigned short dcOwner[DCN_MAX];  // slot -> tabid (0xFFFF: free)
+    int dcNext;
     int remap[NCAND], uniq[NCAND];
     unsigned long long uh[NCAND];
     int tmpIdx, redAny2;
@@ -109,6 +114,20 @@ struct EngSmem {
 };
 
 enum { C_B = 0, C_BEST, C_O, C_H, C_E, C_X, C_CHK, C_T, C_Y, C_B1, C_B2, C_B3, C_B4, C_PP, C_CHK2, C_TMP };
+
+// cycle accounting per engine phase (-DD4_PROF builds only; read back with deft4cu_debug_prof): thread 0's
+// clock64 deltas, [cat] = cycles, [32 + cat] = calls.  Categories nest (recode-miss contains hist, trees, ...).
+#ifdef D4_PROF
+__device__ unsigned long long g_prof[64];
+#define P0() const long long p0_ = clock64()
+#define P1(cat) do { if (tid == 0) { atomicAdd(&g_prof[cat], (unsigned long long)(clock64() - p0_)); atomicAdd(&g_prof[32 + (cat)], 1ull); } } while (0)
+#else
+#define P0()
+#define P1(cat)
+#endif
+enum { PR_BLOCK = 0, PR_REPL_HIT, PR_REPL_MISS, PR_LEAST_HIT, PR_LEAST_MISS, PR_HIST, PR_RECODE_HIT, PR_RECODE_MISS, PR_TREES,
+       PR_HDR_DEFAULT, PR_INTERN_TAB, PR_INTERN_MASK, PR_COPY, PR_CB, PR_TRIALS, PR_TRIALS_EVAL, PR_HDR_OPT, PR_HDR_RECODE,
+       PR_TO_FIXED, PR_FLUSH, PR_PAYLOAD };
 
 #ifdef D4_VERIFY
 #define D4V(c, op) verify(c, op)
@@ -124,6 +143,11 @@ struct Eng {
     Tab* tabs;            // MAXT interned code tables
     Cand* recode;         // MAXM: recodeHuffman result per mask id
     PVal* pvals;          // MEMO_P pass memo values
+    short* dc;            // dcn arrays of maxn: per symbol, (literal cost - match cost) under one Tab
+    uint32_t* hists;      // MAXM * 320: symbol histogram per mask id
+    uint8_t* kind;        // maxn: 0 = not a match, else length symbol - 256
+    uint32_t maxn;        // maxwords * 32
+    int dcn;
     int tid;
 
     __device__ uint32_t* maskp(int id) const { return masks + (size_t)id * maxwords; }
@@ -132,15 +156,18 @@ struct Eng {
     //      pool entries, so a copy shares its source's mask id) --------------------------------------------
     __device__ __noinline__ void copy(int dst, int src) {
         if (dst == src) return;
+        P0();
         const uint32_t* s = (const uint32_t*)&S->c[src];
         uint32_t* d = (uint32_t*)&S->c[dst];
         for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
         __syncthreads();
+        P1(PR_COPY);
         D4V(dst, 7);
     }
 
     // ---- selection callback (DeflateStream.java:349-368) ------------------------------------------
     __device__ __noinline__ void cb(int c, bool isRest = true) {
+        P0();
         long long sz = cand_size(S->c[c]);
         bool better = sz < S->bestSize;
         __syncthreads();
@@ -151,6 +178,7 @@ struct Eng {
             S->candIndex++;
         }
         if (better) copy(C_BEST, c); else __syncthreads();
+        P1(PR_CB);
     }
 
     __device__ __noinline__ unsigned long long hash_words(const uint32_t* p, int nwords32) {
@@ -176,12 +204,15 @@ struct Eng {
         for (int k = tid; k < MEMO_P; k += ENG_NT) S->pkey[k] = 0;
         for (int k = tid; k < MAXM; k += ENG_NT) S->recodeValid[k] = 0;
         if (tid < NCAND) { S->c[tid].mid = 0; S->c[tid].tabid = 0; S->c[tid].pad2 = 0; }
-        if (tid == 0) { S->nMasks = 0; S->nTabs = 0; S->nP = 0; S->fixedTab = -1; }
+        for (int k = tid; k < MAXT; k += ENG_NT) S->tabDc[k] = 0xFF;
+        if (tid < DCN_MAX) S->dcOwner[tid] = 0xFFFF;
+        if (tid == 0) { S->nMasks = 0; S->nTabs = 0; S->nP = 0; S->fixedTab = -1; S->dcNext = 0; }
         __syncthreads();
     }
 
     // Tab of candidate c -> S->c[c].tabid (hash-consed; a hash hit is confirmed by a full comparison)
     __device__ __noinline__ void intern_tab(int c) {
+        P0();
         const uint32_t* q = (const uint32_t*)&S->c[c].tab;
         const unsigned long long h = hash_words(q, (int)(sizeof(Tab) / 4));
         if (tid == 0) { S->tmpIdx = -1; S->redAny2 = 0; }
@@ -215,11 +246,13 @@ struct Eng {
         }
         if (tid == 0) S->c[c].tabid = (uint16_t)hit;
         __syncthreads();
+        P1(PR_INTERN_TAB);
     }
 
     // the mask just written into pool slot nMasks -> its id (an equal older mask wins, so equal symbol lists
     // reached along different paths share their memo entries)
     __device__ __noinline__ int intern_mask() {
+        P0();
         const int fresh = S->nMasks;
         const uint32_t* q = maskp(fresh);
         const unsigned long long h = hash_words(q, (int)v.nwords);
@@ -243,11 +276,13 @@ struct Eng {
             if (tid == 0) { S->maskHash[fresh] = h; S->recodeValid[fresh] = 0; S->nMasks = fresh + 1; }
         }
         __syncthreads();
+        P1(PR_INTERN_MASK);
         return hit;
     }
 
     // a pool is full: keep only what the candidate slots reference
     __device__ __noinline__ void flush_all() {
+        P0();
         __syncthreads();
         if (tid == 0) {
             int nu = 0;
@@ -266,21 +301,30 @@ struct Eng {
             const uint32_t* s = maskp(S->uniq[k]);
             uint32_t* d = maskp(MAXM + k);
             for (uint32_t w = tid; w < v.nwords; w += ENG_NT) d[w] = s[w];
+            const uint32_t* hs = hists + (size_t)S->uniq[k] * 320;
+            uint32_t* hd = hists + (size_t)(MAXM + k) * 320;
+            for (int w = tid; w < 320; w += ENG_NT) hd[w] = hs[w];
         }
         __syncthreads();
         for (int k = 0; k < nu; k++) {
             const uint32_t* s = maskp(MAXM + k);
             uint32_t* d = maskp(k);
             for (uint32_t w = tid; w < v.nwords; w += ENG_NT) d[w] = s[w];
+            const uint32_t* hs = hists + (size_t)(MAXM + k) * 320;
+            uint32_t* hd = hists + (size_t)k * 320;
+            for (int w = tid; w < 320; w += ENG_NT) hd[w] = hs[w];
         }
         if (tid < NCAND) S->c[tid].mid = (uint16_t)S->remap[tid];
         if (tid < nu) S->maskHash[tid] = S->uh[tid];
         for (int k = tid; k < MAXM; k += ENG_NT) S->recodeValid[k] = 0;
         for (int k = tid; k < MEMO_P; k += ENG_NT) S->pkey[k] = 0;
+        for (int k = tid; k < MAXT; k += ENG_NT) S->tabDc[k] = 0xFF;
+        if (tid < DCN_MAX) S->dcOwner[tid] = 0xFFFF;
         __syncthreads();
-        if (tid == 0) { S->nMasks = nu; S->nTabs = 0; S->nP = 0; S->fixedTab = -1; }
+        if (tid == 0) { S->nMasks = nu; S->nTabs = 0; S->nP = 0; S->fixedTab = -1; S->dcNext = 0; }
         __syncthreads();
         for (int c = 0; c < NCAND; c++) intern_tab(c);
+        P1(PR_FLUSH);
     }
     // every op creates at most one mask, one Tab and one memo entry
     __device__ __forceinline__ void maybe_flush() {
@@ -305,16 +349,20 @@ struct Eng {
     }
 
     // ---- CTA-wide passes ----------------------------------------------------------------------------
-    // literal cost of the bytes a match produces; returns -1 when a byte has no code
+    // literal cost of the bytes a match produces; returns -1 when a byte has no code.  Loads are issued
+    // eight at a time so their latencies overlap.
     __device__ __forceinline__ int lit_cost(const uint8_t* L, uint32_t off, int len) const {
-        int tot = 0;
         const uint8_t* p = v.out + off;
-        for (int k = 0; k < len; k++) {
-            int b = L[p[k]];
-            if (b < 1) return -1;
-            tot += b;
+        int tot = 0, bad = 0;
+        for (int k = 0; k < len; k += 8) {
+            uint32_t b[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) b[j] = (k + j < len) ? (uint32_t)p[k + j] : 256u;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (b[j] < 256u) { const int cbits = L[b[j]]; bad |= (cbits < 1); tot += cbits; }
         }
-        return tot;
+        return bad ? -1 : tot;
     }
     // getLitLenSize for a match (:112-128)
     __device__ __forceinline__ int ref_cost(const Tab& t, uint32_t s) const {
@@ -322,49 +370,107 @@ struct Eng {
         return t.L[ls] + len_ebits_of(ls) + t.D[ds] + dist_ebits_of(ds);
     }
 
+    // Per-Tab cost array: dc[i] = (literal cost of match i's bytes) - (cost of the match) under candidate c's
+    // tables, DC_BLOCKED when a byte has no code (DeflateBlockHuffman.java:238-246).  It does not depend on the
+    // mask, so every replace / least pass under the same tables reads it instead of walking the bytes again.
+    static constexpr short DC_BLOCKED = 0x7FFF, DC_NOT_MATCH = 0x7FFE;
+    __device__ __noinline__ const short* ensure_dc(int c) {
+        const Cand& cd = S->c[c];
+        const int t = cd.tabid;
+        int slot = S->tabDc[t];
+        if (slot != 0xFF) return dc + (size_t)slot * maxn;
+        __syncthreads();  // every thread has seen the miss before thread 0 records the new slot
+        if (tid == 0) {
+            slot = S->dcNext;
+            S->dcNext = (slot + 1) % dcn;
+            const int owner = S->dcOwner[slot];
+            if (owner != 0xFFFF) S->tabDc[owner] = 0xFF;
+            S->dcOwner[slot] = (unsigned short)t;
+            S->tabDc[t] = (unsigned char)slot;
+            S->tmpIdx = slot;
+        }
+        __syncthreads();
+        slot = S->tmpIdx;
+        short* d = dc + (size_t)slot * maxn;
+        for (uint32_t i = tid; i < v.n; i += ENG_NT) {
+            short x = DC_NOT_MATCH;
+            if (kind[i]) {
+                const uint32_t s = v.sym[i];
+                const int lit = lit_cost(cd.tab.L, v.symout[i], sym_len(s));
+                x = lit < 0 ? DC_BLOCKED : (short)(lit - ref_cost(cd.tab, s));
+            }
+            d[i] = x;
+        }
+        __syncthreads();
+        return d;
+    }
+
+    // match i leaves the symbol list and its bytes enter it as literals: histogram delta in S->hist
+    __device__ __forceinline__ void hist_delta_replace(uint32_t i) {
+        const uint32_t s = v.sym[i];
+        atomicSub(&S->hist[sym_lensym(s)], 1u);
+        atomicSub(&S->hist[288 + dist_sym(sym_dist(s))], 1u);
+        const uint8_t* p = v.out + v.symout[i];
+        const int len = sym_len(s);
+        for (int k = 0; k < len; k++) atomicAdd(&S->hist[p[k]], 1u);
+    }
+    // hists[dst] = hists[src] + S->hist (the delta of the matches that were just replaced)
+    __device__ __forceinline__ void hist_store_delta(int dst, int src) {
+        const uint32_t* hs = hists + (size_t)src * 320;
+        uint32_t* hd = hists + (size_t)dst * 320;
+        for (int k = tid; k < 320; k += ENG_NT) hd[k] = hs[k] + S->hist[k];
+    }
+
     // replaceBackrefsWithLiteralsIfSmaller(prune) on candidate c (in place)
     __device__ __noinline__ void pass_replace(int c, bool prune) {
         maybe_flush();
+        P0();
         Cand& cd = S->c[c];
         const int mid = cd.mid;
         const unsigned long long key = pm_key(mid, cd.tabid, prune ? 1 : 0);
         if (tid == 0) { S->tmpIdx = pm_find(key); S->red = 0; S->redAny = 0; }
         __syncthreads();
         int slot = S->tmpIdx;
+        __syncthreads();
         if (slot >= 0) {
             if (tid == 0) { const PVal pv = pvals[slot]; cd.mid = (uint16_t)pv.mid; cd.payload -= pv.delta; }
             __syncthreads();
+            P1(PR_REPL_HIT);
             D4V(c, prune ? 2 : 1);
             return;
         }
         slot = -1 - slot;
+        const short* d = ensure_dc(c);
+        for (int k = tid; k < 320; k += ENG_NT) S->hist[k] = 0;
+        __syncthreads();
         const uint32_t* m = maskp(mid);
-        uint32_t* md = maskp(S->nMasks);
+        const int fresh = S->nMasks;
+        uint32_t* md = maskp(fresh);
         long long saved = 0;
         const int lane = tid & 31;
         for (uint32_t base = (tid >> 5) * 32; base < v.n; base += ENG_NT) {
-            uint32_t i = base + lane;
+            const uint32_t i = base + lane;
             bool rep = false;
-            uint32_t word = m[base >> 5];
-            if (i < v.n) {
-                uint32_t s = v.sym[i];
-                if (sym_is_match(s) && !((word >> lane) & 1)) {
-                    int ref = ref_cost(cd.tab, s);
-                    int lit = lit_cost(cd.tab.L, v.symout[i], sym_len(s));
-                    if (lit >= 0 && (prune ? lit <= ref : lit < ref)) { rep = true; saved += ref - lit; }
-                }
+            const uint32_t word = m[base >> 5];
+            if (i < v.n && kind[i] && !((word >> lane) & 1)) {
+                const int x = d[i];
+                rep = prune ? x <= 0 : x < 0;
+                if (rep) { saved -= x; hist_delta_replace(i); }
             }
-            unsigned bal = __ballot_sync(0xffffffffu, rep);
+            const unsigned bal = __ballot_sync(0xffffffffu, rep);
             if (lane == 0) {
                 md[base >> 5] = word | bal;
                 if (bal) S->redAny = 1;
             }
         }
-        for (int d = 16; d > 0; d >>= 1) saved += __shfl_xor_sync(0xffffffffu, saved, d);
+        for (int dd = 16; dd > 0; dd >>= 1) saved += __shfl_xor_sync(0xffffffffu, saved, dd);
         if (lane == 0 && saved) atomicAdd(&S->red, (unsigned long long)saved);
         __syncthreads();
         int newmid = mid;
-        if (S->redAny) newmid = intern_mask();
+        if (S->redAny) {
+            newmid = intern_mask();
+            if (newmid == fresh) hist_store_delta(newmid, mid);
+        }
         if (tid == 0) {
             PVal pv; pv.mid = (uint32_t)newmid; pv.pad = 0; pv.delta = (long long)S->red;
             pvals[slot] = pv;
@@ -374,6 +480,7 @@ struct Eng {
             cd.payload -= pv.delta;
         }
         __syncthreads();
+        P1(PR_REPL_MISS);
         D4V(c, prune ? 2 : 1);
     }
 
@@ -382,6 +489,7 @@ struct Eng {
         Cand& cd = S->c[c];
         if (cd.tab.type != 2) return;
         maybe_flush();
+        P0();
         const int mid = cd.mid;
         const unsigned long long key = pm_key(mid, cd.tabid, 2 + mode);
         if (tid == 0) S->tmpIdx = pm_find(key);
@@ -393,19 +501,32 @@ struct Eng {
         if (slot >= 0) {
             if (tid == 0) { const PVal pv = pvals[slot]; cd.mid = (uint16_t)pv.mid; cd.payload -= pv.delta; }
             __syncthreads();
+            P1(PR_LEAST_HIT);
             D4V(c, 3 + mode);
             return;
         }
         slot = -1 - slot;
+        const short* d = ensure_dc(c);
+        for (int k = tid; k < 320; k += ENG_NT) S->hist[k] = 0;
         const uint32_t* m = maskp(mid);
-        for (uint32_t i = tid; i < v.n; i += ENG_NT) {
-            uint32_t s = v.sym[i];
-            if (sym_is_match(s) && !((m[i >> 5] >> (i & 31)) & 1)) {
-                int bin = sym_lensym(s) - 257;
+        const int lane = tid & 31;
+        // per length symbol: sum of (literal - match) cost, count, blocked (:386-420); lanes of a warp that hold
+        // the same length symbol are summed with one shared-memory atomic
+        for (uint32_t base = (tid >> 5) * 32; base < v.n; base += ENG_NT) {
+            const uint32_t i = base + lane;
+            const int k = i < v.n ? kind[i] : 0;
+            const bool live = k && !((m[base >> 5] >> lane) & 1);
+            const int x = live ? d[i] : 0;
+            const bool blocked = live && x == DC_BLOCKED;
+            const int bin = live ? k - 1 : 31;
+            const unsigned grp = __match_any_sync(0xffffffffu, bin);
+            const int xs = __reduce_add_sync(grp, (live && !blocked) ? x : 0);
+            const int cn = __reduce_add_sync(grp, (live && !blocked) ? 1 : 0);
+            const unsigned anyBlocked = __ballot_sync(0xffffffffu, blocked) & grp;
+            if (live && lane == __ffs(grp) - 1) {
                 atomicOr(&S->leastSeen, 1u << bin);
-                int lit = lit_cost(cd.tab.L, v.symout[i], sym_len(s));
-                if (lit < 0) atomicOr(&S->leastBlocked, 1u << bin);
-                else { atomicAdd(&S->leastSum[bin], lit - ref_cost(cd.tab, s)); atomicAdd(&S->leastCnt[bin], 1); }
+                if (anyBlocked) atomicOr(&S->leastBlocked, 1u << bin);
+                if (cn) { atomicAdd(&S->leastSum[bin], xs); atomicAdd(&S->leastCnt[bin], cn); }
             }
         }
         __syncthreads();
@@ -424,20 +545,19 @@ struct Eng {
         const int rem = S->tmpIdx;
         int newmid = mid;
         if (rem >= 0) {
-            uint32_t* md = maskp(S->nMasks);
-            const int lane = tid & 31;
+            const int fresh = S->nMasks;
+            uint32_t* md = maskp(fresh);
             for (uint32_t base = (tid >> 5) * 32; base < v.n; base += ENG_NT) {
-                uint32_t i = base + lane;
-                bool rep = false;
-                if (i < v.n) {
-                    uint32_t s = v.sym[i];
-                    rep = sym_is_match(s) && (sym_lensym(s) - 257 == rem);
-                }
-                unsigned bal = __ballot_sync(0xffffffffu, rep);
-                if (lane == 0) md[base >> 5] = m[base >> 5] | bal;
+                const uint32_t i = base + lane;
+                const uint32_t word = m[base >> 5];
+                const bool rep = i < v.n && kind[i] == rem + 1;
+                if (rep && !((word >> lane) & 1)) hist_delta_replace(i);
+                const unsigned bal = __ballot_sync(0xffffffffu, rep);
+                if (lane == 0) md[base >> 5] = word | bal;
             }
             __syncthreads();
             newmid = intern_mask();
+            if (newmid == fresh) hist_store_delta(newmid, mid);
         }
         if (tid == 0) {
             PVal pv; pv.mid = (uint32_t)newmid; pv.pad = 0; pv.delta = -(long long)S->red;
@@ -448,11 +568,13 @@ struct Eng {
             cd.payload -= pv.delta;
         }
         __syncthreads();
+        P1(PR_LEAST_MISS);
         D4V(c, 3 + mode);
     }
 
-    // histogram of the symbol list with mask `mid` into S->hist
-    __device__ __noinline__ void pass_hist(int mid) {
+    // histogram of the symbol list with mask `mid` into S->hist, from the symbols (block start, checks)
+    __device__ __noinline__ void pass_hist_full(int mid) {
+        P0();
         const uint32_t* m = maskp(mid);
         for (int k = tid; k < 320; k += ENG_NT) S->hist[k] = 0;
         __syncthreads();
@@ -470,10 +592,19 @@ struct Eng {
             }
         }
         __syncthreads();
+        P1(PR_HIST);
+    }
+    // the same from the per-mask cache (every mask's histogram is derived from its parent's when it is created)
+    __device__ __forceinline__ void load_hist(int mid) {
+        const uint32_t* hs = hists + (size_t)mid * 320;
+        __syncthreads();
+        for (int k = tid; k < 320; k += ENG_NT) S->hist[k] = hs[k];
+        __syncthreads();
     }
 
     // payload of the symbol list described by S->hist under table t (recodeToHuffmanInternal, :759-770)
     __device__ __noinline__ long long hist_payload(const Tab& t) {
+        P0();
         long long acc = 0;
         for (int k = tid; k < 318; k += ENG_NT) {
             uint32_t f = S->hist[k];
@@ -492,6 +623,7 @@ struct Eng {
         __syncthreads();
         long long r = (long long)S->red;
         __syncthreads();
+        P1(PR_PAYLOAD);
         return r;
     }
 
@@ -501,8 +633,8 @@ struct Eng {
     // debug: payload of candidate c recomputed from its mask and tables; first mismatch is recorded
     __device__ __noinline__ void verify(int c, int opcode) {
         __syncthreads();
-        // pass_hist/hist_payload clobber S->hist and S->red only
-        pass_hist(S->c[c].mid);
+        // pass_hist_full/hist_payload clobber S->hist and S->red only
+        pass_hist_full(S->c[c].mid);
         long long t = hist_payload(S->c[c].tab);
         if (tid == 0 && t != S->c[c].payload) {
             if (atomicMax(vgerr, 14) < 13) {
@@ -518,6 +650,7 @@ struct Eng {
     //      The result is a function of the symbol list alone -> cached per mask id.
     __device__ __noinline__ void op_recode(int c) {
         maybe_flush();
+        P0();
         Cand& cd = S->c[c];
         const int mid = cd.mid;
         if (S->recodeValid[mid]) {
@@ -526,11 +659,13 @@ struct Eng {
             __syncthreads();
             for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
             __syncthreads();
+            P1(PR_RECODE_HIT);
             D4V(c, 5);
             return;
         }
-        pass_hist(mid);
+        load_hist(mid);
         // trailing zero-frequency trimming + the distance special cases (:683-740)
+        const long long p0_trees = clock64();
         if (tid == 0) {
             int nl = 286;
             while (nl > 0 && S->hist[nl - 1] == 0) nl--;
@@ -553,15 +688,19 @@ struct Eng {
             }
         }
         __syncthreads();
+        { const long long p0_ = p0_trees; (void)p0_; P1(PR_TREES); }
         if (tid == 0) { cd.tab.type = 2; cd.tab.pad[0] = cd.tab.pad[1] = cd.tab.pad[2] = 0; }
         __syncthreads();
         long long pay = hist_payload(cd.tab);
-        if (tid == 0) {
-            cd.payload = pay;
-            TreeWsCL ws;
-            if (hdr_rewrite(cd.tab, FLAGS_DEFAULT, cd.hdr, ws)) S->err = ERR_TREE;
+        {
+            P0();
+            if (tid == 0) {
+                cd.payload = pay;
+                if (hdr_rewrite(cd.tab, FLAGS_DEFAULT, cd.hdr, S->wsCL)) S->err = ERR_TREE;
+            }
+            __syncthreads();
+            P1(PR_HDR_DEFAULT);
         }
-        __syncthreads();
         intern_tab(c);
         {
             const uint32_t* s = (const uint32_t*)&S->c[c];
@@ -570,6 +709,7 @@ struct Eng {
             if (tid == 0) S->recodeValid[mid] = 1;
         }
         __syncthreads();
+        P1(PR_RECODE_MISS);
         D4V(c, 6);
     }
     // recodeHuffmanLessMatches (:655-658)
@@ -581,6 +721,7 @@ struct Eng {
         if (cd.tab.type == 1) return;
         __syncthreads();  // every thread has read the type before thread 0 rewrites it below
         maybe_flush();
+        P0();
         const int mid = cd.mid;
         const unsigned long long key = pm_key(mid, 0xFFFF, 4);
         if (tid == 0) {
@@ -599,7 +740,7 @@ struct Eng {
             if (tid == 0) cd.payload = pvals[slot].delta;
         } else {
             slot = -1 - slot;
-            pass_hist(mid);
+            load_hist(mid);
             long long pay = hist_payload(cd.tab);
             if (tid == 0) {
                 cd.payload = pay;
@@ -618,6 +759,7 @@ struct Eng {
             if (tid == 0) S->fixedTab = cd.tabid;
             __syncthreads();
         }
+        P1(PR_TO_FIXED);
     }
 
     // DeflateBlockHuffman.optimise (:460-469): returns bits saved
@@ -625,8 +767,10 @@ struct Eng {
         long long before = cand_size(S->c[c]);
         __syncthreads();
         pass_replace(c, false);
+        P0();
         if (tid == 0 && S->c[c].tab.type == 2) hdr_optimise(S->c[c].hdr);
         __syncthreads();
+        P1(PR_HDR_OPT);
         long long after = cand_size(S->c[c]);
         __syncthreads();
         return before - after;
@@ -637,12 +781,16 @@ struct Eng {
         return op_optimise(dst) > 0;
     }
     __device__ void op_recode_header(int c) {
-        if (tid == 0 && S->c[c].tab.type == 2) { TreeWsCL ws; if (hdr_recode(S->c[c].hdr, ws)) S->err = ERR_TREE; }
+        P0();
+        if (tid == 0 && S->c[c].tab.type == 2) { if (hdr_recode(S->c[c].hdr, S->wsCL)) S->err = ERR_TREE; }
         __syncthreads();
+        P1(PR_HDR_RECODE);
     }
     __device__ void op_recode_header_less(int c) {
-        if (tid == 0 && S->c[c].tab.type == 2) { TreeWsCL ws; if (hdr_recode_less(S->c[c].hdr, ws)) S->err = ERR_TREE; }
+        P0();
+        if (tid == 0 && S->c[c].tab.type == 2) { if (hdr_recode_less(S->c[c].hdr, S->wsCL)) S->err = ERR_TREE; }
         __syncthreads();
+        P1(PR_HDR_RECODE);
     }
 
     // ---- the 56 header strategy trials of up to 4 bases (addOptimisedRecoded, :277-316) -------------
@@ -650,6 +798,7 @@ struct Eng {
     // in / added to the per-tabid memo, then the virtual candidates are fed to the selection callback in
     // the reference's order; only a winning trial is materialised.
     __device__ __noinline__ void trials(int nb) {
+        P0();
         __shared__ int s_miss[4];
         if (tid < nb) s_miss[tid] = (S->tabTrialBits[S->c[C_B1 + tid].tabid] == TRIAL_UNSET) || g_trace != nullptr;
         __syncthreads();
@@ -664,6 +813,7 @@ struct Eng {
             }
         }
         __syncthreads();
+        P1(PR_TRIALS_EVAL);
         if (g_trace && tid == 0)
             for (int b = 0; b < nb; b++)
                 for (int k = 0; k < 56; k++) trace_put(S->candIndex + b * 56 + k, S->c[C_B1 + b].payload + S->trialBits[b * 56 + k]);
@@ -692,12 +842,12 @@ struct Eng {
             if (better) {
                 copy(C_BEST, C_B1 + b);
                 if (tid == 0) {
-                    TreeWsCL ws;
-                    if (hdr_trial(S->c[C_BEST].tab, c_trial_flags[arg], S->c[C_BEST].hdr, ws)) S->err = ERR_TREE;
+                    if (hdr_trial(S->c[C_BEST].tab, c_trial_flags[arg], S->c[C_BEST].hdr, S->wsCL)) S->err = ERR_TREE;
                 }
             }
             __syncthreads();
         }
+        P1(PR_TRIALS);
     }
 
     // recodedHuffmanFull (DeflateStream.java:212-229): cur (slot a) is replaced while a further
@@ -756,6 +906,7 @@ struct Eng {
     // candidate is compared (phase A resolves it afterwards from sizeI / sizeC1 / restMin).
     // Result: C_BEST (or stored when S->bestStored).
     __device__ void optimise_block(long long storedSize) {
+        P0();
         if (tid == 0) {
             if (g_trace) trace_put(-1, cand_size(S->c[C_B]));
             S->bestSize = cand_size(S->c[C_B]);
@@ -798,6 +949,7 @@ struct Eng {
         }
         copy(C_E, H); pass_least(C_E, 0); multi(C_E);
         copy(C_E, H); pass_least(C_E, 1); multi(C_E);
+        P1(PR_BLOCK);
     }
 };
 

@@ -79,7 +79,11 @@ struct EngScratch {       // global scratch, one slice per CTA
     Tab* tabs;            // MAXT
     Cand* recode;         // MAXM
     PVal* pvals;          // MEMO_P
+    short* dc;            // dcn * maxwords * 32
+    uint32_t* hists;      // (MAXM + NCAND) * 320
+    uint8_t* kind;        // maxwords * 32
     uint32_t maxwords;
+    int dcn;
 };
 
 __device__ inline void eng_init(Eng& e, EngSmem* S, const EngScratch& sc, int cta) {
@@ -90,6 +94,11 @@ __device__ inline void eng_init(Eng& e, EngSmem* S, const EngScratch& sc, int ct
     e.tabs = sc.tabs + (size_t)cta * MAXT;
     e.recode = sc.recode + (size_t)cta * MAXM;
     e.pvals = sc.pvals + (size_t)cta * MEMO_P;
+    e.maxn = sc.maxwords * 32;
+    e.dcn = sc.dcn;
+    e.dc = sc.dc + (size_t)cta * sc.dcn * e.maxn;
+    e.hists = sc.hists + (size_t)cta * (MAXM + NCAND) * 320;
+    e.kind = sc.kind + (size_t)cta * e.maxn;
     if (threadIdx.x == 0) S->err = 0;
     __syncthreads();
 }
@@ -99,6 +108,13 @@ __device__ inline void eng_adopt_mask0(Eng& e) {
     __syncthreads();
     const unsigned long long h = e.hash_words(e.maskp(0), (int)e.v.nwords);
     if (e.tid == 0) { e.S->maskHash[0] = h; e.S->recodeValid[0] = 0; e.S->nMasks = 1; e.S->c[C_B].mid = 0; }
+    for (uint32_t i = e.tid; i < e.v.n; i += ENG_NT) {
+        const uint32_t s = e.v.sym[i];
+        e.kind[i] = sym_is_match(s) ? (uint8_t)(sym_lensym(s) - 256) : (uint8_t)0;
+    }
+    __syncthreads();
+    e.pass_hist_full(0);
+    for (int k = e.tid; k < 320; k += ENG_NT) e.hists[k] = e.S->hist[k];
     __syncthreads();
 }
 
@@ -153,7 +169,7 @@ k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __rest
             const bool improved = S.bestSize < S.sizeI;
             __syncthreads();
             if (improved && !S.bestStored) {  // self-check: the winner's payload recomputed from its symbol list
-                e.pass_hist(S.c[C_BEST].mid);
+                e.pass_hist_full(S.c[C_BEST].mid);
                 const long long truePay = e.hist_payload(S.c[C_BEST].tab);
                 if (truePay != S.c[C_BEST].payload && tid == 0) {
                     if (atomicMax(gerr, 13) < 13) {
