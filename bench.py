@@ -293,7 +293,7 @@ def run_ours(a):
     algo_bytes = in_bytes + out_bytes + 2 * unc_bytes          # A = C_in + C_out + 2 U per pass
     opt_ms = fam[3] / a.steps
     achieved = algo_bytes / (opt_ms / 1e3) / 1e9 if opt_ms > 0 else 0.0
-    names = ["parse_count", "emit", "lz77", "optimise", "finish_merge", "write", "checksums"]
+    names = ["parse_count", "emit", "lz77", "optimise", "finish_merge", "write", "checksums", "parse_rewalks"]
     roofline = {"bound": "hbm", "kernel": "k_opt_blocks", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": opt_ms,

@@ -20,9 +20,11 @@
 // can pin the very source the kernels run against the oracle (tests/test_host_units.py).
 #ifdef D4_HOST_TEST
 #define D4_DEV inline
+#define D4_DEV_BIG inline
 #define D4_CONST static const
 #else
 #define D4_DEV __device__ inline
+#define D4_DEV_BIG __device__ __noinline__   // one copy of the big serial routines: the engine kernel is i-cache bound
 #define D4_CONST __constant__
 #endif
 

@@ -409,24 +409,37 @@ class Batch {
         cudaEventElapsedTime(&t, ev[0], ev[1]); ms[0] = t;
         cudaEventElapsedTime(&t, ev[1], ev[2]); ms[1] = t;
         cudaEventElapsedTime(&t, ev[2], ev[3]); ms[2] = t;
+        ms[7] = (float)parse_rewalks;  // walkers whose guessed start was wrong or missing
         for (auto& e : ev) cudaEventDestroy(e);
         parsed = true;
         return DEFT4CU_OK;
     }
 
     // per-CTA engine scratch (mask pool, interned tables, recode cache, pass memo values)
-    cudaError_t alloc_scratch(EngScratch& sc, unsigned grid) {
+    cudaError_t alloc_scratch(EngScratch& sc, unsigned grid, uint64_t maxu) {
         cudaError_t e;
+        // literal-cost prefix sums need 4 bytes per decoded byte of the longest block per CTA: used when that fits 4 GiB
+        sc.P = nullptr;
+        sc.maxp = 0;
+        const uint64_t need = ((maxu + 64 + ENG_NT * 16 + 15) & ~15ull);
+        if (!getenv("D4_NO_PREFIX") && need < (1ull << 31) && need * 4 * grid <= (4ull << 30)) {
+            sc.maxp = (uint32_t)need;
+            if ((e = dalloc(&sc.P, (size_t)grid * need, cs)) != cudaSuccess) return e;
+        }
         if ((e = dalloc(&sc.masks, (size_t)grid * (MAXM + NCAND) * sc.maxwords, cs)) != cudaSuccess) return e;
         if ((e = dalloc(&sc.tabs, (size_t)grid * MAXT, cs)) != cudaSuccess) return e;
         if ((e = dalloc(&sc.recode, (size_t)grid * MAXM, cs)) != cudaSuccess) return e;
         if ((e = dalloc(&sc.pvals, (size_t)grid * MEMO_P, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.g, (size_t)grid, cs)) != cudaSuccess) return e;
         // cost arrays: as many per CTA as a 6 GiB budget allows (2 .. DCN_MAX)
         const size_t maxn = (size_t)sc.maxwords * 32;
         sc.dcn = (int)std::max<size_t>(2, std::min<size_t>(DCN_MAX, (6ull << 30) / (2 * maxn * grid)));
         if ((e = dalloc(&sc.dc, (size_t)grid * sc.dcn * maxn, cs)) != cudaSuccess) return e;
         if ((e = dalloc(&sc.hists, (size_t)grid * (MAXM + NCAND) * 320, cs)) != cudaSuccess) return e;
         if ((e = dalloc(&sc.kind, (size_t)grid * maxn, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.meta, (size_t)grid * maxn, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.smctr, 256, cs)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(sc.smctr, 0, 256 * sizeof(unsigned), cs)) != cudaSuccess) return e;
         if (getenv("D4_POISON")) {
             cudaMemsetAsync(sc.masks, 0xFF, sizeof(uint32_t) * (size_t)grid * (MAXM + NCAND) * sc.maxwords, cs);
             cudaMemsetAsync(sc.tabs, 0xFF, sizeof(Tab) * (size_t)grid * MAXT, cs);
@@ -436,8 +449,8 @@ class Batch {
         return cudaSuccess;
     }
     void free_scratch(EngScratch& sc) {
-        dfree(sc.masks, cs); dfree(sc.tabs, cs); dfree(sc.recode, cs); dfree(sc.pvals, cs);
-        dfree(sc.dc, cs); dfree(sc.hists, cs); dfree(sc.kind, cs);
+        dfree(sc.masks, cs); dfree(sc.tabs, cs); dfree(sc.recode, cs); dfree(sc.pvals, cs); dfree(sc.g, cs);
+        dfree(sc.dc, cs); dfree(sc.hists, cs); dfree(sc.kind, cs); dfree(sc.meta, cs); dfree(sc.P, cs); dfree(sc.smctr, cs);
     }
 
     // ---- optimise: phase A over blocks, then per-stream replay/merge/layout ----------------------------
@@ -447,6 +460,7 @@ class Batch {
         const int merge = (flags & DEFT4CU_MERGE_BLOCKS) ? 1 : 0;
         std::vector<uint32_t> jobs;
         uint32_t maxsym = 1, maxstream = 1;
+        uint64_t maxout = 1, maxstream_out = 1;
         for (uint32_t i = 0; i < n; i++) {
             StreamState& s = sstate[i];
             s.selected = selected[i] && s.status == ST_OK;
@@ -456,9 +470,14 @@ class Batch {
             for (uint32_t k = 0; k < s.n_blocks; k++) {
                 const BlkSummary& b = summ[s.blk_base + k];
                 ssum += b.n_sym;
-                if (k < s.cut && b.type != 0) { jobs.push_back((uint32_t)(s.blk_base + k)); maxsym = std::max(maxsym, b.n_sym); }
+                if (k < s.cut && b.type != 0) {
+                    jobs.push_back((uint32_t)(s.blk_base + k));
+                    maxsym = std::max(maxsym, b.n_sym);
+                    maxout = std::max<uint64_t>(maxout, b.out_len);
+                }
             }
             maxstream = (uint32_t)std::max<uint64_t>(maxstream, ssum);
+            maxstream_out = std::max<uint64_t>(maxstream_out, infos[i].out_len);
         }
         std::stable_sort(jobs.begin(), jobs.end(), [&](uint32_t a, uint32_t b) { return summ[a].n_sym > summ[b].n_sym; });
         D4_CUDA_CHECK(cudaMemcpyAsync(d_sstate, sstate.data(), sizeof(StreamState) * n, cudaMemcpyHostToDevice, cs));
@@ -471,12 +490,13 @@ class Batch {
             D4_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, 4, cs));
             D4_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), 4 * jobs.size(), cudaMemcpyHostToDevice, cs));
             int perSM = 0;
+            cudaFuncSetAttribute(k_opt_blocks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             D4_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_opt_blocks, ENG_NT, 0));
             if (perSM < 1) perSM = 1;
             unsigned grid = (unsigned)std::min<uint64_t>(jobs.size(), (uint64_t)g_sms * perSM);
             EngScratch sc;
             sc.maxwords = (maxsym + 31) / 32 + 1;
-            D4_CUDA_CHECK(alloc_scratch(sc, grid));
+            D4_CUDA_CHECK(alloc_scratch(sc, grid, maxout));
             LAUNCH(k_opt_blocks, grid, ENG_NT, cs, d_jobs, (uint32_t)jobs.size(), d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, d_counter, d_gerr);
             free_scratch(sc);
             dfree(d_jobs, cs); dfree(d_counter, cs);
@@ -486,13 +506,14 @@ class Batch {
             EngScratch sc{};
             sc.maxwords = (maxstream + 31) / 32 + 2;
             int perSM = 0;
+            cudaFuncSetAttribute(k_finish, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             D4_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_finish, ENG_NT, 0));
             if (perSM < 1) perSM = 1;
             const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)g_sms * perSM);
             unsigned* d_counter = nullptr;
             D4_CUDA_CHECK(dalloc(&d_counter, 1, cs));
             D4_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, 4, cs));
-            if (merge) D4_CUDA_CHECK(alloc_scratch(sc, grid));
+            if (merge) D4_CUDA_CHECK(alloc_scratch(sc, grid, maxstream_out));
             if (n) LAUNCH(k_finish, grid, ENG_NT, cs, d_sstate, n, d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, merge, d_counter, d_gerr);
             if (merge) free_scratch(sc);
             dfree(d_counter, cs);

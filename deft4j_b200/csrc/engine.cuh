@@ -33,7 +33,14 @@
 
 namespace d4 {
 
-constexpr int ENG_NT = 256;
+// threads per block-in-flight and CTAs per SM the kernels are built for (A/B knobs: -DD4_ENG_NT=128 -DD4_ENG_MINB=7)
+#ifndef D4_ENG_NT
+#define D4_ENG_NT 256
+#endif
+#ifndef D4_ENG_MINB
+#define D4_ENG_MINB 4
+#endif
+constexpr int ENG_NT = D4_ENG_NT;
 constexpr int ERR_TREE = 11, ERR_ROUNDS = 12, ERR_WRITER = 2;  // internal-limit codes reported through gerr
 
 // parity-debug instrumentation (deft4cu_debug_trace): when armed, every candidate the selection callback sees
@@ -66,6 +73,15 @@ struct Cand {
     uint32_t pad2;
 };
 struct PVal { uint32_t mid; uint32_t pad; long long delta; };
+// memo tables of one CTA in global scratch (kept out of shared memory so that more CTAs fit on an SM; they are
+// probed by thread 0 or scanned by all threads a few hundred times per round)
+struct EngG {
+    unsigned long long pkey[MEMO_P];   // pass memo keys (open addressing); values in Eng::pvals
+    unsigned long long maskHash[MAXM];
+    unsigned long long tabHash[MAXT];
+    int tabTrialBits[MAXT];
+    unsigned char tabTrialArg[MAXT];
+};
 __device__ __forceinline__ long long cand_size(const Cand& c) { return c.payload + (c.tab.type == 2 ? c.hdr.bits : 0); }
 
 struct BlkView {
@@ -75,6 +91,7 @@ struct BlkView {
     uint32_t n;       // symbols (including a NOP left by a merge)
     uint32_t nwords;  // mask words
     uint64_t ulen;    // decoded length
+    uint64_t out_off; // pool offset of the block's first decoded byte
 };
 
 struct EngSmem {
@@ -93,15 +110,10 @@ struct EngSmem {
     int bestStored;
     long long sizeI, sizeC1, restMin;
     unsigned candIndex, bestIndex;
-    // pools and memo tables
-    unsigned long long maskHash[MAXM];
+    // pools and memo tables (the tables themselves live in global scratch, EngG)
     unsigned char recodeValid[MAXM];
     int nMasks;
-    unsigned long long tabHash[MAXT];
-    int tabTrialBits[MAXT];
-    unsigned char tabTrialArg[MAXT];
     int nTabs, fixedTab;
-    unsigned long long pkey[MEMO_P];
     int nP;
     unsigned char tabDc[MAXT];        // tabid -> cost-array slot (0xFF: none)
     unsigned short dcOwner[DCN_MAX];  // slot -> tabid (0xFFFF: free)
@@ -143,9 +155,13 @@ struct Eng {
     Tab* tabs;            // MAXT interned code tables
     Cand* recode;         // MAXM: recodeHuffman result per mask id
     PVal* pvals;          // MEMO_P pass memo values
+    EngG* G;
     short* dc;            // dcn arrays of maxn: per symbol, (literal cost - match cost) under one Tab
     uint32_t* hists;      // MAXM * 320: symbol histogram per mask id
     uint8_t* kind;        // maxn: 0 = not a match, else length symbol - 256
+    uint32_t* meta;       // maxn: match only: len-3 | dist symbol << 9 | extra bits of the match << 14
+    uint32_t* P;          // maxp: exclusive prefix sums of per-byte literal costs (nullptr: blocks too long, byte loops)
+    uint32_t maxp;
     uint32_t maxn;        // maxwords * 32
     int dcn;
     int tid;
@@ -201,7 +217,7 @@ struct Eng {
     // start of a new block (new symbol view): everything is forgotten
     __device__ __noinline__ void begin_block() {
         __syncthreads();
-        for (int k = tid; k < MEMO_P; k += ENG_NT) S->pkey[k] = 0;
+        for (int k = tid; k < MEMO_P; k += ENG_NT) G->pkey[k] = 0;
         for (int k = tid; k < MAXM; k += ENG_NT) S->recodeValid[k] = 0;
         if (tid < NCAND) { S->c[tid].mid = 0; S->c[tid].tabid = 0; S->c[tid].pad2 = 0; }
         for (int k = tid; k < MAXT; k += ENG_NT) S->tabDc[k] = 0xFF;
@@ -219,7 +235,7 @@ struct Eng {
         __syncthreads();
         const int nT = S->nTabs;
         for (int k = tid; k < nT; k += ENG_NT)
-            if (S->tabHash[k] == h) atomicMax(&S->tmpIdx, k);
+            if (G->tabHash[k] == h) atomicMax(&S->tmpIdx, k);
         __syncthreads();
         int hit = S->tmpIdx;
         if (hit >= 0) {
@@ -235,8 +251,8 @@ struct Eng {
             if (tid == 0) {
                 int slot = S->nTabs;
                 if (slot >= MAXT) { S->err = ERR_POOL; slot = MAXT - 1; } else S->nTabs = slot + 1;
-                S->tabHash[slot] = h;
-                S->tabTrialBits[slot] = TRIAL_UNSET;
+                G->tabHash[slot] = h;
+                G->tabTrialBits[slot] = TRIAL_UNSET;
                 S->tmpIdx = slot;
             }
             __syncthreads();
@@ -259,7 +275,7 @@ struct Eng {
         if (tid == 0) { S->tmpIdx = -1; S->redAny2 = 0; }
         __syncthreads();
         for (int k = tid; k < fresh; k += ENG_NT)
-            if (S->maskHash[k] == h) atomicMax(&S->tmpIdx, k);
+            if (G->maskHash[k] == h) atomicMax(&S->tmpIdx, k);
         __syncthreads();
         int hit = S->tmpIdx;
         if (hit >= 0) {
@@ -273,7 +289,7 @@ struct Eng {
         __syncthreads();
         if (hit < 0) {
             hit = fresh;
-            if (tid == 0) { S->maskHash[fresh] = h; S->recodeValid[fresh] = 0; S->nMasks = fresh + 1; }
+            if (tid == 0) { G->maskHash[fresh] = h; S->recodeValid[fresh] = 0; S->nMasks = fresh + 1; }
         }
         __syncthreads();
         P1(PR_INTERN_MASK);
@@ -290,7 +306,7 @@ struct Eng {
                 const int m = S->c[c].mid;
                 int k = 0;
                 while (k < nu && S->uniq[k] != m) k++;
-                if (k == nu) { S->uniq[nu] = m; S->uh[nu] = S->maskHash[m]; nu++; }
+                if (k == nu) { S->uniq[nu] = m; S->uh[nu] = G->maskHash[m]; nu++; }
                 S->remap[c] = k;
             }
             S->tmpIdx = nu;
@@ -315,9 +331,9 @@ struct Eng {
             for (int w = tid; w < 320; w += ENG_NT) hd[w] = hs[w];
         }
         if (tid < NCAND) S->c[tid].mid = (uint16_t)S->remap[tid];
-        if (tid < nu) S->maskHash[tid] = S->uh[tid];
+        if (tid < nu) G->maskHash[tid] = S->uh[tid];
         for (int k = tid; k < MAXM; k += ENG_NT) S->recodeValid[k] = 0;
-        for (int k = tid; k < MEMO_P; k += ENG_NT) S->pkey[k] = 0;
+        for (int k = tid; k < MEMO_P; k += ENG_NT) G->pkey[k] = 0;
         for (int k = tid; k < MAXT; k += ENG_NT) S->tabDc[k] = 0xFF;
         if (tid < DCN_MAX) S->dcOwner[tid] = 0xFFFF;
         __syncthreads();
@@ -338,7 +354,7 @@ struct Eng {
         x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
         unsigned h = (unsigned)x & (MEMO_P - 1);
         while (true) {
-            const unsigned long long k = S->pkey[h];
+            const unsigned long long k = G->pkey[h];
             if (k == key) return (int)h;
             if (k == 0) return -1 - (int)h;
             h = (h + 1) & (MEMO_P - 1);
@@ -374,6 +390,67 @@ struct Eng {
     // tables, DC_BLOCKED when a byte has no code (DeflateBlockHuffman.java:238-246).  It does not depend on the
     // mask, so every replace / least pass under the same tables reads it instead of walking the bytes again.
     static constexpr short DC_BLOCKED = 0x7FFF, DC_NOT_MATCH = 0x7FFE;
+    static constexpr uint32_t UNC = 1u << 20;  // prefix-sum cost of a byte without a code (a match has <= 258 bytes)
+
+    // P[j] = sum of literal costs of the block's decoded bytes before position j (positions count from the
+    // 16-byte boundary at or below the block's first byte), so a match's literal cost is P[end] - P[start].
+    // Coalesced 128-bit loads, one tile of ENG_NT * 16 bytes per step, CTA-wide scan.
+    __device__ __noinline__ void build_prefix(const uint8_t* L) {
+        __shared__ uint32_t s_wt[ENG_NT / 32];
+        for (int k = tid; k < 256; k += ENG_NT) S->hist[k] = L[k] ? (uint32_t)L[k] : UNC;
+        __syncthreads();
+        const uint64_t a0 = v.out_off & ~15ull;
+        const uint32_t head = (uint32_t)(v.out_off - a0);
+        const uint32_t endRel = head + (uint32_t)v.ulen;
+        const uint8_t* base = v.out + a0;
+        const int lane = tid & 31, wid = tid >> 5;
+        uint32_t carry = 0;
+        for (uint32_t T = 0; T <= endRel; T += ENG_NT * 16) {
+            const uint32_t idx = T + 16u * tid;
+            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+            uint32_t tot = 0;
+            if (idx < endRel) {
+                const uint4 q = *(const uint4*)(base + idx);
+                w0 = q.x; w1 = q.y; w2 = q.z; w3 = q.w;
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t wk = k < 4 ? w0 : k < 8 ? w1 : k < 12 ? w2 : w3;
+                    const uint32_t j = idx + k;
+                    tot += (j >= head && j < endRel) ? S->hist[(wk >> (8 * (k & 3))) & 0xff] : 0u;
+                }
+            }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += x;
+            }
+            if (lane == 31) s_wt[wid] = incl;
+            __syncthreads();
+            uint32_t wbase = 0, total = 0;
+#pragma unroll
+            for (int k = 0; k < ENG_NT / 32; k++) { const uint32_t x = s_wt[k]; if (k < wid) wbase += x; total += x; }
+            if (idx <= endRel) {  // second walk over the 16 bytes: running exclusive prefix, stored 4 at a time
+                uint32_t run = carry + wbase + incl - tot;
+                uint4* dst = (uint4*)(P + idx);
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const uint32_t wk = g == 0 ? w0 : g == 1 ? w1 : g == 2 ? w2 : w3;
+                    uint32_t o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t j = idx + 4 * g + k;
+                        o[k] = run;
+                        run += (j >= head && j < endRel) ? S->hist[(wk >> (8 * k)) & 0xff] : 0u;
+                    }
+                    dst[g] = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            carry += total;
+            __syncthreads();
+        }
+    }
+
     __device__ __noinline__ const short* ensure_dc(int c) {
         const Cand& cd = S->c[c];
         const int t = cd.tabid;
@@ -392,14 +469,47 @@ struct Eng {
         __syncthreads();
         slot = S->tmpIdx;
         short* d = dc + (size_t)slot * maxn;
-        for (uint32_t i = tid; i < v.n; i += ENG_NT) {
-            short x = DC_NOT_MATCH;
-            if (kind[i]) {
-                const uint32_t s = v.sym[i];
-                const int lit = lit_cost(cd.tab.L, v.symout[i], sym_len(s));
-                x = lit < 0 ? DC_BLOCKED : (short)(lit - ref_cost(cd.tab, s));
+        const bool prefix = P != nullptr && v.ulen + 64 <= (uint64_t)maxp;
+        if (prefix) {
+            build_prefix(cd.tab.L);
+            const uint32_t a0 = (uint32_t)(v.out_off & ~15ull);
+            // 8 consecutive symbols per thread, every load of the batch issued before the first use
+            for (uint32_t i0 = (uint32_t)tid * 8; i0 < v.nwords * 32; i0 += ENG_NT * 8) {
+                const uint2 kk = *(const uint2*)(kind + i0);
+                const uint4 ma = *(const uint4*)(meta + i0), mb = *(const uint4*)(meta + i0 + 4);
+                const uint32_t mt[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+                uint32_t st[8], lit[8];
+                int kq[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    kq[u] = (int)(((u < 4 ? kk.x : kk.y) >> (8 * (u & 3))) & 0xff);
+                    if (i0 + u >= v.n) kq[u] = 0;
+                    st[u] = kq[u] ? v.symout[i0 + u] - a0 : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) lit[u] = kq[u] ? P[st[u] + (mt[u] & 0x1FF) + 3] - P[st[u]] : 0u;
+                uint32_t o[4];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    short x = DC_NOT_MATCH;
+                    if (kq[u]) {
+                        const int ref = cd.tab.L[256 + kq[u]] + cd.tab.D[(mt[u] >> 9) & 31] + (int)((mt[u] >> 14) & 31);
+                        x = lit[u] >= UNC ? DC_BLOCKED : (short)((int)lit[u] - ref);
+                    }
+                    if (u & 1) o[u >> 1] |= (uint32_t)(unsigned short)x << 16; else o[u >> 1] = (uint32_t)(unsigned short)x;
+                }
+                *(uint4*)(d + i0) = make_uint4(o[0], o[1], o[2], o[3]);
             }
-            d[i] = x;
+        } else {
+            for (uint32_t i = tid; i < v.n; i += ENG_NT) {
+                short x = DC_NOT_MATCH;
+                if (kind[i]) {
+                    const uint32_t s = v.sym[i];
+                    const int lit = lit_cost(cd.tab.L, v.symout[i], sym_len(s));
+                    x = lit < 0 ? DC_BLOCKED : (short)(lit - ref_cost(cd.tab, s));
+                }
+                d[i] = x;
+            }
         }
         __syncthreads();
         return d;
@@ -448,20 +558,27 @@ struct Eng {
         uint32_t* md = maskp(fresh);
         long long saved = 0;
         const int lane = tid & 31;
-        for (uint32_t base = (tid >> 5) * 32; base < v.n; base += ENG_NT) {
-            const uint32_t i = base + lane;
-            bool rep = false;
-            const uint32_t word = m[base >> 5];
-            if (i < v.n && kind[i] && !((word >> lane) & 1)) {
-                const int x = d[i];
-                rep = prune ? x <= 0 : x < 0;
-                if (rep) { saved -= x; hist_delta_replace(i); }
+        {   // 8 consecutive symbols (one mask byte) per thread; loads batched
+            const uint8_t* mb = (const uint8_t*)m;
+            uint8_t* mdb = (uint8_t*)md;
+            bool any = false;
+            for (uint32_t i0 = (uint32_t)tid * 8; i0 < v.nwords * 32; i0 += ENG_NT * 8) {
+                const uint2 kk = *(const uint2*)(kind + i0);
+                const uint4 dq = *(const uint4*)(d + i0);
+                const uint32_t ob = mb[i0 >> 3];
+                const uint32_t dw[4] = {dq.x, dq.y, dq.z, dq.w};
+                uint32_t nbits = 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int k = (int)(((u < 4 ? kk.x : kk.y) >> (8 * (u & 3))) & 0xff);
+                    const int x = (int)(short)((u & 1) ? (dw[u >> 1] >> 16) : (dw[u >> 1] & 0xffff));
+                    if (i0 + u < v.n && k && !((ob >> u) & 1) && (prune ? x <= 0 : x < 0)) { saved -= x; nbits |= 1u << u; }
+                }
+                mdb[i0 >> 3] = (uint8_t)(ob | nbits);
+                for (uint32_t b = nbits; b; b &= b - 1) hist_delta_replace(i0 + (uint32_t)__ffs((int)b) - 1);
+                any |= nbits != 0;
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, rep);
-            if (lane == 0) {
-                md[base >> 5] = word | bal;
-                if (bal) S->redAny = 1;
-            }
+            if (any) S->redAny = 1;
         }
         for (int dd = 16; dd > 0; dd >>= 1) saved += __shfl_xor_sync(0xffffffffu, saved, dd);
         if (lane == 0 && saved) atomicAdd(&S->red, (unsigned long long)saved);
@@ -474,7 +591,7 @@ struct Eng {
         if (tid == 0) {
             PVal pv; pv.mid = (uint32_t)newmid; pv.pad = 0; pv.delta = (long long)S->red;
             pvals[slot] = pv;
-            S->pkey[slot] = key;
+            G->pkey[slot] = key;
             S->nP++;
             cd.mid = (uint16_t)newmid;
             cd.payload -= pv.delta;
@@ -512,21 +629,31 @@ struct Eng {
         const int lane = tid & 31;
         // per length symbol: sum of (literal - match) cost, count, blocked (:386-420); lanes of a warp that hold
         // the same length symbol are summed with one shared-memory atomic
-        for (uint32_t base = (tid >> 5) * 32; base < v.n; base += ENG_NT) {
-            const uint32_t i = base + lane;
-            const int k = i < v.n ? kind[i] : 0;
-            const bool live = k && !((m[base >> 5] >> lane) & 1);
-            const int x = live ? d[i] : 0;
-            const bool blocked = live && x == DC_BLOCKED;
-            const int bin = live ? k - 1 : 31;
-            const unsigned grp = __match_any_sync(0xffffffffu, bin);
-            const int xs = __reduce_add_sync(grp, (live && !blocked) ? x : 0);
-            const int cn = __reduce_add_sync(grp, (live && !blocked) ? 1 : 0);
-            const unsigned anyBlocked = __ballot_sync(0xffffffffu, blocked) & grp;
-            if (live && lane == __ffs(grp) - 1) {
-                atomicOr(&S->leastSeen, 1u << bin);
-                if (anyBlocked) atomicOr(&S->leastBlocked, 1u << bin);
-                if (cn) { atomicAdd(&S->leastSum[bin], xs); atomicAdd(&S->leastCnt[bin], cn); }
+        const uint8_t* mbytes = (const uint8_t*)m;
+        // the warp-wide votes below need every lane of a warp in the loop: the bound is per warp, loads are guarded
+        for (uint32_t wb = (uint32_t)(tid >> 5) * 256; wb < v.nwords * 32; wb += ENG_NT * 8) {
+            const uint32_t i0 = wb + (uint32_t)lane * 8;
+            const bool inr = i0 < v.nwords * 32;
+            const uint2 kk = inr ? *(const uint2*)(kind + i0) : make_uint2(0, 0);
+            const uint4 dq = inr ? *(const uint4*)(d + i0) : make_uint4(0, 0, 0, 0);
+            const uint32_t ob = inr ? mbytes[i0 >> 3] : 0u;
+            const uint32_t dw[4] = {dq.x, dq.y, dq.z, dq.w};
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int k = (i0 + u < v.n) ? (int)(((u < 4 ? kk.x : kk.y) >> (8 * (u & 3))) & 0xff) : 0;
+                const bool live = k && !((ob >> u) & 1);
+                const int x = live ? (int)(short)((u & 1) ? (dw[u >> 1] >> 16) : (dw[u >> 1] & 0xffff)) : 0;
+                const bool blocked = live && x == DC_BLOCKED;
+                const int bin = live ? k - 1 : 31;
+                const unsigned grp = __match_any_sync(0xffffffffu, bin);
+                const int xs = __reduce_add_sync(grp, (live && !blocked) ? x : 0);
+                const int cn = __reduce_add_sync(grp, (live && !blocked) ? 1 : 0);
+                const unsigned anyBlocked = __ballot_sync(0xffffffffu, blocked) & grp;
+                if (live && lane == __ffs(grp) - 1) {
+                    atomicOr(&S->leastSeen, 1u << bin);
+                    if (anyBlocked) atomicOr(&S->leastBlocked, 1u << bin);
+                    if (cn) { atomicAdd(&S->leastSum[bin], xs); atomicAdd(&S->leastCnt[bin], cn); }
+                }
             }
         }
         __syncthreads();
@@ -547,13 +674,18 @@ struct Eng {
         if (rem >= 0) {
             const int fresh = S->nMasks;
             uint32_t* md = maskp(fresh);
-            for (uint32_t base = (tid >> 5) * 32; base < v.n; base += ENG_NT) {
-                const uint32_t i = base + lane;
-                const uint32_t word = m[base >> 5];
-                const bool rep = i < v.n && kind[i] == rem + 1;
-                if (rep && !((word >> lane) & 1)) hist_delta_replace(i);
-                const unsigned bal = __ballot_sync(0xffffffffu, rep);
-                if (lane == 0) md[base >> 5] = word | bal;
+            uint8_t* mdb = (uint8_t*)md;
+            for (uint32_t i0 = (uint32_t)tid * 8; i0 < v.nwords * 32; i0 += ENG_NT * 8) {
+                const uint2 kk = *(const uint2*)(kind + i0);
+                const uint32_t ob = mbytes[i0 >> 3];
+                uint32_t nbits = 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int k = (int)(((u < 4 ? kk.x : kk.y) >> (8 * (u & 3))) & 0xff);
+                    if (i0 + u < v.n && k == rem + 1) nbits |= 1u << u;
+                }
+                mdb[i0 >> 3] = (uint8_t)(ob | nbits);
+                for (uint32_t b = nbits & ~ob; b; b &= b - 1) hist_delta_replace(i0 + (uint32_t)__ffs((int)b) - 1);
             }
             __syncthreads();
             newmid = intern_mask();
@@ -562,7 +694,7 @@ struct Eng {
         if (tid == 0) {
             PVal pv; pv.mid = (uint32_t)newmid; pv.pad = 0; pv.delta = -(long long)S->red;
             pvals[slot] = pv;
-            S->pkey[slot] = key;
+            G->pkey[slot] = key;
             S->nP++;
             cd.mid = (uint16_t)newmid;
             cd.payload -= pv.delta;
@@ -746,7 +878,7 @@ struct Eng {
                 cd.payload = pay;
                 PVal pv; pv.mid = (uint32_t)mid; pv.pad = 0; pv.delta = pay;
                 pvals[slot] = pv;
-                S->pkey[slot] = key;
+                G->pkey[slot] = key;
                 S->nP++;
             }
         }
@@ -800,12 +932,11 @@ struct Eng {
     __device__ __noinline__ void trials(int nb) {
         P0();
         __shared__ int s_miss[4];
-        if (tid < nb) s_miss[tid] = (S->tabTrialBits[S->c[C_B1 + tid].tabid] == TRIAL_UNSET) || g_trace != nullptr;
+        if (tid < nb) s_miss[tid] = (G->tabTrialBits[S->c[C_B1 + tid].tabid] == TRIAL_UNSET) || g_trace != nullptr;
         __syncthreads();
         // evaluate the misses: thread j -> (base j / 56, strategy j % 56)
-        {
-            int j = tid;
-            if (j < nb * 56 && s_miss[j / 56]) {
+        for (int j = tid; j < nb * 56; j += ENG_NT) {
+            if (s_miss[j / 56]) {
                 Hdr h;
                 TreeWsCL ws;
                 if (hdr_trial(S->c[C_B1 + j / 56].tab, c_trial_flags[j % 56], h, ws)) S->err = ERR_TREE;
@@ -822,15 +953,15 @@ struct Eng {
             int best = 0x7fffffff, arg = 0;
             for (int k = 0; k < 56; k++) { int bts = S->trialBits[tid * 56 + k]; if (bts < best) { best = bts; arg = k; } }
             const int t = S->c[C_B1 + tid].tabid;   // two bases with one Tab write the same values
-            S->tabTrialBits[t] = best;
-            S->tabTrialArg[t] = (unsigned char)arg;
+            G->tabTrialBits[t] = best;
+            G->tabTrialArg[t] = (unsigned char)arg;
         }
         __syncthreads();
         // selection in reference order: base b's 56 candidates; the first minimum is the only one that
         // can replace the incumbent
         for (int b = 0; b < nb; b++) {
             const int t = S->c[C_B1 + b].tabid;
-            const int bits = S->tabTrialBits[t], arg = S->tabTrialArg[t];
+            const int bits = G->tabTrialBits[t], arg = G->tabTrialArg[t];
             const long long sz = S->c[C_B1 + b].payload + bits;
             const bool better = sz < S->bestSize;
             __syncthreads();

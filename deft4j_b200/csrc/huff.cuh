@@ -17,19 +17,21 @@ constexpr uint16_t NODE_NONE = 0xFFFF;
 
 template <int MAXLEAF, int MAXN>
 struct TreeWs {
-    unsigned long long heap[MAXLEAF + 2];  // (weight << 16) | node id
+    union {                                // the DFS stack is only used once the heap is empty
+        unsigned long long heap[MAXLEAF + 2];  // (weight << 16) | node id
+        uint32_t stack[MAXLEAF + 4];
+    };
     uint16_t parent[MAXN], left[MAXN], right[MAXN];
     uint8_t side[MAXN];
     uint16_t value[MAXLEAF + 2];      // leaf id -> symbol index (dummies included)
     uint16_t leafDepth[MAXLEAF + 2];
     uint16_t first[MAXLEAF + 4];      // first leaf (DFS order) at each depth == depthMap.get(d).get(0)
-    uint32_t stack[MAXLEAF + 4];
 };
 
 // Returns 0 on success, 1 when the tree cannot be balanced (the reference throws AssertionError there).
 // Node ids: [0, nleaf) leaves in insertion order, then internal nodes; MAXN >= 2 * (MAXLEAF + 2).  lens[0..n) receives the code lengths (0 for unused symbols).
 template <int MAXLEAF, int MAXN>
-D4_DEV int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, TreeWs<MAXLEAF, MAXN>& ws) {
+D4_DEV_BIG int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, TreeWs<MAXLEAF, MAXN>& ws) {
     int hs = 0;  // heap size
     auto W = [](unsigned long long k) { return k >> 16; };
     auto add = [&](unsigned long long x) {  // PriorityQueue.offer + siftUp
@@ -196,7 +198,7 @@ D4_DEV int hdr_pairs_bits(const Hdr& h) {
 
 // rewriteHeader (:484-577): pack (HuffmanTable.java:70-159) straight into pairs, build the header code,
 // size it, trim.
-D4_DEV int hdr_rewrite(const Tab& t, int flags, Hdr& h, TreeWsCL& ws) {
+D4_DEV_BIG int hdr_rewrite(const Tab& t, int flags, Hdr& h, TreeWsCL& ws) {
     const bool ohh = flags & 1, use8 = flags & 2, use7 = flags & 4, alt8 = flags & 8, noRep = flags & 16,
                noZRep = flags & 32, noZRep2 = flags & 64, noRepZeros = flags & 128;
     const int nL = t.nL, n = t.nL + t.nD;
@@ -250,7 +252,7 @@ D4_DEV int hdr_rewrite(const Tab& t, int flags, Hdr& h, TreeWsCL& ws) {
 // replaceRLERunsWithLiteralsIfSmaller (:321-332) via replaceWithLiteralsIfSmaller (:222-296): a run is
 // replaced by `run` plain lengths when those cost less (prune: no more) than the run code; only when
 // the repeated value has a header code.  In-place expansion from the back.
-D4_DEV void hdr_replace_runs(Hdr& h, bool prune) {
+D4_DEV_BIG void hdr_replace_runs(Hdr& h, bool prune) {
     int newNp = 0, saved = 0;
     bool any = false;
     for (int i = 0; i < h.np; i++) {
@@ -290,7 +292,7 @@ D4_DEV void hdr_replace_runs(Hdr& h, bool prune) {
 
 // recodeHeader (:579-629): new header code from the existing pairs; numCodelenLens is NOT reset
 // (SURVEY.md H8), only trimmed further.
-D4_DEV int hdr_recode(Hdr& h, TreeWsCL& ws) {
+D4_DEV_BIG int hdr_recode(Hdr& h, TreeWsCL& ws) {
     if (hdr_build_code(h, ws)) return 1;
     hdr_trim(h);
     h.bits = 5 + 5 + 4 + h.ncl * 3 + hdr_pairs_bits(h);

@@ -79,26 +79,45 @@ struct EngScratch {       // global scratch, one slice per CTA
     Tab* tabs;            // MAXT
     Cand* recode;         // MAXM
     PVal* pvals;          // MEMO_P
+    EngG* g;              // 1
     short* dc;            // dcn * maxwords * 32
     uint32_t* hists;      // (MAXM + NCAND) * 320
     uint8_t* kind;        // maxwords * 32
+    uint32_t* meta;       // maxwords * 32
+    uint32_t* P;          // maxp per CTA, or nullptr
+    uint32_t maxp;
     uint32_t maxwords;
     int dcn;
+    unsigned* smctr;      // 256 zeroed counters: CTAs landing on the same SM draw distinct leader-warp rotations
 };
 
 __device__ inline void eng_init(Eng& e, EngSmem* S, const EngScratch& sc, int cta) {
     e.S = S;
-    e.tid = threadIdx.x;
+    // Serial sections (Huffman trees, header models) run in logical thread 0.  A warp's scheduler is fixed by
+    // (warp id % 4), so if every CTA of an SM used its physical warp 0 all serial code of the SM would queue on one
+    // scheduler while three idle: each CTA rotates its logical warps by a distinct amount instead.
+    __shared__ int s_rot;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_rot = (int)(atomicAdd(&sc.smctr[smid & 255u], 1u) & 3u);
+    }
+    __syncthreads();
+    e.tid = (int)((threadIdx.x + 32u * (unsigned)s_rot) & (ENG_NT - 1));
     e.maxwords = sc.maxwords;
     e.masks = sc.masks + (size_t)cta * (MAXM + NCAND) * sc.maxwords;
     e.tabs = sc.tabs + (size_t)cta * MAXT;
     e.recode = sc.recode + (size_t)cta * MAXM;
     e.pvals = sc.pvals + (size_t)cta * MEMO_P;
+    e.G = sc.g + cta;
     e.maxn = sc.maxwords * 32;
     e.dcn = sc.dcn;
     e.dc = sc.dc + (size_t)cta * sc.dcn * e.maxn;
     e.hists = sc.hists + (size_t)cta * (MAXM + NCAND) * 320;
     e.kind = sc.kind + (size_t)cta * e.maxn;
+    e.meta = sc.meta + (size_t)cta * e.maxn;
+    e.maxp = sc.maxp;
+    e.P = sc.P ? sc.P + (size_t)cta * sc.maxp : nullptr;
     if (threadIdx.x == 0) S->err = 0;
     __syncthreads();
 }
@@ -107,10 +126,15 @@ __device__ inline void eng_init(Eng& e, EngSmem* S, const EngScratch& sc, int ct
 __device__ inline void eng_adopt_mask0(Eng& e) {
     __syncthreads();
     const unsigned long long h = e.hash_words(e.maskp(0), (int)e.v.nwords);
-    if (e.tid == 0) { e.S->maskHash[0] = h; e.S->recodeValid[0] = 0; e.S->nMasks = 1; e.S->c[C_B].mid = 0; }
+    if (e.tid == 0) { e.G->maskHash[0] = h; e.S->recodeValid[0] = 0; e.S->nMasks = 1; e.S->c[C_B].mid = 0; }
     for (uint32_t i = e.tid; i < e.v.n; i += ENG_NT) {
         const uint32_t s = e.v.sym[i];
-        e.kind[i] = sym_is_match(s) ? (uint8_t)(sym_lensym(s) - 256) : (uint8_t)0;
+        const bool mt = sym_is_match(s);
+        e.kind[i] = mt ? (uint8_t)(sym_lensym(s) - 256) : (uint8_t)0;
+        if (mt) {
+            const int ds = dist_sym(sym_dist(s));
+            e.meta[i] = (s & 0x1FF) | ((uint32_t)ds << 9) | ((uint32_t)(len_ebits_of(sym_lensym(s)) + dist_ebits_of(ds)) << 14);
+        }
     }
     __syncthreads();
     e.pass_hist_full(0);
@@ -133,7 +157,7 @@ __device__ inline void eng_load(Eng& e, const BlkState& b, const uint32_t* maskS
 // --------------------------------------------------------------------------------------------------
 // phase A
 // --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ENG_NT)
+__global__ void __launch_bounds__(ENG_NT, D4_ENG_MINB)
 k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __restrict__ bs, RoundLog* __restrict__ logs,
              const uint32_t* __restrict__ sym, const uint32_t* __restrict__ symout, const uint8_t* __restrict__ out,
              uint32_t* __restrict__ maskpool, EngScratch sc, unsigned* __restrict__ counter, int* __restrict__ gerr) {
@@ -155,6 +179,7 @@ k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __rest
         e.v.n = b.n_sym;
         e.v.nwords = (b.n_sym + 31) / 32;
         e.v.ulen = b.out_len;
+        e.v.out_off = b.out_off;
 #ifdef D4_VERIFY
         e.vgerr = gerr; e.vjob = (int)job;
 #endif
@@ -325,6 +350,7 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
                 e.v.n = nA + nB;
                 e.v.nwords = (nA + nB + 31) / 32;
                 e.v.ulen = c.out_len + nx.out_len;
+                e.v.out_off = c.out_off;
                 e.begin_block();
                 uint32_t* m = e.maskp(0);
                 for (uint32_t k = tid; k < e.v.nwords; k += ENG_NT) m[k] = 0;
@@ -406,7 +432,7 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
 }
 
 // streams are taken from a queue by a grid sized to the machine, so the engine scratch is per CTA, not per stream
-__global__ void __launch_bounds__(ENG_NT)
+__global__ void __launch_bounds__(ENG_NT, D4_ENG_MINB)
 k_finish(StreamState* __restrict__ streams, uint32_t nstreams, BlkState* __restrict__ bs, const RoundLog* __restrict__ logs,
          uint32_t* __restrict__ sym, const uint32_t* __restrict__ symout, const uint8_t* __restrict__ out,
          uint32_t* __restrict__ maskpool, EngScratch sc, int merge, unsigned* __restrict__ counter, int* __restrict__ gerr) {

@@ -321,3 +321,15 @@ def test_segmented_parse_matches_oracle(gpu, oracle, seg, monkeypatch):
     ref = gpu.optimise_batch(streams, True)
     for a, b in zip(res, ref):
         assert (a["status"], a["saved_bits"], a["out"], a["crc32"]) == (b["status"], b["saved_bits"], b["out"], b["crc32"])
+
+
+def test_literal_cost_paths_agree(gpu, oracle, monkeypatch):
+    """The engine takes a match's literal cost from prefix sums over the block's decoded bytes when the scratch for
+    them fits, and walks the bytes otherwise (very long blocks): both must give the oracle's bytes."""
+    raw = _deflate(W.c2_text(120_000, seed=21))
+    monkeypatch.setenv("D4_NO_PREFIX", "1")
+    compare_stream(gpu, oracle, raw, True, check_model=False)
+    slow = gpu.optimise_batch([raw] + W.c3_streams(2, first=7), True)
+    monkeypatch.delenv("D4_NO_PREFIX")
+    fast = gpu.optimise_batch([raw] + W.c3_streams(2, first=7), True)
+    assert [(r["saved_bits"], r["out"]) for r in slow] == [(r["saved_bits"], r["out"]) for r in fast]
