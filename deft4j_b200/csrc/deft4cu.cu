@@ -344,10 +344,11 @@ class Batch {
             for (int it = 0; it < 64; it++) {
                 int changed = 0;
                 D4_CUDA_CHECK(cudaMemsetAsync(d_changed, 0, sizeof(int), cs));
-                for (int rep = 0; rep < 3; rep++) LAUNCH(k_lz_jump, (unsigned)((ob + 255) / 256), 256, cs, d_ptr, ob, d_changed);
+                for (int rep = 0; rep < (it == 0 ? 2 : 1); rep++) LAUNCH(k_lz_jump, (unsigned)((ob + 255) / 256), 256, cs, d_ptr, ob, d_changed);
                 D4_CUDA_CHECK(cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, cs));
                 D4_CUDA_CHECK(cudaStreamSynchronize(cs));
                 if (!changed) break;
+                if (it == 63) { set_error("LZ77 resolve did not converge"); return DEFT4CU_ERR_CUDA; }
             }
             LAUNCH(k_lz_gather, (unsigned)((ob + 255) / 256), 256, cs, d_out, d_ptr, ob);
             dfree(d_ptr, cs); dfree(d_changed, cs);
@@ -421,6 +422,8 @@ class Batch {
         // literal-cost prefix sums need 4 bytes per decoded byte of the longest block per CTA: used when that fits 4 GiB
         sc.P = nullptr;
         sc.maxp = 0;
+        sc.prefix_ratio = 24;
+        if (const char* pr = getenv("D4_PREFIX_RATIO")) sc.prefix_ratio = (uint32_t)atoi(pr);
         const uint64_t need = ((maxu + 64 + ENG_NT * 16 + 15) & ~15ull);
         if (!getenv("D4_NO_PREFIX") && need < (1ull << 31) && need * 4 * grid <= (4ull << 30)) {
             sc.maxp = (uint32_t)need;

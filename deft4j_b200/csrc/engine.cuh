@@ -162,6 +162,7 @@ struct Eng {
     uint32_t* meta;       // maxn: match only: len-3 | dist symbol << 9 | extra bits of the match << 14
     uint32_t* P;          // maxp: exclusive prefix sums of per-byte literal costs (nullptr: blocks too long, byte loops)
     uint32_t maxp;
+    uint32_t prefixRatio; // use P when decoded bytes per symbol >= this
     uint32_t maxn;        // maxwords * 32
     int dcn;
     int tid;
@@ -469,7 +470,9 @@ struct Eng {
         __syncthreads();
         slot = S->tmpIdx;
         short* d = dc + (size_t)slot * maxn;
-        const bool prefix = P != nullptr && v.ulen + 64 <= (uint64_t)maxp;
+        // prefix sums pay off when matches are long (one pass over the bytes instead of one per match byte); on
+        // ordinary text (about 4 decoded bytes per symbol) the per-match loops move far fewer bytes through DRAM
+        const bool prefix = P != nullptr && v.ulen + 64 <= (uint64_t)maxp && v.ulen >= (uint64_t)prefixRatio * v.n;
         if (prefix) {
             build_prefix(cd.tab.L);
             const uint32_t a0 = (uint32_t)(v.out_off & ~15ull);

@@ -30,7 +30,8 @@ struct BlkState {
     uint64_t bit_pos;     // position of the 3-bit header in the rewritten stream
     long long size_bits;  // getSizeBits(bit_pos + 3)
 };
-struct RoundLog { long long sizeI[MAXR], sizeC1[MAXR], restMin[MAXR], best[MAXR]; };
+struct RoundRec { long long sizeI, sizeC1, restMin, best; };   // one optimiseBlock round of phase A
+struct RoundLog { RoundRec r[MAXR]; };
 
 struct StreamState {
     uint64_t blk_base;
@@ -86,6 +87,7 @@ struct EngScratch {       // global scratch, one slice per CTA
     uint32_t* meta;       // maxwords * 32
     uint32_t* P;          // maxp per CTA, or nullptr
     uint32_t maxp;
+    uint32_t prefix_ratio;
     uint32_t maxwords;
     int dcn;
     unsigned* smctr;      // 256 zeroed counters: CTAs landing on the same SM draw distinct leader-warp rotations
@@ -117,6 +119,7 @@ __device__ inline void eng_init(Eng& e, EngSmem* S, const EngScratch& sc, int ct
     e.kind = sc.kind + (size_t)cta * e.maxn;
     e.meta = sc.meta + (size_t)cta * e.maxn;
     e.maxp = sc.maxp;
+    e.prefixRatio = sc.prefix_ratio;
     e.P = sc.P ? sc.P + (size_t)cta * sc.maxp : nullptr;
     if (threadIdx.x == 0) S->err = 0;
     __syncthreads();
@@ -189,7 +192,8 @@ k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __rest
         while (true) {
             e.optimise_block(-1);
             if (tid == 0 && r < MAXR) {
-                lg.sizeI[r] = S.sizeI; lg.sizeC1[r] = S.sizeC1; lg.restMin[r] = S.restMin; lg.best[r] = S.bestSize;
+                RoundRec rr; rr.sizeI = S.sizeI; rr.sizeC1 = S.sizeC1; rr.restMin = S.restMin; rr.best = S.bestSize;
+                lg.r[r] = rr;
             }
             const bool improved = S.bestSize < S.sizeI;
             __syncthreads();
@@ -240,48 +244,72 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
     const uint32_t nb = st.n_blocks;
 
     // ---- replay of DeflateStream.optimise (:496-566) with the real bit position --------------------
-    if (tid == 0) {
-        long long pos = 0, saved = 0;
-        for (uint32_t k = 0; k < nb; k++) {
-            BlkState& b = B[k];
-            if (b.out_len > 0 || (k == 0 && nb == 1)) {
-                if (b.cand.tab.type == 0) {  // stored blocks have no candidates
-                    pos += 3;
-                    pos += stored_size(b.out_len, pos);
-                } else {
-                    const RoundLog& lg = logs[st.blk_base + k];
-                    int r = 0;
-                    while (true) {
-                        pos += 3;
-                        const long long I = lg.sizeI[r], C1 = lg.sizeC1[r], R = lg.restMin[r], W = lg.best[r];
-                        const long long m1 = I < C1 ? I : C1;
-                        bool storedWins = false;
-                        long long Ssz = 0;
-                        if (b.out_len <= 65535) {
-                            Ssz = stored_size(b.out_len, pos);
-                            storedWins = Ssz < m1 && Ssz <= R;
-                        }
-                        if (storedWins) {
-                            saved += I - Ssz;
-                            b.cand.tab.type = 0;
-                            pos += stored_size(b.out_len, pos);
-                            // next pass over the (now stored) block finds nothing
+    // The walk is sequential in `pos` (one thread), so the CTA stages what it reads — block type, decoded length and
+    // the first rounds of the log — in shared memory a tile of blocks at a time (the engine's shared state is not
+    // live yet); the serial loop then never waits on global memory.
+    {
+        constexpr int RT = 64, RR = 4;   // blocks per tile, rounds staged per block
+        struct Tile { unsigned long long out_len[RT]; int type[RT]; RoundRec rr[RT][RR]; };
+        static_assert(sizeof(Tile) <= sizeof(EngSmem), "replay tile must fit in the engine's shared storage");
+        Tile& T = *reinterpret_cast<Tile*>(&S);
+        __shared__ long long s_rpos, s_rsaved;
+        __shared__ int s_stop;
+        if (tid == 0) { s_rpos = 0; s_rsaved = 0; s_stop = 0; }
+        __syncthreads();
+        for (uint32_t t0 = 0; t0 < nb && !s_stop; t0 += RT) {
+            const uint32_t cnt = nb - t0 < RT ? nb - t0 : RT;
+            for (uint32_t k = tid; k < cnt; k += ENG_NT) { T.out_len[k] = B[t0 + k].out_len; T.type[k] = B[t0 + k].cand.tab.type; }
+            for (uint32_t q = tid; q < cnt * RR; q += ENG_NT) T.rr[q / RR][q % RR] = logs[st.blk_base + t0 + q / RR].r[q % RR];
+            __syncthreads();
+            if (tid == 0) {
+                long long pos = s_rpos, saved = s_rsaved;
+                for (uint32_t kk = 0; kk < cnt; kk++) {
+                    const uint32_t k = t0 + kk;
+                    const unsigned long long out_len = T.out_len[kk];
+                    if (out_len > 0 || (k == 0 && nb == 1)) {
+                        if (T.type[kk] == 0) {  // stored blocks have no candidates
                             pos += 3;
-                            pos += stored_size(b.out_len, pos);
-                            break;
+                            pos += stored_size(out_len, pos);
+                        } else {
+                            const RoundLog& lg = logs[st.blk_base + k];
+                            int r = 0;
+                            while (true) {
+                                pos += 3;
+                                const RoundRec rr = r < RR ? T.rr[kk][r] : lg.r[r];
+                                const long long I = rr.sizeI, C1 = rr.sizeC1, R = rr.restMin, W = rr.best;
+                                const long long m1 = I < C1 ? I : C1;
+                                bool storedWins = false;
+                                long long Ssz = 0;
+                                if (out_len <= 65535) {
+                                    Ssz = stored_size(out_len, pos);
+                                    storedWins = Ssz < m1 && Ssz <= R;
+                                }
+                                if (storedWins) {
+                                    saved += I - Ssz;
+                                    B[k].cand.tab.type = 0;
+                                    pos += stored_size(out_len, pos);
+                                    // next pass over the (now stored) block finds nothing
+                                    pos += 3;
+                                    pos += stored_size(out_len, pos);
+                                    break;
+                                }
+                                if (W < I) { saved += I - W; pos += W; r++; continue; }
+                                pos += I;
+                                break;
+                            }
                         }
-                        if (W < I) { saved += I - W; pos += W; r++; continue; }
-                        pos += I;
+                    } else {  // empty block: removed, and the reference's loop ends here (H6)
+                        saved += blk_size(B[k], pos + 3) + 3;
+                        B[k].alive = 0;
+                        s_stop = 1;
                         break;
                     }
                 }
-            } else {  // empty block: removed, and the reference's loop ends here (H6)
-                saved += blk_size(b, pos + 3) + 3;
-                b.alive = 0;
-                break;
+                s_rpos = pos; s_rsaved = saved;
             }
+            __syncthreads();
         }
-        s_saved = saved;
+        if (tid == 0) { s_saved = s_rsaved; S.err = 0; }  // the tile overlaid the engine state: start it clean
     }
     __syncthreads();
 
@@ -412,22 +440,51 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
     __syncthreads();
 
     // ---- layout: DeflateStream.getSizeBits (:171-182) + BFINAL from list position (:128-145) ----------
-    if (tid == 0) {
-        long long size = 0;
-        int last = -1;
-        for (uint32_t k = 0; k < nb; k++) {
-            BlkState& b = B[k];
-            if (!b.alive) continue;
-            b.bit_pos = (uint64_t)size;
-            size += 3;
-            b.size_bits = blk_size(b, size);
-            size += b.size_bits;
-            b.bfinal = 0;
-            last = (int)k;
+    // sequential in the running size; inputs and outputs are staged through shared memory like the replay above
+    {
+        constexpr int LT = 128;
+        struct LTile { unsigned long long out_len[LT], bit_pos[LT]; long long csize[LT], size_bits[LT]; int type[LT], alive[LT]; };
+        static_assert(sizeof(LTile) <= sizeof(EngSmem), "layout tile must fit in the engine's shared storage");
+        __syncthreads();
+        LTile& T = *reinterpret_cast<LTile*>(&S);
+        __shared__ long long s_size;
+        __shared__ int s_last;
+        if (tid == 0) { s_size = 0; s_last = -1; }
+        __syncthreads();
+        for (uint32_t t0 = 0; t0 < nb; t0 += LT) {
+            const uint32_t cnt = nb - t0 < LT ? nb - t0 : LT;
+            for (uint32_t k = tid; k < cnt; k += ENG_NT) {
+                const BlkState& b = B[t0 + k];
+                T.out_len[k] = b.out_len; T.type[k] = b.cand.tab.type; T.alive[k] = b.alive; T.csize[k] = cand_size(b.cand);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                long long size = s_size;
+                int last = s_last;
+                for (uint32_t k = 0; k < cnt; k++) {
+                    if (!T.alive[k]) continue;
+                    T.bit_pos[k] = (unsigned long long)size;
+                    size += 3;
+                    T.size_bits[k] = T.type[k] == 0 ? stored_size(T.out_len[k], size) : T.csize[k];
+                    size += T.size_bits[k];
+                    last = (int)(t0 + k);
+                }
+                s_size = size; s_last = last;
+            }
+            __syncthreads();
+            for (uint32_t k = tid; k < cnt; k += ENG_NT) {
+                if (!T.alive[k]) continue;
+                BlkState& b = B[t0 + k];
+                b.bit_pos = T.bit_pos[k]; b.size_bits = T.size_bits[k]; b.bfinal = 0;
+            }
+            __syncthreads();
         }
-        if (last >= 0) B[last].bfinal = 1;
-        st.total_bits = (uint64_t)size;
-        st.saved_bits = s_saved;
+        if (tid == 0) {
+            if (s_last >= 0) B[s_last].bfinal = 1;
+            st.total_bits = (uint64_t)s_size;
+            st.saved_bits = s_saved;
+        }
+        __syncthreads();
     }
 }
 

@@ -677,10 +677,19 @@ __global__ void k_lz_jump(uint32_t* __restrict__ ptr, uint64_t n, int* __restric
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool ch = false;
     if (i < n) {
+        // follow up to 8 links per pass (any value read on the way is an ancestor, so concurrent updates by
+        // other threads only shorten the walk); the chain depth shrinks by at least 8x per pass
         uint32_t p = ptr[i];
         if (p != i) {
-            uint32_t pp = ptr[p];
-            if (pp != p) { ptr[i] = pp; ch = true; }
+            const uint32_t p0 = p;
+#pragma unroll 1
+            for (int h = 0; h < 8; h++) {
+                const uint32_t q = ptr[p];
+                if (q == p) break;
+                p = q;
+            }
+            if (p != p0) ptr[i] = p;
+            ch = ptr[p] != p;   // not at a root yet
         }
     }
     if (__syncthreads_or(ch) && threadIdx.x == 0) *changed = 1;

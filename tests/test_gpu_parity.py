@@ -324,12 +324,19 @@ def test_segmented_parse_matches_oracle(gpu, oracle, seg, monkeypatch):
 
 
 def test_literal_cost_paths_agree(gpu, oracle, monkeypatch):
-    """The engine takes a match's literal cost from prefix sums over the block's decoded bytes when the scratch for
-    them fits, and walks the bytes otherwise (very long blocks): both must give the oracle's bytes."""
+    """The engine takes a match's literal cost from prefix sums over the block's decoded bytes when matches are long
+    (>= 24 decoded bytes per symbol) and the scratch fits, and walks the match's bytes otherwise: forced either way,
+    both must give the oracle's bytes."""
     raw = _deflate(W.c2_text(120_000, seed=21))
+    batch = [raw] + W.c3_streams(2, first=7)
     monkeypatch.setenv("D4_NO_PREFIX", "1")
     compare_stream(gpu, oracle, raw, True, check_model=False)
-    slow = gpu.optimise_batch([raw] + W.c3_streams(2, first=7), True)
+    loops = gpu.optimise_batch(batch, True)
     monkeypatch.delenv("D4_NO_PREFIX")
-    fast = gpu.optimise_batch([raw] + W.c3_streams(2, first=7), True)
-    assert [(r["saved_bits"], r["out"]) for r in slow] == [(r["saved_bits"], r["out"]) for r in fast]
+    monkeypatch.setenv("D4_PREFIX_RATIO", "0")   # prefix sums for every block
+    compare_stream(gpu, oracle, raw, True, check_model=False)
+    sums = gpu.optimise_batch(batch, True)
+    monkeypatch.delenv("D4_PREFIX_RATIO")
+    auto = gpu.optimise_batch(batch, True)
+    key = lambda rs: [(r["saved_bits"], r["out"]) for r in rs]
+    assert key(loops) == key(sums) == key(auto)

@@ -40,7 +40,34 @@ def text_chunks(seed=0xDEF7, words_per_chunk=1 << 18):
 
 
 def c2_stream(target_bytes, seed=0xDEF7):
-    """ONE raw deflate stream (zlib.compressobj(6, DEFLATED, -15, 8)) of at least target_bytes."""
+    """ONE raw deflate stream (zlib.compressobj(6, DEFLATED, -15, 8)) of at least target_bytes.  Generating 1 GiB
+    takes about two minutes of single-thread zlib, so large streams are cached under the temp directory (the
+    generator is deterministic: the cache only saves time when bench.py runs more than once on a box)."""
+    import os
+    import tempfile
+    cache = None
+    if target_bytes >= (64 << 20):
+        cache = os.path.join(tempfile.gettempdir(), "deft4cu_c2_%d_%x.bin" % (target_bytes, seed))
+        try:
+            with open(cache, "rb") as f:
+                data = f.read()
+            if len(data) >= target_bytes:
+                return data
+        except OSError:
+            pass
+    data = _c2_stream(target_bytes, seed)
+    if cache:
+        try:
+            tmp = "%s.%d.tmp" % (cache, os.getpid())
+            with open(tmp, "wb") as f:
+                f.write(data)
+            os.replace(tmp, cache)
+        except OSError:
+            pass
+    return data
+
+
+def _c2_stream(target_bytes, seed):
     co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
     parts, n = [], 0
     # ~2.6 bytes of text per compressed byte; feed text until the compressor has emitted enough
