@@ -649,8 +649,10 @@ struct Eng {
                 const bool blocked = live && x == DC_BLOCKED;
                 const int bin = live ? k - 1 : 31;
                 const unsigned grp = __match_any_sync(0xffffffffu, bin);
-                const int xs = __reduce_add_sync(grp, (live && !blocked) ? x : 0);
-                const int cn = __reduce_add_sync(grp, (live && !blocked) ? 1 : 0);
+                // one group reduction carries both the count (bits 24+) and the biased cost sum (x >= -64, 32 lanes)
+                const unsigned packed = __reduce_add_sync(grp, (live && !blocked) ? (1u << 24) + (unsigned)(x + 64) : 0u);
+                const int cn = (int)(packed >> 24);
+                const int xs = (int)(packed & 0xFFFFFFu) - 64 * cn;
                 const unsigned anyBlocked = __ballot_sync(0xffffffffu, blocked) & grp;
                 if (live && lane == __ffs(grp) - 1) {
                     atomicOr(&S->leastSeen, 1u << bin);
@@ -1003,13 +1005,16 @@ struct Eng {
 
     // addOptimisedRecoded (DeflateStream.java:265-317) for base block y
     __device__ __noinline__ int aor(int y) {
-        op_optimise_normal(C_B1, y);                       // optimiseBlockCopyHelper(toOptimise)
-        copy(C_B2, y); op_recode(C_B2); op_optimise(C_B2);  // optimiseBlockHelper(recodedHuffman(.., false))
+        // The four bases are only ever read by trials(): their Tab and payload.  Every trial rewrites the header from
+        // the Tab (optimiseBlockDynBlock -> rewriteHeader, DeflateStream.java:184-198), so the header half of
+        // DeflateBlockHuffman.optimise() (optimiseHeader, :471-476) cannot influence any candidate here and is not run.
+        copy(C_B1, y); pass_replace(C_B1, false);                      // optimiseBlockCopyHelper(toOptimise)
+        copy(C_B2, y); op_recode(C_B2); pass_replace(C_B2, false);     // optimiseBlockHelper(recodedHuffman(.., false))
         copy(C_PP, y); op_recode_less(C_PP);                // pruned
-        op_optimise_normal(C_B3, C_PP);                     // optimiseBlockCopyHelper(pruned)
+        copy(C_B3, C_PP); pass_replace(C_B3, false);                   // optimiseBlockCopyHelper(pruned)
         copy(C_B4, C_PP);
         bool full = op_recoded_full(C_B4, C_CHK2);          // prunedFull
-        if (full) op_optimise(C_B4);
+        if (full) pass_replace(C_B4, false);
         trials(full ? 4 : 3);
         return full ? 4 : 3;
     }
