@@ -939,13 +939,49 @@ struct Eng {
         __shared__ int s_miss[4];
         if (tid < nb) s_miss[tid] = (G->tabTrialBits[S->c[C_B1 + tid].tabid] == TRIAL_UNSET) || g_trace != nullptr;
         __syncthreads();
-        // evaluate the misses: thread j -> (base j / 56, strategy j % 56)
-        for (int j = tid; j < nb * 56; j += ENG_NT) {
-            if (s_miss[j / 56]) {
-                Hdr h;
+        // Evaluate the misses.  Sizes only (huff.cuh trial_sizes): warp b cuts base b's code lengths into runs of equal
+        // values (ballot + popcount compaction into shared memory, overlaying the litlen tree workspace, which is idle
+        // here); then thread j = 28 b + c evaluates rewrite strategy c of base b for both prune values, regenerating
+        // the RLE pair stream from the runs instead of storing it.
+        {
+            struct RunListW : RunList { uint16_t start[MAX_PAIRS]; };
+            static_assert(4 * sizeof(RunListW) <= sizeof(S->tl), "run lists overlay the litlen tree workspace");
+            RunListW* rls = reinterpret_cast<RunListW*>(&S->tl);
+            const int w = tid >> 5, lane = tid & 31;
+            for (int b = w; b < nb; b += ENG_NT / 32) {   // warp-uniform
+                if (!s_miss[b]) continue;
+                const Tab& t = S->c[C_B1 + b].tab;
+                RunListW& rl = rls[b];
+                const int nL = t.nL, n = t.nL + t.nD;
+                int cnt = 0;
+                for (int i0 = 0; i0 < n; i0 += 32) {
+                    const int i = i0 + lane;
+                    const int v = i < n ? (i < nL ? t.L[i] : t.D[i - nL]) : -1;
+                    const int pv = (i > 0 && i < n) ? (i - 1 < nL ? t.L[i - 1] : t.D[i - 1 - nL]) : -2;
+                    const bool st = i < n && v != pv;
+                    const unsigned bal = __ballot_sync(0xffffffffu, st);
+                    if (st) {
+                        const int k = cnt + __popc(bal & ((1u << lane) - 1u));
+                        rl.val[k] = (uint8_t)v;
+                        rl.start[k] = (uint16_t)i;
+                    }
+                    cnt += __popc(bal);
+                }
+                __syncwarp();
+                for (int k = lane; k < cnt; k += 32) rl.len[k] = (uint16_t)((k + 1 < cnt ? rl.start[k + 1] : n) - rl.start[k]);
+                if (lane == 0) rl.n = (uint16_t)cnt;
+            }
+            __syncthreads();
+            for (int j = tid; j < nb * 28; j += ENG_NT) {
+                const int b = j / 28, c = j % 28;
+                if (!s_miss[b]) continue;
+                // c_trial_flags order: [0,20) and [40,48) are the rewrite strategies without prune, +20 / +8 with it
+                const int kF = c < 20 ? c : 40 + (c - 20), kT = c < 20 ? 20 + c : 48 + (c - 20);
                 TreeWsCL ws;
-                if (hdr_trial(S->c[C_B1 + j / 56].tab, c_trial_flags[j % 56], h, ws)) S->err = ERR_TREE;
-                S->trialBits[j] = h.bits;
+                int a = 0, bp = 0;
+                if (trial_sizes(rls[b], c_trial_flags[kF], &a, &bp, ws)) S->err = ERR_TREE;
+                S->trialBits[b * 56 + kF] = a;
+                S->trialBits[b * 56 + kT] = bp;
             }
         }
         __syncthreads();

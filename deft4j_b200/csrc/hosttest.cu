@@ -38,4 +38,19 @@ long long host_header_trial(const uint8_t* lit, int nlit, const uint8_t* dist, i
 
 int host_trial_flags(int k) { return c_trial_flags[k]; }
 
+// size-only evaluation of one rewrite strategy for both prune values (trial_sizes over the run list)
+int host_trial_sizes(const uint8_t* lit, int nlit, const uint8_t* dist, int ndist, int flags, int32_t* no_prune, int32_t* prune) {
+    static Tab t;
+    static RunList rl;
+    static TreeWsCL ws;
+    for (int i = 0; i < MAX_LL; i++) t.L[i] = i < nlit ? lit[i] : 0;
+    for (int i = 0; i < MAX_D; i++) t.D[i] = i < ndist ? dist[i] : 0;
+    t.nL = (uint16_t)nlit; t.nD = (uint16_t)ndist; t.type = 2;
+    runlist_build(t, rl);
+    int a = 0, b = 0;
+    if (trial_sizes(rl, flags, &a, &b, ws)) return 1;
+    *no_prune = a; *prune = b;
+    return 0;
+}
+
 }  // extern "C"

@@ -316,4 +316,125 @@ D4_DEV int hdr_trial(const Tab& t, int flags, Hdr& h, TreeWsCL& ws) {
     return 0;
 }
 
+// ---- size-only header trials over a run list ---------------------------------------------------------
+// The candidate enumerator only needs the SIZE of a header strategy trial (optimiseBlockDynBlock,
+// DeflateStream.java:184-198); the winner alone is materialised (hdr_trial).  trial_sizes() evaluates one
+// rewrite strategy (the 8 flags of HuffmanTable.pack) for both values of `prune` without storing the RLE
+// pairs: the pair stream of rewriteHeader is re-generated from the runs of equal code lengths each time it
+// is needed (three times), in exactly the order hdr_rewrite emits it, and everything else the reference
+// derives from the pairs is a sum over them:
+//   A  symbol frequencies                                   -> header code CL1 (Huffman.ofRLEPacked), trimmed ncl1
+//   B  under CL1: pair bits; runs replaceRLERunsWithLiteralsIfSmaller would expand with `<` (prune = false:
+//      optimiseHeader) and with `<=` (prune = true: recodeHeaderToLessRLEMatches) -> size without prune, and the
+//      frequencies after the `<=` expansion                  -> CL2 (recodeHeader), ncl2 trimmed on from ncl1 (H8)
+//   C  under CL2: expanded runs as plain lengths, the others as pairs that optimiseHeader may still expand (`<`).
+struct RunList {
+    uint16_t n;
+    uint8_t val[MAX_PAIRS];
+    uint16_t len[MAX_PAIRS];
+};
+
+// runs of equal values over litlen lengths followed by distance lengths (they may straddle the boundary,
+// HuffmanTable.java:70-159)
+D4_DEV void runlist_build(const Tab& t, RunList& r) {
+    const int nL = t.nL, n = t.nL + t.nD;
+    int k = 0;
+    int last = t.nL ? t.L[0] : t.D[0], run = 1;
+    for (int i = 1; i <= n; i++) {
+        const int v = i < n ? (i < nL ? t.L[i] : t.D[i - nL]) : -1;
+        if (v == last) { run++; continue; }
+        r.val[k] = (uint8_t)last; r.len[k] = (uint16_t)run; k++;
+        last = v; run = 1;
+    }
+    r.n = (uint16_t)k;
+}
+
+// the pairs hdr_rewrite emits for one run, in its order: f(sym, run, repeated value, count)
+template <class F>
+D4_DEV void emit_run(int last, int runLength, int flags, F&& f) {
+    const bool ohh = flags & 1, use8 = flags & 2, use7 = flags & 4, alt8 = flags & 8, noRep = flags & 16,
+               noZRep = flags & 32, noZRep2 = flags & 64, noRepZeros = flags & 128;
+    if (last == 0) {
+        if (!noZRep2) {
+            if (runLength >= 138) { f(18, 138, 0, runLength / 138); runLength %= 138; }
+            if (runLength >= 11) { f(18, runLength, 0, 1); runLength = 0; }
+        }
+        if (!noZRep) {
+            if (runLength >= 10) { f(17, 10, 0, runLength / 10); runLength %= 10; }
+            if (runLength >= 3) { f(17, runLength, 0, 1); runLength = 0; }
+        }
+    }
+    if (!noRep && runLength > 0 && (!noRepZeros || last != 0)) {
+        f(last, 0, last, 1);
+        runLength--;
+        int j = 6;
+        while (j >= 3) {
+            if (ohh) {
+                if (use8 && runLength == 8) { f(16, alt8 ? 5 : 4, last, 1); f(16, alt8 ? 3 : 4, last, 1); runLength -= 8; break; }
+                if (use7 && runLength == 7) { f(16, 4, last, 1); f(16, 3, last, 1); runLength -= 7; break; }
+            }
+            if (runLength - j >= 0) { f(16, j, last, 1); runLength -= j; } else j--;
+        }
+    }
+    if (runLength > 0) f(last, 0, last, runLength);
+}
+
+// removeTrailingHeaderCodes on a bare length array: trims on from ncl (never grows it)
+D4_DEV int trim_ncl(const uint8_t* CL, int ncl) {
+    while (true) {
+        int lastZero = -1, lastNonZero = ncl;
+        for (int i = 0; i < ncl; i++) { if (CL[c_codelen_order[i]] == 0) lastZero = i; else lastNonZero = i; }
+        if (lastZero > lastNonZero) ncl = lastZero; else break;
+    }
+    return ncl;
+}
+
+// sizes in bits of the trials (flags, prune = false) and (flags, prune = true); returns 1 when a tree cannot be
+// balanced (the reference throws)
+D4_DEV int trial_sizes(const RunList& rl, int flags, int* bitsNoPrune, int* bitsPrune, TreeWsCL& ws) {
+    uint32_t f1[19], f2[19];
+    uint8_t c1[19], c2[19];
+    for (int i = 0; i < 19; i++) { f1[i] = 0; f2[i] = 0; }
+    for (int r = 0; r < rl.n; r++)
+        emit_run(rl.val[r], rl.len[r], flags, [&](int sym, int, int, int cnt) { f1[sym] += (uint32_t)cnt; });
+    if (huff_tree<21, 46>(f1, 19, 7, c1, ws)) return 1;
+    const int ncl1 = trim_ncl(c1, 19);
+    int sizeSum = 0, saved = 0;
+    for (int r = 0; r < rl.n; r++)
+        emit_run(rl.val[r], rl.len[r], flags, [&](int sym, int run, int val, int cnt) {
+            const int size = c1[sym] + (run > 0 ? pair_extra_bits(sym) : 0);
+            sizeSum += size * cnt;
+            bool expand = false;
+            if (run > 0) {
+                const int b = c1[val], tot = b * run;
+                if (b >= 1) {
+                    if (tot < size) saved += (size - tot) * cnt;
+                    expand = tot <= size;
+                }
+            }
+            if (expand) f2[val] += (uint32_t)(run * cnt); else f2[sym] += (uint32_t)cnt;
+        });
+    *bitsNoPrune = 5 + 5 + 4 + 3 * ncl1 + sizeSum - saved;
+    if (huff_tree<21, 46>(f2, 19, 7, c2, ws)) return 1;
+    const int ncl2 = trim_ncl(c2, ncl1);
+    int sum2 = 0;
+    for (int r = 0; r < rl.n; r++)
+        emit_run(rl.val[r], rl.len[r], flags, [&](int sym, int run, int val, int cnt) {
+            int bits;
+            const int size1 = c1[sym] + (run > 0 ? pair_extra_bits(sym) : 0);
+            if (run > 0 && c1[val] >= 1 && c1[val] * run <= size1) {
+                bits = run * c2[val];                       // expanded by the prune step: `run` plain lengths
+            } else {
+                bits = c2[sym] + (run > 0 ? pair_extra_bits(sym) : 0);
+                if (run > 0) {
+                    const int b = c2[val], tot = b * run;
+                    if (b >= 1 && tot < bits) bits = tot;   // expanded by optimiseHeader
+                }
+            }
+            sum2 += bits * cnt;
+        });
+    *bitsPrune = 5 + 5 + 4 + 3 * ncl2 + sum2;
+    return 0;
+}
+
 }  // namespace d4

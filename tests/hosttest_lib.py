@@ -50,3 +50,15 @@ def header_trial(lit, dist, flags, post_op=0):
 
 def trial_flags():
     return [lib().host_trial_flags(k) for k in range(56)]
+
+
+def trial_sizes(lit, dist, flags):
+    """(bits without prune, bits with prune) of one rewrite strategy, by the size-only evaluator."""
+    a = (C.c_uint8 * len(lit))(*lit)
+    b = (C.c_uint8 * len(dist))(*dist)
+    x, y = C.c_int32(0), C.c_int32(0)
+    L = lib()
+    L.host_trial_sizes.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8), C.c_int, C.c_int,
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    rc = L.host_trial_sizes(a, len(lit), b, len(dist), flags, C.byref(x), C.byref(y))
+    return rc, x.value, y.value

@@ -75,3 +75,46 @@ def test_header_mutators_match_oracle(oracle, post_op):
         L, D = _rand_tables(rnd, oracle)
         for f in rnd.sample(flags, 12):
             assert H.header_trial(L, D, f, post_op) == oracle.header_trial(L, D, f, post_op), (it, hex(f), post_op)
+
+
+def test_size_only_trials_match_full_trials():
+    """trial_sizes (run list, no pair storage, both prune values at once — what the engine's trials() evaluates)
+    against hdr_trial (the materialising implementation pinned on the oracle above) for every strategy."""
+    rnd = random.Random(23)
+    flags = H.trial_flags()
+    rewrite = sorted({f & 0xFF for f in flags})
+    assert len(rewrite) == 28
+
+    def tables(kind):
+        if kind == 0:      # sparse alphabets: long zero runs (18/17 paths), straddling the litlen/dist boundary
+            L = [0] * rnd.randint(257, 288)
+            for _ in range(rnd.randint(1, 12)):
+                L[rnd.randrange(len(L))] = rnd.randint(1, 15)
+            L[256] = L[256] or rnd.randint(1, 15)
+            D = [0] * rnd.randint(1, 32)
+            for _ in range(rnd.randint(0, 3)):
+                D[rnd.randrange(len(D))] = rnd.randint(1, 15)
+        elif kind == 1:    # long equal non-zero runs (16 paths incl. the 8 / 7 special cases)
+            L, v = [], rnd.randint(1, 15)
+            while len(L) < 286:
+                L += [v] * rnd.choice([1, 2, 3, 7, 8, 9, 13, 14, 15, 20, 21, 22, 70])
+                v = rnd.randint(0, 15)
+            L = L[:rnd.randint(257, 288)]
+            D = [rnd.choice([5, 5, 5, 0, 6])] * rnd.randint(1, 32)
+        else:              # noisy
+            L = [rnd.choice([0, 0, 7, 8, 8, 9, 9, 10, 12]) for _ in range(rnd.randint(257, 288))]
+            D = [rnd.choice([0, 4, 5, 5, 6]) for _ in range(rnd.randint(1, 32))]
+        return L, D
+
+    checked = 0
+    for it in range(90):
+        L, D = tables(it % 3)
+        for f in rewrite:
+            rc, a, b = H.trial_sizes(L, D, f)
+            want_a = H.header_trial(L, D, f)[0]
+            want_b = H.header_trial(L, D, f | 0x100)[0]
+            if want_a < 0 or want_b < 0:
+                continue
+            assert rc == 0 and (a, b) == (want_a, want_b), (it, hex(f), L, D, (a, b), (want_a, want_b))
+            checked += 1
+    assert checked > 2000
