@@ -831,11 +831,8 @@ struct Eng {
         long long pay = hist_payload(cd.tab);
         {
             P0();
-            if (tid == 0) {
-                cd.payload = pay;
-                if (hdr_rewrite(cd.tab, FLAGS_DEFAULT, cd.hdr, S->wsCL)) S->err = ERR_TREE;
-            }
-            __syncthreads();
+            if (tid == 0) cd.payload = pay;
+            hdr_default_parallel(c);
             P1(PR_HDR_DEFAULT);
         }
         intern_tab(c);
@@ -919,15 +916,111 @@ struct Eng {
     }
     __device__ void op_recode_header(int c) {
         P0();
-        if (tid == 0 && S->c[c].tab.type == 2) { if (hdr_recode(S->c[c].hdr, S->wsCL)) S->err = ERR_TREE; }
-        __syncthreads();
+        if (S->c[c].tab.type == 2) hdr_recode_parallel(c);
         P1(PR_HDR_RECODE);
     }
     __device__ void op_recode_header_less(int c) {
         P0();
-        if (tid == 0 && S->c[c].tab.type == 2) { if (hdr_recode_less(S->c[c].hdr, S->wsCL)) S->err = ERR_TREE; }
-        __syncthreads();
+        if (S->c[c].tab.type == 2) {
+            if (tid == 0) hdr_replace_runs(S->c[c].hdr, true);   // recodeHeaderToLessRLEMatches (:632-635)
+            __syncthreads();
+            hdr_recode_parallel(c);
+        }
         P1(PR_HDR_RECODE);
+    }
+
+    // runs of equal code lengths of a Tab, cut by one warp: ballot + popcount compaction (same result as runlist_build)
+    struct RunListW : RunList { uint16_t start[MAX_PAIRS]; };
+    __device__ __forceinline__ void runlist_warp(const Tab& t, RunListW& rl, int lane) {
+        const int nL = t.nL, n = t.nL + t.nD;
+        int cnt = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const int v = i < n ? (i < nL ? t.L[i] : t.D[i - nL]) : -1;
+            const int pv = (i > 0 && i < n) ? (i - 1 < nL ? t.L[i - 1] : t.D[i - 1 - nL]) : -2;
+            const bool st = i < n && v != pv;
+            const unsigned bal = __ballot_sync(0xffffffffu, st);
+            if (st) {
+                const int k = cnt + __popc(bal & ((1u << lane) - 1u));
+                rl.val[k] = (uint8_t)v;
+                rl.start[k] = (uint16_t)i;
+            }
+            cnt += __popc(bal);
+        }
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) rl.len[k] = (uint16_t)((k + 1 < cnt ? rl.start[k + 1] : n) - rl.start[k]);
+        if (lane == 0) rl.n = (uint16_t)cnt;
+    }
+
+    // header code of the pair frequencies in S->hist[0..19) (Huffman.ofRLEPacked), trimmed on from `ncl`, and the
+    // header size: sum of pair bits = sum_s freq[s] * CL[s] + 2 f16 + 3 f17 + 7 f18.  Thread 0 only.
+    __device__ __forceinline__ void hdr_code_from_freq(Hdr& h, int ncl) {
+        if (huff_tree<21, 46>(S->hist, 19, 7, h.CL, S->wsCL)) S->err = ERR_TREE;
+        ncl = trim_ncl(h.CL, ncl);
+        int bits = 5 + 5 + 4 + 3 * ncl + 2 * (int)S->hist[16] + 3 * (int)S->hist[17] + 7 * (int)S->hist[18];
+        for (int k = 0; k < 19; k++) bits += (int)S->hist[k] * h.CL[k];
+        h.ncl = (uint8_t)ncl;
+        h.bits = bits;
+    }
+
+    // rewriteHeader with the default strategy (DeflateBlockHuffman.java:480-577) for candidate c, by the whole CTA:
+    // runs -> pairs per run -> exclusive scan -> every run writes its pairs; same bytes as hdr_rewrite(FLAGS_DEFAULT)
+    __device__ __noinline__ void hdr_default_parallel(int c) {
+        struct HdrWs { RunListW rl; uint16_t off[MAX_PAIRS + 2]; };
+        static_assert(sizeof(HdrWs) <= sizeof(S->tl), "overlays the litlen tree workspace (idle once the trees are built)");
+        HdrWs& W = *reinterpret_cast<HdrWs*>(&S->tl);
+        Cand& cd = S->c[c];
+        const int w = tid >> 5, lane = tid & 31;
+        if (tid < 19) S->hist[tid] = 0;
+        if (w == 0) runlist_warp(cd.tab, W.rl, lane);
+        __syncthreads();
+        const int R = W.rl.n;
+        for (int r = tid; r < R; r += ENG_NT) {
+            int cnt = 0;
+            emit_run(W.rl.val[r], W.rl.len[r], FLAGS_DEFAULT, [&](int, int, int, int k) { cnt += k; });
+            W.off[r] = (uint16_t)cnt;
+        }
+        __syncthreads();
+        if (w == 0) {
+            int carry = 0;
+            for (int i0 = 0; i0 < R; i0 += 32) {
+                const int i = i0 + lane;
+                const int x = i < R ? W.off[i] : 0;
+                int incl = x;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+                if (i < R) W.off[i] = (uint16_t)(carry + incl - x);
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) W.off[R] = (uint16_t)carry;
+        }
+        __syncthreads();
+        for (int r = tid; r < R; r += ENG_NT) {
+            int o = W.off[r];
+            emit_run(W.rl.val[r], W.rl.len[r], FLAGS_DEFAULT, [&](int sym, int run, int val, int k) {
+                const uint16_t p = pair_pack(sym, run, val);
+                for (int q = 0; q < k; q++) cd.hdr.pairs[o++] = p;
+                atomicAdd(&S->hist[sym], (uint32_t)k);
+            });
+        }
+        __syncthreads();
+        if (tid == 0) {
+            cd.hdr.np = W.off[R];
+            hdr_code_from_freq(cd.hdr, 19);
+        }
+        __syncthreads();
+    }
+
+    // recodeHeader (:579-629) for candidate c: pair frequencies by all threads, the code by thread 0
+    __device__ __noinline__ void hdr_recode_parallel(int c) {
+        Cand& cd = S->c[c];
+        if (tid < 19) S->hist[tid] = 0;
+        __syncthreads();
+        const int np = cd.hdr.np;
+        for (int i = tid; i < np; i += ENG_NT) atomicAdd(&S->hist[pair_sym(cd.hdr.pairs[i])], 1u);
+        __syncthreads();
+        if (tid == 0) hdr_code_from_freq(cd.hdr, cd.hdr.ncl);
+        __syncthreads();
     }
 
     // ---- the 56 header strategy trials of up to 4 bases (addOptimisedRecoded, :277-316) -------------
@@ -944,32 +1037,12 @@ struct Eng {
         // here); then thread j = 28 b + c evaluates rewrite strategy c of base b for both prune values, regenerating
         // the RLE pair stream from the runs instead of storing it.
         {
-            struct RunListW : RunList { uint16_t start[MAX_PAIRS]; };
             static_assert(4 * sizeof(RunListW) <= sizeof(S->tl), "run lists overlay the litlen tree workspace");
             RunListW* rls = reinterpret_cast<RunListW*>(&S->tl);
             const int w = tid >> 5, lane = tid & 31;
             for (int b = w; b < nb; b += ENG_NT / 32) {   // warp-uniform
                 if (!s_miss[b]) continue;
-                const Tab& t = S->c[C_B1 + b].tab;
-                RunListW& rl = rls[b];
-                const int nL = t.nL, n = t.nL + t.nD;
-                int cnt = 0;
-                for (int i0 = 0; i0 < n; i0 += 32) {
-                    const int i = i0 + lane;
-                    const int v = i < n ? (i < nL ? t.L[i] : t.D[i - nL]) : -1;
-                    const int pv = (i > 0 && i < n) ? (i - 1 < nL ? t.L[i - 1] : t.D[i - 1 - nL]) : -2;
-                    const bool st = i < n && v != pv;
-                    const unsigned bal = __ballot_sync(0xffffffffu, st);
-                    if (st) {
-                        const int k = cnt + __popc(bal & ((1u << lane) - 1u));
-                        rl.val[k] = (uint8_t)v;
-                        rl.start[k] = (uint16_t)i;
-                    }
-                    cnt += __popc(bal);
-                }
-                __syncwarp();
-                for (int k = lane; k < cnt; k += 32) rl.len[k] = (uint16_t)((k + 1 < cnt ? rl.start[k + 1] : n) - rl.start[k]);
-                if (lane == 0) rl.n = (uint16_t)cnt;
+                runlist_warp(S->c[C_B1 + b].tab, rls[b], lane);
             }
             __syncthreads();
             for (int j = tid; j < nb * 28; j += ENG_NT) {
