@@ -496,6 +496,7 @@ class Batch {
             cudaFuncSetAttribute(k_opt_blocks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             D4_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_opt_blocks, ENG_NT, 0));
             if (perSM < 1) perSM = 1;
+            if (const char* e = getenv("D4_CTAS_PER_SM")) perSM = std::max(1, std::min(perSM, atoi(e)));  // A/B knob
             unsigned grid = (unsigned)std::min<uint64_t>(jobs.size(), (uint64_t)g_sms * perSM);
             EngScratch sc;
             sc.maxwords = (maxsym + 31) / 32 + 1;
