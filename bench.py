@@ -274,6 +274,10 @@ def run_ours(a):
     pinned = [torch.frombuffer(bytearray(s), dtype=torch.uint8).pin_memory() for s in streams]
     pp = (C.c_char_p * n)(*[C.cast(t.data_ptr(), C.c_char_p) for t in pinned])
     e2e_res = (N.Result * n)()
+    if a.warmup > 0:  # one untimed call: the library pins its result block on first use
+        rc = L.deft4cu_optimise_batch(pp, lens, n, merge, e2e_res)
+        assert rc == 0, N.last_error()
+        L.deft4cu_free_results(e2e_res, n)
     barrier()
     t0 = time.perf_counter()
     d2h = 0

@@ -60,6 +60,46 @@ static void dfree(T*& p, cudaStream_t s) {
 
 struct BlkSummary { uint32_t type, n_sym; uint64_t out_len; };
 
+// Result buffers handed to the caller (deft4cu_result::out) live in pinned host blocks so that the device -> host
+// copy of a batch's output is one DMA at PCIe speed; blocks are reference counted by the `out` pointers that point
+// into them and recycled by deft4cu_free_results / deft4cu_free_buffer (pinning memory is slow, so a few idle blocks
+// are kept).
+struct HostBlock { uint8_t* p; size_t cap; int refs; bool pinned; };
+static std::mutex g_hmu;
+static std::vector<HostBlock> g_hblocks;
+static uint8_t* host_block_acquire(size_t bytes, int refs) {
+    std::lock_guard<std::mutex> lk(g_hmu);
+    int best = -1;
+    for (size_t k = 0; k < g_hblocks.size(); k++)
+        if (g_hblocks[k].refs == 0 && g_hblocks[k].cap >= bytes && (best < 0 || g_hblocks[k].cap < g_hblocks[best].cap)) best = (int)k;
+    if (best < 0) {
+        // drop idle blocks that are too small before growing
+        for (size_t k = 0; k < g_hblocks.size();) {
+            if (g_hblocks[k].refs == 0) {
+                if (g_hblocks[k].pinned) cudaFreeHost(g_hblocks[k].p); else free(g_hblocks[k].p);
+                g_hblocks.erase(g_hblocks.begin() + k);
+            } else k++;
+        }
+        HostBlock hb{nullptr, (bytes + (1u << 20)) & ~(size_t)((1u << 20) - 1), 0, true};
+        if (cudaMallocHost((void**)&hb.p, hb.cap) != cudaSuccess) {
+            cudaGetLastError();
+            hb.pinned = false;
+            hb.p = (uint8_t*)malloc(hb.cap);
+            if (!hb.p) return nullptr;
+        }
+        g_hblocks.push_back(hb);
+        best = (int)g_hblocks.size() - 1;
+    }
+    g_hblocks[best].refs = refs;
+    return g_hblocks[best].p;
+}
+static void host_release(const uint8_t* ptr) {
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk(g_hmu);
+    for (auto& hb : g_hblocks)
+        if (ptr >= hb.p && ptr < hb.p + hb.cap) { if (hb.refs > 0) hb.refs--; return; }
+}
+
 __global__ void k_blk_summary(const BlockRec* __restrict__ recs, BlkSummary* __restrict__ out, uint64_t n) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -911,6 +951,7 @@ uint32_t deft4cu_stream_block_codelens(const deft4cu_stream* s, uint32_t block, 
 
 // ---- batch entry -------------------------------------------------------------------------------------------
 static int fill_results(Batch& b, deft4cu_result* results, bool fetch_out) {
+    int nout = 0;
     for (uint32_t i = 0; i < b.n; i++) {
         deft4cu_result& r = results[i];
         memset(&r, 0, sizeof r);
@@ -924,10 +965,15 @@ static int fill_results(Batch& b, deft4cu_result* results, bool fetch_out) {
         r.crc32 = b.crc.size() > i ? b.crc[i] : 0;
         r.adler32 = b.adler.size() > i ? b.adler[i] : 0;
         r.out_len = b.dst_len[i];
-        if (fetch_out) {
-            r.out = (uint8_t*)malloc(r.out_len ? r.out_len : 1);
-            if (r.out_len) D4_CUDA_CHECK(cudaMemcpyAsync(r.out, b.d_dst + b.dst_off[i], r.out_len, cudaMemcpyDeviceToHost, b.cs));
-        }
+        nout++;
+    }
+    if (fetch_out && nout) {
+        // the rewritten streams sit back to back in d_dst: one copy into one pinned block, `out` pointers into it
+        uint8_t* blk = host_block_acquire(b.dst_total, nout);
+        if (!blk) { set_error("out of host memory for the result buffers"); return DEFT4CU_ERR_CUDA; }
+        D4_CUDA_CHECK(cudaMemcpyAsync(blk, b.d_dst, b.dst_total, cudaMemcpyDeviceToHost, b.cs));
+        for (uint32_t i = 0; i < b.n; i++)
+            if (results[i].status == ST_OK) results[i].out = blk + b.dst_off[i];
     }
     D4_CUDA_CHECK(cudaStreamSynchronize(b.cs));
     return DEFT4CU_OK;
@@ -957,7 +1003,7 @@ int deft4cu_optimise_batch(const uint8_t* const* in, const uint64_t* in_len, uin
     return rc2 ? rc2 : rc;
 }
 void deft4cu_free_results(deft4cu_result* results, uint32_t n) {
-    for (uint32_t i = 0; i < n; i++) { free(results[i].out); results[i].out = nullptr; }
+    for (uint32_t i = 0; i < n; i++) { host_release(results[i].out); results[i].out = nullptr; }
 }
 
 // ---- facade -------------------------------------------------------------------------------------------------
@@ -968,10 +1014,10 @@ int deft4cu_optimise_deflate_stream(const uint8_t* in, uint64_t len, int merge_b
     int rc = deft4cu_optimise_batch(&in, &len, 1, merge_blocks ? DEFT4CU_MERGE_BLOCKS : 0, &r);
     if (rc == DEFT4CU_ERR_CUDA || rc == DEFT4CU_ERR_ARG) return rc;
     if (r.status == ST_OK && r.saved_bits > 0) { *out = r.out; *out_len = r.out_len; }
-    else free(r.out);
+    else host_release(r.out);
     return DEFT4CU_OK;
 }
-void deft4cu_free_buffer(uint8_t* p) { free(p); }
+void deft4cu_free_buffer(uint8_t* p) { host_release(p); }
 int64_t deft4cu_size_bits_fallback(const uint8_t* in, uint64_t len) {
     deft4cu_stream* s = nullptr;
     uint64_t c;
