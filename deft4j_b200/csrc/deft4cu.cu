@@ -375,11 +375,7 @@ class Batch {
             D4_CUDA_CHECK(dalloc(&d_ptr, ob, cs));
             D4_CUDA_CHECK(dalloc(&d_changed, 1, cs));
             if (sb) LAUNCH(k_lz_fill, (unsigned)((sb + 255) / 256), 256, cs, d_sym, d_symout, sb, d_out, d_ptr);
-            // stored bytes: roots
-            // (k_emit wrote them into d_out; their pointers are set here)
-            {
-                // ptr for stored block bytes = self: a tiny kernel over blocks would do; reuse k_lz_root
-            }
+            // stored bytes are roots (k_emit wrote them into d_out; their pointers are set here)
             LAUNCH(k_lz_root_stored, (unsigned)std::max<uint64_t>(1, nblk_total), 256, cs, d_descs, d_blocks, d_jobs, (uint32_t)nblk_total, d_ptr);
             for (int it = 0; it < 64; it++) {
                 int changed = 0;
@@ -687,8 +683,6 @@ struct deft4cu_stream {
 struct deft4cu_device_batch {
     std::shared_ptr<Batch> batch;
 };
-
-static int status_of(const Batch& b, uint32_t i) { return b.sstate.size() > i ? b.sstate[i].status : b.infos[i].status; }
 
 extern "C" {
 

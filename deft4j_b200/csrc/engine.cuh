@@ -5,13 +5,16 @@
 // A candidate ("Cand") is the reference's DeflateBlockHuffman copy reduced to what determines its bytes:
 //   Tab (code lengths + table lengths + type), Hdr (header RLE pairs, header code, numCodelenLens),
 //   payload = litlenSizeBits, and a bit mask over the block's symbols (1 = match replaced by literals).
-// Candidate i's mask lives in mask slot i of the CTA's global scratch.
+// Masks are immutable entries of a per-CTA pool in global scratch; a candidate holds a mask id.
 //
 // O(n) work (n = symbols of the block) is done by CTA-wide passes:
 //   pass_replace : replaceBackrefsWithLiteralsIfSmaller (DeflateBlockHuffman.java:222-319)
 //   pass_least   : removeDistLitLeastExpensive          (:373-458)
-//   pass_hist    : the histogram loop of recodeHuffman   (:671-681); payload = hist . (len + extra bits)
-// Small serial work (Huffman trees, header model) runs in single threads (huff.cuh).
+//   pass_hist_full / hist deltas : the histogram loop of recodeHuffman (:671-681); payload = hist . (len + extra bits)
+// Serial work runs in single threads (huff.cuh): the litlen / distance Huffman trees (exact PriorityQueue order),
+// the header code, run replacement in headers.  The 56 header strategy trials are evaluated size-only, one
+// thread per rewrite strategy, over a run list of the code lengths; the default header rewrite and the header
+// recode are spread over the CTA (run list -> scan -> parallel pair emission).
 //
 // Exact shortcuts (pure-function memoisation; none changes any candidate's size or the order in which
 // candidates are compared).  The enumeration revisits the same (symbol list, code tables) states many

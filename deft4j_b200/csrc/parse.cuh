@@ -1,7 +1,9 @@
 // parse.cuh — Huffman decode of deflate streams on the GPU.
 //
-// Pass 1  k_count : one CTA per stream.  Blocks are walked in order (block boundaries are found on the
-//                   device); inside a Huffman block the CTA decodes a window of NT*CHUNK_BITS bits
+// Pass 0  k_find  : one CTA per 128 KiB segment of a long stream: first well-formed dynamic block header in it.
+// Pass 1  k_count : one CTA per walker (a stream, or a segment of one starting at the header k_find guessed;
+//                   the host validates the chain, deft4cu.cu Batch::parse).  Blocks are walked in order; inside
+//                   a Huffman block the CTA decodes a window of NT*CHUNK_BITS bits
 //                   speculatively: thread t starts at bit t*CHUNK_BITS assuming a symbol boundary,
 //                   then a fix-up loop re-decodes every chunk whose predecessor ended elsewhere until
 //                   the chain from the (known) window start is consistent (self-synchronisation).
@@ -9,8 +11,8 @@
 //                   ChunkRec per valid chunk (start bit, symbol index, decoded offset), stream totals.
 // Pass 2  k_emit  : one CTA per Huffman block, one thread per ChunkRec: decode again, now writing the
 //                   packed symbols and their decoded offsets.  Stored blocks are copied.
-// Pass 3  k_lz_*  : LZ77 resolution by pointer doubling over the decoded bytes (every byte of a match
-//                   points at its source byte; literals are roots), replacing the reference's
+// Pass 3  k_lz_*  : LZ77 resolution by pointer jumping over the decoded bytes (every byte of a match
+//                   points at its source byte; literals are roots; up to 8 links per pass), replacing the reference's
 //                   byte-serial readSlice (DeflateBlock.java:147-222).
 //
 // Decoding restates the reference decoder's semantics (Huffman.java:170-197): codes are matched one
