@@ -1,0 +1,147 @@
+"""`python -m deft4j_b200 optimise|optimise-folder ...` — mirror of deft4j-cmd.
+
+cmd/Main.java:8-25 (subcommands), cmd/Optimise.java:15-54, cmd/OptimiseFolder.java:33-67 and
+cmd/CMDUtil.java:57-181: same positional arguments, option names, stdout/stderr lines, temp-file overwrite protocol
+and exit codes.  Only `--mode NONE` exists here (the recompress modes call third-party compressors).
+"""
+import argparse
+import os
+import shutil
+import sys
+import tempfile
+
+from .container import getContainerForBytes, getContainerForExt, RawDeflateFile
+
+
+def _stream_cls(name):
+    if name == "oracle":   # test hook: the CPU oracle as the stream engine (tests/ only, never the product path)
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+        import oracle_lib
+        return oracle_lib.OracleDeflateStream
+    from .deflate_stream import DeflateStream
+    return DeflateStream
+
+
+def optimise_bytes(data, container, merge_blocks, out=None, err=None):
+    """CMDUtil.optimise (CMDUtil.java:57-116): returns the rewritten bytes or None."""
+    out, err = out or sys.stdout, err or sys.stderr
+    if container is None:
+        print("Invalid file container", file=err)
+        return None
+    if container.read(data):
+        print("File type recognised as " + container.fileType(), file=out)
+        saved = container.optimise(merge_blocks, out)
+        if saved != 0:
+            print("Saved %d bits with optimisation" % saved, file=out)
+        try:
+            return container.write()   # always re-serialised, even when nothing was saved
+        except IOError:
+            print("Failed to write output", file=err)
+    print("Invalid %s file" % container.fileType(), file=err)
+    return None
+
+
+def optimise_file(inp, outp, fmt, raw, merge_blocks, stream_cls, out=None, err=None):
+    """CMDUtil.optimiseFile (CMDUtil.java:119-181)."""
+    out, err = out or sys.stdout, err or sys.stderr
+    if not os.path.isfile(inp):
+        print("Error: Input file does not exist", file=err)
+        return False
+    if os.path.isdir(outp):
+        print("Error: Output file is a directory", file=err)
+        return False
+    with open(inp, "rb") as f:
+        data = f.read()
+    if raw:
+        container = RawDeflateFile(stream_cls)
+    elif fmt is not None:
+        container = getContainerForExt(fmt, stream_cls)
+    else:
+        container = getContainerForBytes(data, os.path.basename(inp), stream_cls)
+    result = optimise_bytes(data, container, merge_blocks, out, err)
+    if result is None:
+        print("Failed to optimise input file", file=err)
+        return False
+    if os.path.isfile(outp):       # overwrite through a temp file, only on success (:137-176)
+        ext = os.path.splitext(inp)[1] or None
+        fd, tmp = tempfile.mkstemp(prefix="deft-temp-", suffix=ext)
+        try:
+            with os.fdopen(fd, "wb") as f:
+                f.write(result)
+            shutil.copyfile(tmp, outp)
+        finally:
+            try:
+                os.unlink(tmp)
+            except OSError:
+                print("Issue deleting temporary file " + tmp, file=err)
+    else:
+        with open(outp, "wb") as f:
+            f.write(result)
+    return True
+
+
+def main(argv=None, out=None, err=None):
+    out, err = out or sys.stdout, err or sys.stderr
+    ap = argparse.ArgumentParser(prog="deft4j", description="Deflate stream optimiser")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+
+    def common(p):
+        p.add_argument("--recompress-mode", "--mode", "-m", default="NONE", choices=["NONE"], dest="mode",
+                       help="only NONE is available in this build")
+        p.add_argument("--zopfli-iter", "--iter", "-I", type=int, default=20, help="(unused with --mode NONE)")
+        p.add_argument("--merge-blocks", "-b", dest="merge_blocks", action="store_true", default=True,
+                       help="Try merging deflate blocks (default)")
+        p.add_argument("--no-merge-blocks", dest="merge_blocks", action="store_false")
+        p.add_argument("--engine", default="cuda", choices=["cuda", "oracle"], help=argparse.SUPPRESS)
+
+    p = sub.add_parser("optimise", help="Deflate stream optimiser")
+    p.add_argument("inputFile", help="The file to optimise")
+    p.add_argument("outputFile", help="The optimised file")
+    p.add_argument("--format", "-f", default=None, help="File format")
+    p.add_argument("--raw", "-r", action="store_true", help="Ignore file format, treat input as a raw deflate stream")
+    common(p)
+    p = sub.add_parser("optimise-folder", help="Optimise every recognised file below a folder, in place")
+    p.add_argument("inputFolder")
+    common(p)
+    a = ap.parse_args(argv)
+    cls = _stream_cls(a.engine)
+    if a.cmd == "optimise":
+        try:
+            ok = optimise_file(a.inputFile, a.outputFile, a.format, a.raw, a.merge_blocks, cls, out, err)
+        except Exception:
+            print("Error when optimising file " + a.inputFile, file=err)
+            raise
+        if not ok:
+            print("Failed to optimise " + a.inputFile, file=err)
+        return 0 if ok else 1
+    # optimise-folder (OptimiseFolder.java:33-67): regular files whose format is recognised by magic or extension
+    ok = True
+    paths = []
+    if os.path.isdir(a.inputFolder):
+        for root, _, files in os.walk(a.inputFolder):
+            paths += [os.path.join(root, f) for f in sorted(files)]
+    else:
+        paths = [a.inputFolder]
+    for path in paths:
+        if not os.path.isfile(path):
+            continue
+        with open(path, "rb") as f:
+            head = f.read(16)
+        cont = getContainerForBytes(head, os.path.basename(path), cls)
+        if cont is None or isinstance(cont, RawDeflateFile):
+            continue
+        print("Optimising file " + path, file=out)
+        try:
+            if not optimise_file(path, path, None, False, a.merge_blocks, cls, out, err):
+                print("Error when optimising file " + path, file=err)
+                ok = False
+        except Exception as e:  # noqa: BLE001 - the reference prints the stack trace and carries on
+            print("Error when optimising file %s: %r" % (path, e), file=err)
+            ok = False
+    if not ok:
+        print("Failed to optimise " + a.inputFolder, file=err)
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

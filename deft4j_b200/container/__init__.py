@@ -4,7 +4,8 @@ from .gz_file import GZFile
 from .png_file import PNGFile
 from .raw_deflate_file import RawDeflateFile
 from .zlib_file import ZLibFile
+from .zip_file import ZipFile
 from .container_util import getContainerForExt, getContainerForBytes
 
-__all__ = ["DeflateFilesContainer", "optimise_streams", "GZFile", "PNGFile", "RawDeflateFile", "ZLibFile",
+__all__ = ["DeflateFilesContainer", "optimise_streams", "GZFile", "PNGFile", "RawDeflateFile", "ZLibFile", "ZipFile",
            "getContainerForExt", "getContainerForBytes"]

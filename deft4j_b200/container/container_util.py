@@ -1,12 +1,13 @@
 """Mirror of cont/ContainerUtil.java:48-175: magic sniffing and extension → container mapping.
 
-ZIP is listed but not implemented in this round (the reference delegates ZIP
-parsing to the un-vendored lljzip dependency; parity unpinned) — asking for it raises.
+ZIP: the reference delegates parsing to the un-vendored lljzip dependency; zip_file.py restates the standard
+layout and RecalculatingZipWriter (parity unpinned).
 """
 from .gz_file import GZFile
 from .png_file import PNGFile
 from .raw_deflate_file import RawDeflateFile
 from .zlib_file import ZLibFile
+from .zip_file import ZipFile
 
 _MAGICS = [
     (bytes([0x89, 0x50, 0x4E, 0x47, 0x0D, 0x0A, 0x1A, 0x0A]), "png"),
@@ -48,7 +49,7 @@ def getContainerForExt(ext, stream_cls=None):
     if e in _ZLIB_EXT:
         return ZLibFile(stream_cls)
     if e in _ZIP_EXT:
-        raise NotImplementedError("ZIP container: SURVEY.md §8f row 3, not built yet")
+        return ZipFile(stream_cls)
     if e == "png":
         return PNGFile(stream_cls)
     return RawDeflateFile(stream_cls)

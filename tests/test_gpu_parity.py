@@ -2,6 +2,7 @@
 against the CPU oracle and the reference's committed golden files.  Integer/byte work: the bar is bit-exact.
 """
 import io
+import os
 import zlib
 
 import pytest
@@ -340,3 +341,30 @@ def test_literal_cost_paths_agree(gpu, oracle, monkeypatch):
     auto = gpu.optimise_batch(batch, True)
     key = lambda rs: [(r["saved_bits"], r["out"]) for r in rs]
     assert key(loops) == key(sums) == key(auto)
+
+
+def test_zip_container_and_cli_on_the_gpu(gpu, oracle, tmp_path, capsys):
+    """SURVEY.md §8f rows 3-4 with the CUDA stream engine: the ZIP container mirror batches its entries through
+    deft4cu_stream_optimise_batch, the CLI mirror reproduces a reference golden byte for byte."""
+    import zipfile
+    from deft4j_b200.container import getContainerForBytes
+    from deft4j_b200.__main__ import main
+    buf = io.BytesIO()
+    with zipfile.ZipFile(buf, "w") as z:
+        for k in range(5):
+            zi = zipfile.ZipInfo("dir/f%d.txt" % k, date_time=(2024, 5, 6, 7, 8, 10))
+            zi.compress_type = zipfile.ZIP_DEFLATED if k != 3 else zipfile.ZIP_STORED
+            z.writestr(zi, W.c2_text(9000 + 7000 * k, seed=40 + k), compresslevel=[6, 1, 9, None, 6][k])
+    data = buf.getvalue()
+    cg = getContainerForBytes(data, "a.zip", gpu.DeflateStream)
+    co = getContainerForBytes(data, "a.zip", oracle.OracleDeflateStream)
+    assert cg.read(data) and co.read(data)
+    assert cg.optimise(True, None) == co.optimise(True, None)
+    out = cg.write()
+    assert out == co.write()
+    with zipfile.ZipFile(io.BytesIO(out)) as z, zipfile.ZipFile(io.BytesIO(data)) as z0:
+        assert z.testzip() is None and [z.read(n) for n in z.namelist()] == [z0.read(n) for n in z0.namelist()]
+    dst = tmp_path / "o.gz"
+    assert main(["optimise", os.path.join(os.path.dirname(__file__), "golden", "asyoulik", "asyoulik-gzip.txt.gz"), str(dst)]) == 0
+    assert dst.read_bytes() == read_golden("asyoulik/asyoulik-gzip-opt.txt.gz")
+    assert "167 bits saved in stream 0" in capsys.readouterr().out
