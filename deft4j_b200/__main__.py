@@ -13,12 +13,8 @@ import tempfile
 from .container import getContainerForBytes, getContainerForExt, RawDeflateFile
 
 
-def _stream_cls(name):
-    if name == "oracle":   # test hook: the CPU oracle as the stream engine (tests/ only, never the product path)
-        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-        import oracle_lib
-        return oracle_lib.OracleDeflateStream
-    from .deflate_stream import DeflateStream
+def _stream_cls():
+    from .deflate_stream import DeflateStream   # the CUDA engine; raises when the library or a device is missing
     return DeflateStream
 
 
@@ -80,7 +76,9 @@ def optimise_file(inp, outp, fmt, raw, merge_blocks, stream_cls, out=None, err=N
     return True
 
 
-def main(argv=None, out=None, err=None):
+def main(argv=None, out=None, err=None, stream_cls=None):
+    """`stream_cls` lets a caller supply another implementation of the DeflateStream interface (the CPU-only tests
+    pass their checker); the command line always uses the CUDA engine."""
     out, err = out or sys.stdout, err or sys.stderr
     ap = argparse.ArgumentParser(prog="deft4j", description="Deflate stream optimiser")
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -92,7 +90,6 @@ def main(argv=None, out=None, err=None):
         p.add_argument("--merge-blocks", "-b", dest="merge_blocks", action="store_true", default=True,
                        help="Try merging deflate blocks (default)")
         p.add_argument("--no-merge-blocks", dest="merge_blocks", action="store_false")
-        p.add_argument("--engine", default="cuda", choices=["cuda", "oracle"], help=argparse.SUPPRESS)
 
     p = sub.add_parser("optimise", help="Deflate stream optimiser")
     p.add_argument("inputFile", help="The file to optimise")
@@ -104,7 +101,7 @@ def main(argv=None, out=None, err=None):
     p.add_argument("inputFolder")
     common(p)
     a = ap.parse_args(argv)
-    cls = _stream_cls(a.engine)
+    cls = stream_cls or _stream_cls()
     if a.cmd == "optimise":
         try:
             ok = optimise_file(a.inputFile, a.outputFile, a.format, a.raw, a.merge_blocks, cls, out, err)

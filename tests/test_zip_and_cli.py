@@ -91,45 +91,46 @@ def test_zip_refuses_what_the_reference_refuses(oracle):
     assert ZipFile(oracle.OracleDeflateStream).read(b"") is False
 
 
-def test_cli_optimise_matches_reference_goldens(tmp_path, capsys):
+def test_cli_optimise_matches_reference_goldens(oracle, tmp_path, capsys):
     """`deft4j optimise -m NONE` on three of the reference's fixtures with runTestOpt.sh's flags: same output bytes,
     same stdout lines (CMDUtil.java:64-72, DeflateFilesContainer.java:31-39)."""
     from deft4j_b200.__main__ import main
     for inp, gold, merge in [GOLDEN_PAIRS[0], GOLDEN_PAIRS[1], GOLDEN_PAIRS[2]]:
         out = tmp_path / ("out-" + os.path.basename(inp))
-        argv = ["optimise", golden_path(inp), str(out), "--engine", "oracle"] + ([] if merge else ["--no-merge-blocks"])
-        assert main(argv) == 0
+        argv = ["optimise", golden_path(inp), str(out)] + ([] if merge else ["--no-merge-blocks"])
+        assert main(argv, stream_cls=oracle.OracleDeflateStream) == 0
         assert out.read_bytes() == read_golden(gold)
         printed = capsys.readouterr().out.splitlines()
         ref = [l for l in read_golden(gold + ".txt").decode().splitlines() if l.strip()]
         assert printed == ref, (printed, ref)
 
 
-def test_cli_errors_and_overwrite(tmp_path, capsys):
+def test_cli_errors_and_overwrite(oracle, tmp_path, capsys):
     from deft4j_b200.__main__ import main
-    assert main(["optimise", str(tmp_path / "missing.gz"), str(tmp_path / "o.gz"), "--engine", "oracle"]) == 1
+    cls = oracle.OracleDeflateStream
+    assert main(["optimise", str(tmp_path / "missing.gz"), str(tmp_path / "o.gz")], stream_cls=cls) == 1
     assert "Error: Input file does not exist" in capsys.readouterr().err
     bad = tmp_path / "bad.gz"
     bad.write_bytes(b"\x1f\x8b\x08\x00" + b"\xff" * 30)
-    assert main(["optimise", str(bad), str(tmp_path / "o.gz"), "--engine", "oracle"]) == 1
+    assert main(["optimise", str(bad), str(tmp_path / "o.gz")], stream_cls=cls) == 1
     assert not (tmp_path / "o.gz").exists()
     # in-place overwrite goes through a temp file and only happens on success
     src = tmp_path / "lz.gz"
     src.write_bytes(read_golden("lz-twice-twice.txt.gz"))
-    assert main(["optimise", str(src), str(src), "--engine", "oracle"]) == 0
+    assert main(["optimise", str(src), str(src)], stream_cls=cls) == 0
     assert src.read_bytes() == read_golden("lz-twice-twice-opt.txt.gz")
     bad_before = bad.read_bytes()
-    assert main(["optimise", str(bad), str(bad), "--engine", "oracle"]) == 1 and bad.read_bytes() == bad_before
+    assert main(["optimise", str(bad), str(bad)], stream_cls=cls) == 1 and bad.read_bytes() == bad_before
 
 
-def test_cli_optimise_folder(tmp_path, capsys):
+def test_cli_optimise_folder(oracle, tmp_path, capsys):
     from deft4j_b200.__main__ import main
     d = tmp_path / "tree" / "sub"
     d.mkdir(parents=True)
     (d / "a.txt.gz").write_bytes(read_golden("lz-twice-twice.txt.gz"))
     (d / "notes.txt").write_bytes(b"plain text, not a container")       # RawDeflateFile by extension: skipped
     (tmp_path / "tree" / "t.png").write_bytes(read_golden("text.png"))
-    assert main(["optimise-folder", str(tmp_path / "tree"), "--engine", "oracle"]) == 0
+    assert main(["optimise-folder", str(tmp_path / "tree")], stream_cls=oracle.OracleDeflateStream) == 0
     assert (d / "a.txt.gz").read_bytes() == read_golden("lz-twice-twice-opt.txt.gz")
     assert (tmp_path / "tree" / "t.png").read_bytes() == read_golden("text-opt.png")
     assert (d / "notes.txt").read_bytes() == b"plain text, not a container"
