@@ -38,11 +38,17 @@ long long host_header_trial(const uint8_t* lit, int nlit, const uint8_t* dist, i
 
 int host_trial_flags(int k) { return c_trial_flags[k]; }
 
+// the compact header-code workspace (weights must add up to less than 1024)
+int host_huff_tree_compact(const uint32_t* freq, int n, int limit, uint8_t* lens) {
+    static TreeWsCLc ws;
+    return huff_tree_ws(freq, n, limit, lens, ws);
+}
+
 // size-only evaluation of one rewrite strategy for both prune values (trial_sizes over the run list)
 int host_trial_sizes(const uint8_t* lit, int nlit, const uint8_t* dist, int ndist, int flags, int32_t* no_prune, int32_t* prune) {
     static Tab t;
     static RunList rl;
-    static TreeWsCL ws;
+    static TreeWsCL ws;    // the workspace the engine's trial threads use
     for (int i = 0; i < MAX_LL; i++) t.L[i] = i < nlit ? lit[i] : 0;
     for (int i = 0; i < MAX_D; i++) t.D[i] = i < ndist ? dist[i] : 0;
     t.nL = (uint16_t)nlit; t.nD = (uint16_t)ndist; t.type = 2;

@@ -13,32 +13,65 @@
 
 namespace d4 {
 
-constexpr uint16_t NODE_NONE = 0xFFFF;
-
+// Workspace of one tree build.  The algorithm below is written against the members of a workspace type:
+//   key_t / ID_BITS   heap entry = (weight << ID_BITS) | node id
+//   stack_t / STACK_SHIFT   DFS stack entry = node | (depth << STACK_SHIFT)
+//   idx_t / NONE / NDEPTH   node ids, "no node", number of depth slots
 template <int MAXLEAF, int MAXN>
 struct TreeWs {
+    typedef unsigned long long key_t;
+    typedef uint32_t stack_t;
+    typedef uint16_t idx_t;
+    static constexpr int ID_BITS = 16, STACK_SHIFT = 16, NDEPTH = MAXLEAF + 4;
+    static constexpr unsigned NONE = 0xFFFF;
     union {                                // the DFS stack is only used once the heap is empty
-        unsigned long long heap[MAXLEAF + 2];  // (weight << 16) | node id
-        uint32_t stack[MAXLEAF + 4];
+        key_t heap[MAXLEAF + 2];
+        stack_t stack[MAXLEAF + 4];
     };
-    uint16_t parent[MAXN], left[MAXN], right[MAXN];
+    idx_t parent[MAXN], left[MAXN], right[MAXN];
     uint8_t side[MAXN];
-    uint16_t value[MAXLEAF + 2];      // leaf id -> symbol index (dummies included)
-    uint16_t leafDepth[MAXLEAF + 2];
-    uint16_t first[MAXLEAF + 4];      // first leaf (DFS order) at each depth == depthMap.get(d).get(0)
+    idx_t value[MAXLEAF + 2];         // leaf id -> symbol index (dummies included)
+    idx_t leafDepth[MAXLEAF + 2];
+    idx_t first[MAXLEAF + 4];         // first leaf (DFS order) at each depth == depthMap.get(d).get(0)
+};
+
+// Compact workspace for the header code (19 symbols + 2 dummies, <= 46 nodes) when the weights add up to less than
+// 1024 — true for header trials, whose weights count RLE pairs of at most 320 code lengths.  305 bytes, so a warp's
+// worth of them fits in shared memory next to the engine state.
+struct TreeWsCLc {
+    typedef uint16_t key_t;
+    typedef uint16_t stack_t;
+    typedef uint8_t idx_t;
+    static constexpr int ID_BITS = 6, STACK_SHIFT = 8, NDEPTH = 25;
+    static constexpr unsigned NONE = 0xFF;
+    union {
+        key_t heap[23];
+        stack_t stack[25];
+    };
+    idx_t parent[46], left[46], right[46];
+    uint8_t side[46];
+    idx_t value[23];
+    idx_t leafDepth[23];
+    idx_t first[25];
 };
 
 // Returns 0 on success, 1 when the tree cannot be balanced (the reference throws AssertionError there).
-// Node ids: [0, nleaf) leaves in insertion order, then internal nodes; MAXN >= 2 * (MAXLEAF + 2).  lens[0..n) receives the code lengths (0 for unused symbols).
-template <int MAXLEAF, int MAXN>
-D4_DEV_BIG int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, TreeWs<MAXLEAF, MAXN>& ws) {
+// Node ids: [0, nleaf) leaves in insertion order, then internal nodes.  lens[0..n) receives the code lengths (0 for
+// unused symbols).
+template <class WS>
+D4_DEV_BIG int huff_tree_ws(const uint32_t* freq, int n, int limit, uint8_t* lens, WS& ws) {
+    typedef typename WS::key_t key_t;
+    typedef typename WS::stack_t stack_t;
+    typedef typename WS::idx_t idx_t;
+    constexpr int IDB = WS::ID_BITS, SSH = WS::STACK_SHIFT;
+    constexpr unsigned IDM = (1u << IDB) - 1u, SNM = (1u << SSH) - 1u;
     int hs = 0;  // heap size
-    auto W = [](unsigned long long k) { return k >> 16; };
-    auto add = [&](unsigned long long x) {  // PriorityQueue.offer + siftUp
+    auto W = [](key_t k) { return (unsigned long long)k >> IDB; };
+    auto add = [&](key_t x) {  // PriorityQueue.offer + siftUp
         int k = hs++;
         while (k > 0) {
             int p = (k - 1) >> 1;
-            unsigned long long e = ws.heap[p];
+            key_t e = ws.heap[p];
             if (W(x) >= W(e)) break;
             ws.heap[k] = e;
             k = p;
@@ -46,17 +79,17 @@ D4_DEV_BIG int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, 
         ws.heap[k] = x;
     };
     auto poll = [&]() {  // PriorityQueue.poll + siftDown
-        unsigned long long result = ws.heap[0];
+        key_t result = ws.heap[0];
         int s = --hs;
-        unsigned long long x = ws.heap[s];
+        key_t x = ws.heap[s];
         if (s > 0) {
             int k = 0, half = s >> 1;
             while (k < half) {
                 int child = 2 * k + 1;
-                unsigned long long c = ws.heap[child];
+                key_t c = ws.heap[child];
                 int r = child + 1;
                 if (r < s) {
-                    unsigned long long cr = ws.heap[r];
+                    key_t cr = ws.heap[r];
                     if (W(c) > W(cr)) { c = cr; child = r; }
                 }
                 if (W(x) <= W(c)) break;
@@ -71,15 +104,15 @@ D4_DEV_BIG int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, 
     int nleaf = 0;
     for (int i = 0; i < n; i++)
         if (freq[i] > 0) {
-            ws.value[nleaf] = (uint16_t)i;
-            add(((unsigned long long)freq[i] << 16) | (unsigned)nleaf);
+            ws.value[nleaf] = (idx_t)i;
+            add((key_t)(((unsigned long long)freq[i] << IDB) | (unsigned)nleaf));
             nleaf++;
         }
     int index = 0;
     while (hs < 2) {  // dummy leaves (HuffmanTree.java:50-58)
         if (index >= n || freq[index] == 0) {
-            ws.value[nleaf] = (uint16_t)index;
-            add((1ull << 16) | (unsigned)nleaf);
+            ws.value[nleaf] = (idx_t)index;
+            add((key_t)((1ull << IDB) | (unsigned)nleaf));
             nleaf++;
         }
         index++;
@@ -87,32 +120,32 @@ D4_DEV_BIG int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, 
     int nn = nleaf;
     const int total = hs;
     for (int i = 0; i < total - 1; i++) {
-        unsigned long long l = poll(), r = poll();
+        key_t l = poll(), r = poll();
         int id = nn++;
-        int li = (int)(l & 0xFFFF), ri = (int)(r & 0xFFFF);
-        ws.left[id] = (uint16_t)li; ws.right[id] = (uint16_t)ri;
-        ws.parent[li] = (uint16_t)id; ws.side[li] = 0;
-        ws.parent[ri] = (uint16_t)id; ws.side[ri] = 1;
-        add(((W(l) + W(r)) << 16) | (unsigned)id);
+        int li = (int)(l & IDM), ri = (int)(r & IDM);
+        ws.left[id] = (idx_t)li; ws.right[id] = (idx_t)ri;
+        ws.parent[li] = (idx_t)id; ws.side[li] = 0;
+        ws.parent[ri] = (idx_t)id; ws.side[ri] = 1;
+        add((key_t)(((W(l) + W(r)) << IDB) | (unsigned)id));
     }
-    const int root = (int)(poll() & 0xFFFF);
-    ws.parent[root] = NODE_NONE;
+    const int root = (int)(poll() & IDM);
+    ws.parent[root] = (idx_t)WS::NONE;
     int maxDepth = 0;
     auto traverse = [&]() {  // HuffmanTree.traverse (:134-158), left-first DFS
-        for (int d = 0; d < MAXLEAF + 4; d++) ws.first[d] = NODE_NONE;
+        for (int d = 0; d < WS::NDEPTH; d++) ws.first[d] = (idx_t)WS::NONE;
         maxDepth = 0;
         int sp = 0;
-        ws.stack[sp++] = (uint32_t)root;
+        ws.stack[sp++] = (stack_t)root;
         while (sp > 0) {
-            uint32_t e = ws.stack[--sp];
-            int node = (int)(e & 0xFFFF), d = (int)(e >> 16);
+            stack_t e = ws.stack[--sp];
+            int node = (int)(e & SNM), d = (int)(e >> SSH);
             if (d > maxDepth) maxDepth = d;
             if (node >= nleaf) {
-                ws.stack[sp++] = (uint32_t)ws.right[node] | ((uint32_t)(d + 1) << 16);
-                ws.stack[sp++] = (uint32_t)ws.left[node] | ((uint32_t)(d + 1) << 16);
+                ws.stack[sp++] = (stack_t)((unsigned)ws.right[node] | ((unsigned)(d + 1) << SSH));
+                ws.stack[sp++] = (stack_t)((unsigned)ws.left[node] | ((unsigned)(d + 1) << SSH));
             } else {
-                if (ws.first[d] == NODE_NONE) ws.first[d] = (uint16_t)node;
-                ws.leafDepth[node] = (uint16_t)d;
+                if (ws.first[d] == (idx_t)WS::NONE) ws.first[d] = (idx_t)node;
+                ws.leafDepth[node] = (idx_t)d;
             }
         }
     };
@@ -122,21 +155,21 @@ D4_DEV_BIG int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, 
         int parent1 = ws.parent[leafA];
         int leafB = (ws.side[leafA] == 0) ? ws.right[parent1] : ws.left[parent1];
         int parent2 = ws.parent[parent1];
-        if (ws.side[parent1] == 0) { ws.left[parent2] = (uint16_t)leafB; ws.side[leafB] = 0; }
-        else                       { ws.right[parent2] = (uint16_t)leafB; ws.side[leafB] = 1; }
-        ws.parent[leafB] = (uint16_t)parent2;
+        if (ws.side[parent1] == 0) { ws.left[parent2] = (idx_t)leafB; ws.side[leafB] = 0; }
+        else                       { ws.right[parent2] = (idx_t)leafB; ws.side[leafB] = 1; }
+        ws.parent[leafB] = (idx_t)parent2;
         bool moved = false;
         for (int i = maxDepth - 2; i >= 1; i--) {
-            if (ws.first[i] != NODE_NONE) {
+            if (ws.first[i] != (idx_t)WS::NONE) {
                 int leafC = ws.first[i];
                 int parent3 = ws.parent[leafC];
                 int sideC = ws.side[leafC];
                 const int in = parent1;  // parent1 has just left the tree: its slot becomes the new internal node
-                ws.left[in] = (uint16_t)leafA; ws.parent[leafA] = (uint16_t)in; ws.side[leafA] = 0;
-                ws.right[in] = (uint16_t)leafC; ws.parent[leafC] = (uint16_t)in; ws.side[leafC] = 1;
-                if (sideC == 0) { ws.left[parent3] = (uint16_t)in; ws.side[in] = 0; }
-                else            { ws.right[parent3] = (uint16_t)in; ws.side[in] = 1; }
-                ws.parent[in] = (uint16_t)parent3;
+                ws.left[in] = (idx_t)leafA; ws.parent[leafA] = (idx_t)in; ws.side[leafA] = 0;
+                ws.right[in] = (idx_t)leafC; ws.parent[leafC] = (idx_t)in; ws.side[leafC] = 1;
+                if (sideC == 0) { ws.left[parent3] = (idx_t)in; ws.side[in] = 0; }
+                else            { ws.right[parent3] = (idx_t)in; ws.side[in] = 1; }
+                ws.parent[in] = (idx_t)parent3;
                 moved = true;
                 break;
             }
@@ -147,6 +180,10 @@ D4_DEV_BIG int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, 
     for (int l = 0; l < nleaf; l++)
         if (ws.value[l] < n) lens[ws.value[l]] = (uint8_t)ws.leafDepth[l];
     return 0;
+}
+template <int MAXLEAF, int MAXN>
+D4_DEV int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, TreeWs<MAXLEAF, MAXN>& ws) {
+    return huff_tree_ws(freq, n, limit, lens, ws);
 }
 
 using TreeWsCL = TreeWs<21, 46>;
@@ -391,13 +428,14 @@ D4_DEV int trim_ncl(const uint8_t* CL, int ncl) {
 
 // sizes in bits of the trials (flags, prune = false) and (flags, prune = true); returns 1 when a tree cannot be
 // balanced (the reference throws)
-D4_DEV int trial_sizes(const RunList& rl, int flags, int* bitsNoPrune, int* bitsPrune, TreeWsCL& ws) {
+template <class WS>
+D4_DEV int trial_sizes(const RunList& rl, int flags, int* bitsNoPrune, int* bitsPrune, WS& ws) {
     uint32_t f1[19], f2[19];
     uint8_t c1[19], c2[19];
     for (int i = 0; i < 19; i++) { f1[i] = 0; f2[i] = 0; }
     for (int r = 0; r < rl.n; r++)
         emit_run(rl.val[r], rl.len[r], flags, [&](int sym, int, int, int cnt) { f1[sym] += (uint32_t)cnt; });
-    if (huff_tree<21, 46>(f1, 19, 7, c1, ws)) return 1;
+    if (huff_tree_ws(f1, 19, 7, c1, ws)) return 1;
     const int ncl1 = trim_ncl(c1, 19);
     int sizeSum = 0, saved = 0;
     for (int r = 0; r < rl.n; r++)
@@ -415,7 +453,7 @@ D4_DEV int trial_sizes(const RunList& rl, int flags, int* bitsNoPrune, int* bits
             if (expand) f2[val] += (uint32_t)(run * cnt); else f2[sym] += (uint32_t)cnt;
         });
     *bitsNoPrune = 5 + 5 + 4 + 3 * ncl1 + sizeSum - saved;
-    if (huff_tree<21, 46>(f2, 19, 7, c2, ws)) return 1;
+    if (huff_tree_ws(f2, 19, 7, c2, ws)) return 1;
     const int ncl2 = trim_ncl(c2, ncl1);
     int sum2 = 0;
     for (int r = 0; r < rl.n; r++)

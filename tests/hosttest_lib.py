@@ -62,3 +62,13 @@ def trial_sizes(lit, dist, flags):
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     rc = L.host_trial_sizes(a, len(lit), b, len(dist), flags, C.byref(x), C.byref(y))
     return rc, x.value, y.value
+
+
+def huff_tree_compact(freq, limit):
+    n = len(freq)
+    f = (C.c_uint32 * n)(*freq)
+    lens = (C.c_uint8 * n)()
+    L = lib()
+    L.host_huff_tree_compact.argtypes = [C.POINTER(C.c_uint32), C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    rc = L.host_huff_tree_compact(f, n, limit, lens)
+    return rc, list(lens)

@@ -118,3 +118,36 @@ def test_size_only_trials_match_full_trials():
             assert rc == 0 and (a, b) == (want_a, want_b), (it, hex(f), L, D, (a, b), (want_a, want_b))
             checked += 1
     assert checked > 2000
+
+
+def test_compact_header_tree_matches_the_general_one():
+    """huff_tree_ws over the 305-byte TreeWsCLc (what trial threads keep in shared memory) against the general
+    workspace pinned on the oracle: 19 symbols, limit 7, weights adding up to at most 322 — including shapes that
+    need the depth limiter and shapes with fewer than two used symbols (dummy leaves)."""
+    rnd = random.Random(5)
+    n_limited = 0
+    for it in range(6000):
+        k = rnd.choice([0, 1, 2, 3, 5, 8, 12, 19])
+        freq = [0] * 19
+        budget = rnd.randint(k, 320) if k else 0
+        for s in rnd.sample(range(19), k):
+            freq[s] = 1
+            budget -= 1
+        while budget > 0 and k:
+            s = rnd.choice([i for i in range(19) if freq[i]])
+            add = min(budget, rnd.choice([1, 1, 2, 3, 8, 21, 55, 144]))
+            freq[s] += add
+            budget -= add
+        if it % 7 == 0 and k >= 9:   # Fibonacci-like weights force depth > 7
+            fib = [1, 1, 2, 3, 5, 8, 13, 21, 34, 55, 89]
+            used = [i for i in range(19) if freq[i]][:len(fib)]
+            for i in range(19):
+                freq[i] = 0
+            for i, s in enumerate(used):
+                freq[s] = fib[i]
+        assert sum(freq) <= 322
+        a = H.huff_tree(freq, 7)
+        b = H.huff_tree_compact(freq, 7)
+        assert a == b, (freq, a, b)
+        n_limited += max(a[1]) == 7
+    assert n_limited > 50
