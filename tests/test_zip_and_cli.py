@@ -135,3 +135,16 @@ def test_cli_optimise_folder(oracle, tmp_path, capsys):
     assert (tmp_path / "tree" / "t.png").read_bytes() == read_golden("text-opt.png")
     assert (d / "notes.txt").read_bytes() == b"plain text, not a container"
     assert capsys.readouterr().out.count("Optimising file ") == 2
+
+
+def test_cli_has_no_cpu_fallback(tmp_path):
+    """Without a CUDA device the command line must fail loudly (no silent CPU path): the default stream engine is the
+    CUDA one and its first call raises."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    from deft4j_b200.__main__ import main
+    from deft4j_b200._native import Deft4cuError
+    with pytest.raises(Deft4cuError):
+        main(["optimise", golden_path("lz-twice-twice.txt.gz"), str(tmp_path / "o.gz")])
+    assert not (tmp_path / "o.gz").exists()
