@@ -1,37 +1,5 @@
-# INTEGRATION — binding `libdeft4cu.so` from the reference (deft4j)
-
-The drop-in boundary is the C ABI in `include/deft4cu.h`: plain pointers and sizes, one process per GPU.  This file shows the
-binding a deft4j maintainer would add.  **It cannot be compiled in this image** (no `java`/`javac`; probed), so the automated
-evidence for the ABI is `tests/test_abi.py` (every declared symbol exported, no-GPU) and `tests/test_gpu_parity.py` (ctypes calls
-through the same entry points, on the B200).  The Python package `deft4j_b200` is the working mirror of the reference's host API.
-
-## 1. What replaces what
-
-Paths relative to `deft4j-base/src/main/java/com/github/NeRdTheNed/deft4j/` (container paths under
-`deft4j-container/.../container/`).
-
-| Reference call | Replacement | C entry point |
-|---|---|---|
-| `DeflateStream.parse(byte[])` / `parse(InputStream)` `deflate/DeflateStream.java:68,72-126` | native handle + consumed byte count (the container then reads its trailer from `consumed`) | `deft4cu_stream_parse`, `deft4cu_stream_parse_batch` |
-| `DeflateStream.optimise(boolean)` `:496-566` | returns saved bits | `deft4cu_stream_optimise`, `deft4cu_stream_optimise_batch` |
-| `static DeflateFilesContainer.optimise(List<DeflateStream>, boolean)` `DeflateFilesContainer.java:18-43` | one device batch for the whole list (this is where the throughput is) | `deft4cu_stream_optimise_batch` or, fused with parse+write, `deft4cu_optimise_batch` |
-| `DeflateStream.write(OutputStream)` `:128-145`, `asBytes()` `:652-660` | bytes of the rewritten stream | `deft4cu_stream_write` |
-| `DeflateStream.getUncompressedData()` `:159-169` and its only consumers, `CRC32`/`Adler32`/ISIZE in `GZFile.java:130-145`, `ZLibFile.java:42-51` | length + device-computed checksums (copy-out still available) | `deft4cu_stream_uncompressed_len`, `deft4cu_stream_checksums`, `deft4cu_stream_uncompressed` |
-| `DeflateStream.getSizeBits()` `:171-182` | | `deft4cu_stream_size_bits` |
-| `DeflateStream.printBlockInfo()` `:35-51` (block type / size listing) | per-block records | `deft4cu_stream_block_count`, `deft4cu_stream_block_info` |
-| `Deft.optimiseDeflateStream(byte[], boolean)` `Deft.java:21-34` (returns the same array when nothing was saved or the parse failed) | `*out == NULL` ⇒ keep the caller's array | `deft4cu_optimise_deflate_stream`, `deft4cu_free_buffer` |
-| `Deft.getSizeBitsFallback(byte[])` `Deft.java:48-54` | | `deft4cu_size_bits_fallback` |
-
-Error mapping: `DEFT4CU_ERR_PARSE` → `parse` returns `false`; `DEFT4CU_ERR_WRITE` → `IOException` from `write/asBytes`;
-`DEFT4CU_ERR_UNSUPPORTED` → treat as parse failure (inputs the reference only accepts by accident, SURVEY H10, or a batch whose
-decoded size exceeds 4 GiB); `DEFT4CU_ERR_CUDA` → fatal (there is no CPU fallback; do not catch and fall back to the Java path
-silently).  Threading: one handle per thread at a time; batch calls may come from several host threads.
-
-## 2. Java binding (Panama FFM, JDK 22+) — the stub to add to `deft4j-base`
-
-The same sources are kept as files under `java/` (`deflate/DeflateStream.java`, `Deft.java`); nothing in this repository builds them.
-
-```java
+// Panama FFM facade over libdeft4cu.so (include/deft4cu.h) with the public surface of deft4j-base's DeflateStream.
+// NOT compiled or tested in this repository's image (no JDK): see INTEGRATION.md.  JDK 22+.
 package com.github.NeRdTheNed.deft4j.deflate;
 
 import java.lang.foreign.*;
@@ -132,31 +100,3 @@ public final class DeflateStream implements AutoCloseable {
     }
     private static String lastError() throws Throwable { return ((MemorySegment) LASTERR.invokeExact()).reinterpret(4096).getString(0); }
 }
-```
-
-`Deft.optimiseDeflateStream` (`Deft.java:21-34`) becomes a call to `deft4cu_optimise_deflate_stream(in, len, merge, &out, &outLen)`:
-`out == NULL` ⇒ `return original;` (same array object, as the reference does), else copy `outLen` bytes and
-`deft4cu_free_buffer(out)`.
-
-Container changes (the only edits outside `deft4j-base`):
-* `DeflateFilesContainer.optimise(List<DeflateStream>, boolean)` (`DeflateFilesContainer.java:18-43`): replace the per-stream loop
-  with `DeflateStream.optimiseAll(streams, mergeBlocks)`, keep the two `println`s (they print `saved[i]` and the total).
-* `GZFile.write` (`GZFile.java:129-145`) and `ZLibFile.write` (`ZLibFile.java:41-51`): take CRC-32 / Adler-32 / ISIZE from
-  `getChecksums()` / `getUncompressedLength()` instead of recomputing them over `getUncompressedData()`.
-* For a folder / archive of many files (`OptimiseFolder`, ZIP entries, PNG chunk lists) collect all `DeflateStream`s first and
-  make one `optimiseAll` call: small streams only fill the GPU as a batch.
-* JNI alternative: one `native` method per entry point with `GetPrimitiveArrayCritical` on the `byte[]`s; the C side is the
-  same calls.
-
-Multi-GPU: one JVM (or one worker process) per GPU with `deft4cu_init(device)`; deal streams to workers by size
-(`deft4j_b200/sharding.py` is the reference implementation of that policy); no cross-process communication is needed.
-
-## 3. Python mirror (what the tests drive)
-
-`python -m deft4j_b200 optimise [-f FORMAT] [-r] [--no-merge-blocks] IN OUT` and `python -m deft4j_b200 optimise-folder DIR`
-mirror `deft4j-cmd` (`cmd/Optimise.java:15-54`, `cmd/OptimiseFolder.java:33-67`, `cmd/CMDUtil.java:57-181`): same messages on
-stdout/stderr, the temp-file overwrite protocol, exit code 1 on failure.
-
-`deft4j_b200.DeflateStream` / `Deft` / `container.{GZFile, ZLibFile, PNGFile, ZipFile, RawDeflateFile, getContainerForBytes}` keep the
-reference's method names and return conventions; `deft4j_b200.optimise_batch(list_of_bytes, merge)` is the fused batch entry;
-`deft4j_b200.sharding.optimise_sharded` is the N-GPU entry (torch.distributed process group, one rank per GPU).
