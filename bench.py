@@ -7,9 +7,15 @@ A step = one pass of the whole path (parse -> optimise -> write -> checksums) ov
   e2e    : the same through the reference-facing batch entry of the C ABI (deft4cu_optimise_batch) with pinned HOST
            buffers in and host buffers out, host<->device copies inside the timed region
   roofline / cpu_baseline : see DESIGN.md "Measurement"
+  output_verified : after the timed loops the rewritten streams of the last step are inflated with zlib and compared
+           (length, CRC-32, Adler-32) with the inflate of the input and with the checksums the device computed
+  shapes : short runs of the other named shapes (C3 PNG IDAT batch, C4 ZIP entry mix, C5 adversarial, and the very
+           sample the CPU reference arm is timed on), sharded by stream over the ranks (strong scaling over one list)
+  per_rank : every rank's own step time and kernel-family times (N > 1)
 
 Launch: `python bench.py --gpus N --steps K --warmup W` (N=1) or under torch.distributed.run with N ranks (one
-process per GPU; streams are sharded by rank, C2's single stream is replicated per rank: no data-path collective).
+process per GPU; C2's single stream is replicated per rank, stream lists are sharded by rank: no data-path collective,
+the process group is gloo and only carries barriers, timings and result lists).
 `--impl reference` times the CPU restatement of the reference (oracle/, the reference itself is Java and this image
 has no JVM) with every host core on a bounded sample of the same workload.
 """
@@ -18,11 +24,11 @@ import ctypes as C
 import json
 import multiprocessing as mp
 import os
+import shutil
 import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 import zlib
 
@@ -31,6 +37,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "input MB/s optimised (-m NONE)"
+C2_WHY_NO_MERGE = ("--no-merge-blocks: on stationary text every adjacent merge saves a header, so mergeBlocks() "
+                   "(DeflateStream.java:568-650) cascades the whole stream into ONE block, re-running optimiseBlock on the "
+                   "growing union each time (quadratic; the oracle turns 29 blocks into 1 at 660 KB and needs 4.5x the "
+                   "time) - not computable at 1 GiB by any implementation of these semantics, the reference included, "
+                   "which is why its own runTestOpt.sh:10-11 uses this flag for its large fixtures; merge-on throughput "
+                   "is reported per shape under `shapes`")
 
 
 def parse_args():
@@ -39,12 +51,15 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "ref"])
     ap.add_argument("--size-mib", type=float, default=float(os.environ.get("DEFT4CU_BENCH_MIB", "1024")),
                     help="C2: size of the single raw deflate stream per GPU (BASELINE config: 1024)")
     ap.add_argument("--count", type=int, default=0, help="C3/C4: streams per GPU (default 12500 / 1250)")
     ap.add_argument("--merge", type=int, default=-1, help="mergeBlocks; default: 0 for C2 (see DESIGN.md), 1 otherwise")
-    ap.add_argument("--sample-seconds", type=float, default=20.0, help="CPU baseline budget")
+    ap.add_argument("--sample-seconds", type=float, default=30.0, help="CPU baseline budget per sample")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the short C3/C4/C5 runs")
+    ap.add_argument("--no-verify", action="store_true", help="skip inflating the output of the last timed step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
 
 
@@ -52,23 +67,32 @@ def workload_config(a):
     merge = a.merge if a.merge >= 0 else (0 if a.workload == "c2" else 1)
     if a.workload == "c2":
         name = ("single %d MiB raw deflate stream per GPU, zlib level 6 dynamic blocks over synthetic Zipf text "
-                "(BASELINE configs[1]), --no-merge-blocks" % a.size_mib)
+                "(BASELINE configs[1]), %s" % (a.size_mib, "merge blocks" if merge else "--no-merge-blocks"))
     elif a.workload == "c3":
         a.count = a.count or 12500
         name = "%d synthetic 256x256 RGBA PNG IDAT streams per GPU (BASELINE configs[2]), merge blocks" % a.count
-    else:
+    elif a.workload == "c4":
         a.count = a.count or 1250
         name = "%d ZIP-entry deflate payloads per GPU mixing stored/fixed/dynamic (BASELINE configs[3]), merge blocks" % a.count
+    elif a.workload == "c5":
+        name = "adversarial streams (BASELINE configs[4]): len-258 / dist-1 and dist-32768 matches at 8 MiB, RLE-heavy headers"
+    else:
+        name = "the CPU reference arm's own sample (C2-style streams, one or two per host core)"
     return name, merge
 
 
 def make_streams(a, rank):
     import workloads as W
     if a.workload == "c2":
-        return [W.c2_stream(int(a.size_mib * (1 << 20)), seed=0xDEF7 + rank)]
+        # every rank optimises the SAME stream (replicas): per-rank times are then comparable
+        return [W.c2_stream(int(a.size_mib * (1 << 20)), seed=0xDEF7)]
     if a.workload == "c3":
         return W.c3_streams(a.count, first=rank * a.count)
-    return W.c4_streams(a.count, seed=4 + rank)
+    if a.workload == "c4":
+        return W.c4_streams(a.count, seed=4 + rank)
+    if a.workload == "c5":
+        return W.c5_streams(scale=8)
+    return reference_sample("c2", os.cpu_count() or 1, a.sample_seconds)[0]
 
 
 # ---- CPU baseline: the oracle on every host core, one process per stream -------------------------------------------
@@ -83,35 +107,62 @@ def _oracle_job(args):
     return time.perf_counter() - t0
 
 
-def cpu_sample_streams(a, cores, per_stream_seconds):
-    """A bounded sample of the workload: `cores` independent streams of the same kind, each sized for about
-    per_stream_seconds of single-thread oracle time (the oracle runs ~45 KB/s of C2 input per core)."""
+def _oracle_out(args):
+    """(saved bits, output bytes, consumed, crc32, adler32, uncompressed length) of the oracle for one stream: the
+    checker used by the parity tests."""
+    raw, merge = args
+    import oracle_lib
+    s = oracle_lib.OracleDeflateStream()
+    assert s.parse(raw)
+    saved = s.optimise(bool(merge))
+    out = s.asBytes()
+    crc, adler, n = s.getChecksums()
+    return saved, out, s.consumed, crc, adler, n
+
+
+ORACLE_KBPS_PER_CORE = 45e3   # C2 input bytes per second of one oracle thread (no merge), measured on this pool's hosts
+
+
+def reference_sample(workload, cores, seconds):
+    """THE bounded sample both CPU legs use (`cpu_baseline` inside our arm and `--impl reference`): deterministic
+    streams of the workload's kind, two per host core, sized so that all cores together need about `seconds`."""
     import workloads as W
-    if a.workload == "c2":
-        text_bytes = int(45e3 * 2.4 * per_stream_seconds)
+    if workload in ("c2", "ref"):
+        text_bytes = int(ORACLE_KBPS_PER_CORE * 2.4 * seconds / 2)
         out = []
-        for k in range(cores):
+        for k in range(2 * cores):
             co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
             out.append(co.compress(W.c2_text(text_bytes, seed=0xBA5E + k)) + co.flush())
-        return out, "%d independent C2-style streams of %d KiB text each (one per core)" % (cores, text_bytes >> 10)
-    if a.workload == "c3":
-        n = max(cores, int(cores * per_stream_seconds / 1.5))
+        return out, "%d independent C2-style streams of %d KiB text each (two per core)" % (2 * cores, text_bytes >> 10)
+    if workload == "c3":
+        n = max(cores, int(cores * seconds / 1.5))
         return W.c3_streams(n, first=5_000_000), "%d C3 PNG IDAT streams" % n
-    n = max(cores, int(cores * per_stream_seconds / 0.8))
-    return W.c4_streams(n, seed=99), "%d C4 entry payloads" % n
+    if workload == "c4":
+        n = max(cores, int(cores * seconds / 0.8))
+        return W.c4_streams(n, seed=99), "%d C4 entry payloads" % n
+    return W.c5_streams(scale=1), "the C5 adversarial streams at 1 MiB"
 
 
-def run_cpu_baseline(a, merge, budget_s):
+def jvm_probe():
+    """The reference is Java: say whether this box could have run it (it cannot be built without /root/reference,
+    which only exists in the build container, and that container has no JDK: DESIGN.md 'Oracle')."""
+    j, jc = shutil.which("java"), shutil.which("javac")
+    return "java=%s javac=%s" % (j or "absent", jc or "absent")
+
+
+def run_cpu_baseline(a, merge, budget_s, streams=None, what=None):
     import oracle_lib
     oracle_lib.build()
     cores = os.cpu_count() or 1
-    streams, what = cpu_sample_streams(a, cores, budget_s)
+    if streams is None:
+        streams, what = reference_sample(a.workload, cores, budget_s)
     t0 = time.perf_counter()
     with mp.get_context("spawn").Pool(cores) as pool:
         pool.map(_oracle_job, [(s, merge) for s in streams], chunksize=1)
     dt = time.perf_counter() - t0
     total = sum(len(s) for s in streams)
     return {"value": total / dt / 1e6, "unit": "MB/s", "cores": cores, "kind": "port",
+            "value_per_core": total / dt / 1e6 / cores, "merge_blocks": bool(merge), "seconds": dt, "jvm": jvm_probe(),
             "sample": "%s, %.2f MB of input deflate in %.1f s; the reference is Java (no JVM in this image), so this is "
                       "the C++ restatement (oracle/), which is faster than the JVM original" % (what, total / 1e6, dt)}
 
@@ -163,24 +214,26 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# ---- the two arms ----------------------------------------------------------------------------------------------------
+FAMILIES = ["parse_count", "emit", "lz77", "optimise", "finish_merge", "write", "checksums", "parse_rewalks"]
+
+
+# ---- the reference arm -----------------------------------------------------------------------------------------------
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     name, merge = workload_config(a)
-    # K+W bounded samples; each is the whole CPU budget divided over the steps
-    per = max(2.0, a.sample_seconds / max(1, a.steps))
-    vals = []
-    base = None
-    for i in range(a.warmup + a.steps):
-        if i < a.warmup and i > 0:
-            continue  # one warm-up sample is enough to page the library in
-        base = run_cpu_baseline(a, merge, per)
-        if i >= a.warmup:
+    cores = os.cpu_count() or 1
+    streams, what = reference_sample(a.workload, cores, a.sample_seconds)
+    vals, base = [], None
+    # one warm-up sample pages the library in; every timed step is the same bounded sample
+    for i in range(min(a.warmup, 1) + a.steps):
+        base = run_cpu_baseline(a, merge, a.sample_seconds, streams, what)
+        if i >= min(a.warmup, 1):
             vals.append(base["value"])
     v = sum(vals) / len(vals)
     base["value"] = v
+    base["value_per_core"] = v / cores
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "MB/s", "n_gpus": a.gpus, "steps": a.steps,
                       "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                       "dtype": "u8", "data": "synthetic", "config": {"workload": name, "merge_blocks": bool(merge)},
@@ -188,151 +241,249 @@ def run_reference(a):
                       "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ---- our arm ---------------------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-group plumbing: gloo only (barriers, timings, result lists): the data path has no collective."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        os.environ["DEFT4CU_DEVICE"] = str(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("gloo")
+            self.dist = dist
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+
+    def gather(self, obj):
+        if not self.dist:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def max(self, x):
+        return max(self.gather(x))
+
+    def sum(self, x):
+        return sum(self.gather(x))
+
+
+def measure(ctx, L, N, streams, merge, steps, warmup, sample_clocks=False, verify=False, e2e_steps=None):
+    """value (device-resident, CUDA events on the launching stream), e2e (pinned host buffers through the batch
+    entry), kernel-family times, launches, output verification — for this rank's `streams`."""
+    torch = ctx.torch
+    n = len(streams)
+    in_bytes = sum(len(s) for s in streams)
+    out = {"n": n, "in_bytes": in_bytes}
+    ptrs, lens = N.make_ptr_arrays(streams)
+    stream = torch.cuda.Stream()
+    fam = [0.0] * 8
+    launches = C.c_uint64(0)
+    h = C.c_void_p()
+    if n:
+        rc = L.deft4cu_device_batch_create(ptrs, lens, n, C.byref(h))
+        assert rc == 0, N.last_error()
+
+    def step():
+        if not n:
+            return
+        rc = L.deft4cu_device_batch_run(h, merge, C.byref(launches), C.c_void_p(stream.cuda_stream))
+        assert rc == 0, N.last_error()
+
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            step()
+        ctx.barrier()
+        sampler = ClockSampler(ctx.local) if sample_clocks and ctx.rank == 0 else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        total_launches = 0
+        for _ in range(steps):
+            step()
+            total_launches += launches.value
+            if n:
+                ms = (C.c_float * 8)()
+                L.deft4cu_device_batch_timings(h, ms, 8)
+                fam = [x + y for x, y in zip(fam, ms)]
+        ev1.record(stream)
+        ctx.barrier()
+        out["clocks"] = sampler.stop() if sampler else None
+    out["dev_ms"] = ev0.elapsed_time(ev1)
+    out["launches"] = total_launches
+    out["fam"] = [x / max(1, steps) for x in fam]
+    out["out_bytes"] = out["unc_bytes"] = out["saved_bits"] = 0
+    out["verified"] = None
+    if n:
+        res = (N.Result * n)()
+        assert L.deft4cu_device_batch_fetch(h, res) == 0, N.last_error()
+        assert all(r.status == 0 for r in res), [r.status for r in res if r.status]
+        out["out_bytes"] = sum(r.out_len for r in res)
+        out["unc_bytes"] = sum(r.uncompressed_len for r in res)
+        out["saved_bits"] = sum(r.saved_bits for r in res)
+        if verify:
+            t0 = time.time()
+            for raw, r in zip(streams, res):
+                verify_stream(raw, C.string_at(r.out, r.out_len), r)
+            out["verified"] = {"streams": n, "seconds": round(time.time() - t0, 1)}
+        L.deft4cu_free_results(res, n)
+        L.deft4cu_device_batch_free(h)
+    # ---- e2e: pinned host buffers through the batch entry of the C ABI -----------------------------------------------
+    e2e_steps = e2e_steps or steps
+    out["e2e_s"] = 0.0
+    out["d2h"] = 0
+    if n:
+        pinned = [torch.frombuffer(bytearray(s), dtype=torch.uint8).pin_memory() for s in streams]
+        pp = (C.c_char_p * n)(*[C.cast(t.data_ptr(), C.c_char_p) for t in pinned])
+        e2e_res = (N.Result * n)()
+        if warmup > 0:  # one untimed call: the library pins its result block on first use
+            rc = L.deft4cu_optimise_batch(pp, lens, n, merge, e2e_res)
+            assert rc == 0, N.last_error()
+            L.deft4cu_free_results(e2e_res, n)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    if n:
+        for _ in range(e2e_steps):
+            rc = L.deft4cu_optimise_batch(pp, lens, n, merge, e2e_res)
+            assert rc == 0, N.last_error()
+            out["d2h"] = sum(r.out_len for r in e2e_res) + C.sizeof(N.Result) * n
+            L.deft4cu_free_results(e2e_res, n)
+        torch.cuda.synchronize()
+    out["e2e_s"] = (time.perf_counter() - t0) / e2e_steps
+    ctx.barrier()
+    return out
+
+
+def verify_stream(raw, opt, r):
+    """The rewritten stream inflates to exactly the bytes the input inflates to, and the device's length / CRC-32 /
+    Adler-32 are theirs (incremental, so a 2.8 GB inflate never sits in memory twice)."""
+    def digest(data):
+        d = zlib.decompressobj(-15)
+        crc, ad, n = 0, 1, 0
+        for off in range(0, len(data), 1 << 24):
+            chunk = d.decompress(data[off:off + (1 << 24)])
+            crc, ad, n = zlib.crc32(chunk, crc), zlib.adler32(chunk, ad), n + len(chunk)
+        chunk = d.flush()
+        crc, ad, n = zlib.crc32(chunk, crc), zlib.adler32(chunk, ad), n + len(chunk)
+        assert d.eof, "stream does not end with a final block"
+        return crc & 0xffffffff, ad & 0xffffffff, n
+    want = digest(raw)
+    got = digest(opt)
+    assert got == want, ("rewritten stream inflates differently", got, want)
+    assert (r.crc32, r.adler32, r.uncompressed_len) == want, ("device checksums differ", (r.crc32, r.adler32, r.uncompressed_len), want)
+    assert len(opt) * 8 - 7 <= r.size_bits_out <= len(opt) * 8 and r.size_bits_out == r.size_bits_in - r.saved_bits
+    assert len(opt) <= len(raw)
+
+
+def roofline_of(m, peak, peak_src):
+    algo = m["in_bytes"] + m["out_bytes"] + 2 * m["unc_bytes"]      # DESIGN.md: A = C_in + C_out + 2 U per pass
+    opt_ms = m["fam"][3]
+    achieved = algo / (opt_ms / 1e3) / 1e9 if opt_ms > 0 else 0.0
+    return {"bound": "hbm", "kernel": "k_opt_blocks", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+            "kernel_ms": opt_ms, "family_ms_per_step": dict(zip(FAMILIES, m["fam"]))}
+
+
+def run_shapes(ctx, L, N, a, peak, peak_src):
+    """Short runs of the other named shapes: ONE list per shape, the same on every rank, dealt to the ranks by
+    deft4j_b200.sharding.shard_streams (strong scaling; no collective on the data path)."""
+    import workloads as W
+    from deft4j_b200.sharding import shard_streams
+    cores = os.cpu_count() or 1
+    shapes = {}
+    plan = [("c3_png_idat", lambda: W.c3_streams(768, first=10_000), 1, "768 synthetic 256x256 RGBA PNG IDAT streams, merge blocks"),
+            ("c4_zip_entries", lambda: W.c4_streams(768, seed=5), 1, "768 ZIP-entry payloads (stored / Z_FIXED / dynamic, 1-256 KiB), merge blocks"),
+            ("c5_adversarial", lambda: W.c5_streams(scale=8), 1, "15 adversarial streams: len-258 dist-1 / dist-32768 at 8 MiB, sparse alphabets; merge blocks"),
+            ("c2_reference_sample", lambda: reference_sample("c2", cores, a.sample_seconds)[0], 0,
+             "exactly the streams the CPU reference arm is timed on (same_config), --no-merge-blocks like the headline")]
+    for name, gen, merge, what in plan:
+        t0 = time.time()
+        streams = gen()
+        shards = shard_streams([len(s) for s in streams], ctx.world)
+        mine = [streams[i] for i in shards[ctx.rank]]
+        m = measure(ctx, L, N, mine, merge, steps=2, warmup=1, verify=not a.no_verify, e2e_steps=2)
+        dev_ms = ctx.max(m["dev_ms"]) / 2
+        e2e_s = ctx.max(m["e2e_s"])
+        total_in = sum(len(s) for s in streams)
+        fams = ctx.gather(m["fam"])
+        rf = roofline_of({"in_bytes": ctx.sum(m["in_bytes"]), "out_bytes": ctx.sum(m["out_bytes"]),
+                          "unc_bytes": ctx.sum(m["unc_bytes"]), "fam": [max(f[k] for f in fams) for k in range(8)]}, peak, peak_src)
+        shapes[name] = {"workload": what, "streams": len(streams), "input_bytes": total_in, "merge_blocks": bool(merge),
+                        "value": total_in / (dev_ms / 1e3) / 1e6, "e2e": total_in / e2e_s / 1e6, "unit": "MB/s",
+                        "ms_per_step": dev_ms, "scaling": "strong", "frac": rf["frac"],
+                        "family_ms_per_step": rf["family_ms_per_step"], "saved_bits": ctx.sum(m["saved_bits"]),
+                        "uncompressed_bytes": ctx.sum(m["unc_bytes"]),
+                        "output_verified": None if a.no_verify else bool(m["verified"]), "seconds": round(time.time() - t0, 1)}
+    return shapes
+
+
 def run_ours(a):
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    os.environ["DEFT4CU_DEVICE"] = str(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Ctx()
     from deft4j_b200 import _native as N
     L = N.lib()
     name, merge = workload_config(a)
     t_gen = time.time()
-    streams = make_streams(a, rank)
+    streams = make_streams(a, ctx.rank)
     t_gen = time.time() - t_gen
-    in_bytes = sum(len(s) for s in streams)
-    n = len(streams)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return t.item()
-
-    # ---- value: inputs resident in HBM ---------------------------------------------------------------------------
-    ptrs, lens = N.make_ptr_arrays(streams)
-    h = C.c_void_p()
-    rc = L.deft4cu_device_batch_create(ptrs, lens, n, C.byref(h))
-    assert rc == 0, N.last_error()
-    stream = torch.cuda.Stream()
-    launches = C.c_uint64(0)
-    fam = [0.0] * 8
-
-    def step():
-        rc = L.deft4cu_device_batch_run(h, merge, C.byref(launches), None if os.environ.get('D4_OWN') else C.c_void_p(stream.cuda_stream))
-        assert rc == 0, N.last_error()
-
-    with torch.cuda.stream(stream):
-        for _ in range(a.warmup):
-            step()
-        barrier()
-        sampler = ClockSampler(local) if rank == 0 and not os.environ.get('D4_NOSAMPLER') else None
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        total_launches = 0
-        for _ in range(a.steps):
-            step()
-            total_launches += launches.value
-            ms = (C.c_float * 8)()
-            L.deft4cu_device_batch_timings(h, ms, 8)
-            fam = [x + y for x, y in zip(fam, ms)]
-        ev1.record(stream)
-        barrier()
-        clocks = sampler.stop() if sampler else None
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    res = (N.Result * n)()
-    assert L.deft4cu_device_batch_fetch(h, res) == 0
-    out_bytes = sum(r.out_len for r in res)
-    unc_bytes = sum(r.uncompressed_len for r in res)
-    saved_bits = sum(r.saved_bits for r in res)
-    assert all(r.status == 0 for r in res)
-    L.deft4cu_free_results(res, n)
-    L.deft4cu_device_batch_free(h)
-    total_in = sum_over_ranks(in_bytes)
+    m = measure(ctx, L, N, streams, merge, a.steps, a.warmup, sample_clocks=True, verify=not a.no_verify)
+    dev_ms = ctx.max(m["dev_ms"])
+    total_in = ctx.sum(m["in_bytes"])
     value = total_in * a.steps / (dev_ms / 1e3) / 1e6
-
-    # ---- e2e: pinned host buffers through the batch entry of the C ABI ---------------------------------------------
-    pinned = [torch.frombuffer(bytearray(s), dtype=torch.uint8).pin_memory() for s in streams]
-    pp = (C.c_char_p * n)(*[C.cast(t.data_ptr(), C.c_char_p) for t in pinned])
-    e2e_res = (N.Result * n)()
-    if a.warmup > 0:  # one untimed call: the library pins its result block on first use
-        rc = L.deft4cu_optimise_batch(pp, lens, n, merge, e2e_res)
-        assert rc == 0, N.last_error()
-        L.deft4cu_free_results(e2e_res, n)
-    barrier()
-    t0 = time.perf_counter()
-    d2h = 0
-    for _ in range(a.steps):
-        rc = L.deft4cu_optimise_batch(pp, lens, n, merge, e2e_res)
-        assert rc == 0, N.last_error()
-        d2h = sum(r.out_len for r in e2e_res) + C.sizeof(N.Result) * n
-        L.deft4cu_free_results(e2e_res, n)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    if world > 1:
-        dist.barrier()
-    e2e_value = total_in * a.steps / e2e_s / 1e6
-
-    # ---- roofline of the dominant kernel (k_opt_blocks, the candidate enumerator) ------------------------------------
+    e2e_value = total_in / ctx.max(m["e2e_s"]) / 1e6
     peak, peak_src = peaks()
-    algo_bytes = in_bytes + out_bytes + 2 * unc_bytes          # A = C_in + C_out + 2 U per pass
-    opt_ms = fam[3] / a.steps
-    achieved = algo_bytes / (opt_ms / 1e3) / 1e9 if opt_ms > 0 else 0.0
-    names = ["parse_count", "emit", "lz77", "optimise", "finish_merge", "write", "checksums", "parse_rewalks"]
-    roofline = {"bound": "hbm", "kernel": "k_opt_blocks", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": opt_ms,
-                "family_ms_per_step": {k: v / a.steps for k, v in zip(names, fam)}}
+    roofline = roofline_of(m, peak, peak_src)
     # DRAM traffic of the dominant kernel comes from an ncu capture (never measured inside a timed run):
     # profiles/traffic.json records dram__bytes_read.sum + dram__bytes_write.sum of one k_opt_blocks launch and the input
     # size it was captured on; it is reported as `traffic` only when this run's launch processes the same input.
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        if abs(tj.get("input_bytes", 0) - in_bytes) <= 0.01 * in_bytes and tj.get("merge_blocks", 0) == merge:
+        if abs(tj.get("input_bytes", 0) - m["in_bytes"]) <= 0.01 * m["in_bytes"] and tj.get("merge_blocks", 0) == merge:
             roofline["traffic"] = tj["dram_bytes"]
         roofline["traffic_note"] = tj
     except Exception:
         pass
-
-    if rank == 0:
-        base = run_cpu_baseline(a, merge, a.sample_seconds) if world == 1 else None
-        line = {"metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+    per_rank = ctx.gather({"rank": ctx.rank, "ms_per_step": m["dev_ms"] / a.steps, "e2e_s_per_step": m["e2e_s"],
+                           "family_ms_per_step": dict(zip(FAMILIES, m["fam"]))})
+    shapes = None
+    if a.workload == "c2" and not a.no_shapes:
+        shapes = run_shapes(ctx, L, N, a, peak, peak_src)
+    if ctx.rank == 0:
+        base = None
+        if ctx.world == 1 and not a.no_cpu:
+            base = run_cpu_baseline(a, merge, a.sample_seconds)
+        in_bytes = m["in_bytes"]
+        cfg = {"workload": name, "merge_blocks": bool(merge), "streams_per_gpu": m["n"], "input_bytes_per_gpu": in_bytes,
+               "uncompressed_bytes_per_gpu": m["unc_bytes"], "saved_bits_per_gpu": m["saved_bits"],
+               "l2": "inputs larger than L2" if in_bytes > (126 << 20) else
+               "inputs smaller than L2; every step re-parses from HBM-resident input after the previous step's "
+               "multi-GB intermediates passed through L2", "datagen_s": round(t_gen, 1)}
+        if a.workload == "c2" and not merge:
+            cfg["merge_note"] = C2_WHY_NO_MERGE
+        line = {"metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": ctx.world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic",
-                "config": {"workload": name, "merge_blocks": bool(merge), "streams_per_gpu": n,
-                           "input_bytes_per_gpu": in_bytes, "uncompressed_bytes_per_gpu": unc_bytes,
-                           "saved_bits_per_gpu": saved_bits, "l2": "inputs larger than L2" if in_bytes > (126 << 20) else
-                           "inputs smaller than L2; every step re-parses from HBM-resident input after the previous step's "
-                           "multi-GB intermediates passed through L2",
-                           "datagen_s": round(t_gen, 1)},
-                "clocks": clocks, "gpu_launches": total_launches,
-                "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h},
-                "roofline": roofline}
+                "dtype": "u8", "data": "synthetic", "config": cfg, "clocks": m["clocks"], "gpu_launches": m["launches"],
+                "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": m["d2h"]},
+                "roofline": roofline, "output_verified": bool(m["verified"]) if not a.no_verify else None,
+                "verify": m["verified"], "saved_bits": m["saved_bits"], "per_rank": per_rank}
+        if shapes is not None:
+            line["shapes"] = shapes
         if base:
             line["cpu_baseline"] = base
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.dist:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -58,7 +58,12 @@ static void dfree(T*& p, cudaStream_t s) {
     p = nullptr;
 }
 
-struct BlkSummary { uint32_t type, n_sym; uint64_t out_len; };
+// parity-debug trace buffer (deft4cu_debug_trace_*): while armed, phase A runs the blocks one after the other in
+// stream order on a single CTA, so that the log reads like the reference's sequential optimise loop
+static long long* g_trace_dev = nullptr;
+static uint32_t g_trace_dev_cap = 0;
+
+struct BlkSummary { uint32_t type, n_sym; uint64_t out_len; uint32_t alive, pad; };
 
 // Result buffers handed to the caller (deft4cu_result::out) live in pinned host blocks so that the device -> host
 // copy of a batch's output is one DMA at PCIe speed; blocks are reference counted by the `out` pointers that point
@@ -106,6 +111,16 @@ __global__ void k_blk_summary(const BlockRec* __restrict__ recs, BlkSummary* __r
     out[i].type = recs[i].type;
     out[i].n_sym = recs[i].n_sym;
     out[i].out_len = recs[i].out_len;
+    out[i].alive = 1; out[i].pad = 0;
+}
+// the same from the current model: a second optimise call on a batch sees merged / removed / stored blocks
+__global__ void k_state_summary(const BlkState* __restrict__ bs, BlkSummary* __restrict__ out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i].type = bs[i].cand.tab.type;
+    out[i].n_sym = bs[i].n_sym;
+    out[i].out_len = bs[i].out_len;
+    out[i].alive = bs[i].alive ? 1u : 0u; out[i].pad = 0;
 }
 
 class Batch {
@@ -151,6 +166,7 @@ class Batch {
     std::vector<uint32_t> crc, adler;
     bool have_sums = false;
     bool parsed = false;
+    bool optimised = false;
 
     ~Batch() { release_all(); if (own_cs) cudaStreamDestroy(own_cs); }
 
@@ -159,7 +175,7 @@ class Batch {
         dfree(d_sym, cs); dfree(d_symout, cs); dfree(d_out, cs);
         dfree(d_blk_stream, cs); dfree(d_bs, cs); dfree(d_logs, cs); dfree(d_maskpool, cs);
         dfree(d_sstate, cs); dfree(d_gerr, cs); dfree(d_dst, cs); dfree(d_dst_off, cs);
-        parsed = false; have_sums = false;
+        parsed = false; have_sums = false; optimised = false;
     }
     void release_all() {
         release_model();
@@ -174,7 +190,7 @@ class Batch {
         in_off.resize(n);
         uint64_t off = 0;
         for (uint32_t i = 0; i < n; i++) { in_off[i] = off; off += (in_len[i] + 32 + 15) & ~15ull; }
-        total_in = off + 64;
+        total_in = off + 512;   // k_find loads three 8-byte words per thread of its last tile (FIND_TILE / 8 + 24 bytes)
         D4_CUDA_CHECK(dalloc(&d_in, total_in, cs));
         D4_CUDA_CHECK(cudaMemsetAsync(d_in, 0, total_in, cs));
         for (uint32_t i = 0; i < n; i++)
@@ -422,10 +438,6 @@ class Batch {
             s.status = infos[i].status;
             s.n_blocks = infos[i].status == ST_OK ? infos[i].n_blocks : 0;
             s.cut = s.n_blocks;
-            for (uint32_t k = 0; k < s.n_blocks; k++) {
-                const BlkSummary& bsu = summ[s.blk_base + k];
-                if (bsu.out_len == 0 && !(k == 0 && s.n_blocks == 1)) { s.cut = k; break; }
-            }
             s.total_bits = infos[i].total_bits;
             size_bits_in[i] = (int64_t)infos[i].total_bits;
         }
@@ -497,6 +509,17 @@ class Batch {
         cudaEvent_t ev[3];
         for (auto& e : ev) cudaEventCreate(&e);
         const int merge = (flags & DEFT4CU_MERGE_BLOCKS) ? 1 : 0;
+        if (optimised && nblk_total) {
+            // DeflateStream.optimise may be called again on the same object (DeflateStream.java:496): the block list is
+            // the current model's (merged, removed and stored blocks), not the parsed one
+            BlkSummary* d_summ = nullptr;
+            D4_CUDA_CHECK(dalloc(&d_summ, nblk_total, cs));
+            LAUNCH(k_state_summary, (unsigned)((nblk_total + 255) / 256), 256, cs, d_bs, d_summ, nblk_total);
+            D4_CUDA_CHECK(cudaMemcpyAsync(summ.data(), d_summ, sizeof(BlkSummary) * nblk_total, cudaMemcpyDeviceToHost, cs));
+            D4_CUDA_CHECK(cudaStreamSynchronize(cs));
+            dfree(d_summ, cs);
+        }
+        optimised = true;
         std::vector<uint32_t> jobs;
         uint32_t maxsym = 1, maxstream = 1;
         uint64_t maxout = 1, maxstream_out = 1;
@@ -506,10 +529,19 @@ class Batch {
             s.saved_bits = 0;
             if (!s.selected) continue;
             uint64_t ssum = 0;
+            // blocks [0, cut) take part in phase A: the loop of DeflateStream.optimise ends at the first empty block it
+            // removes; a sole block is optimised even when empty (:510)
+            uint32_t n_alive = 0;
+            for (uint32_t k = 0; k < s.n_blocks; k++) n_alive += summ[s.blk_base + k].alive;
+            s.cut = s.n_blocks;
+            for (uint32_t k = 0; k < s.n_blocks; k++) {
+                const BlkSummary& b = summ[s.blk_base + k];
+                if (b.alive && b.out_len == 0 && n_alive != 1) { s.cut = k; break; }
+            }
             for (uint32_t k = 0; k < s.n_blocks; k++) {
                 const BlkSummary& b = summ[s.blk_base + k];
                 ssum += b.n_sym;
-                if (k < s.cut && b.type != 0) {
+                if (k < s.cut && b.type != 0 && b.alive) {
                     jobs.push_back((uint32_t)(s.blk_base + k));
                     maxsym = std::max(maxsym, b.n_sym);
                     maxout = std::max<uint64_t>(maxout, b.out_len);
@@ -518,7 +550,8 @@ class Batch {
             maxstream = (uint32_t)std::max<uint64_t>(maxstream, ssum);
             maxstream_out = std::max<uint64_t>(maxstream_out, infos[i].out_len);
         }
-        std::stable_sort(jobs.begin(), jobs.end(), [&](uint32_t a, uint32_t b) { return summ[a].n_sym > summ[b].n_sym; });
+        const bool tracing = g_trace_dev != nullptr;
+        if (!tracing) std::stable_sort(jobs.begin(), jobs.end(), [&](uint32_t a, uint32_t b) { return summ[a].n_sym > summ[b].n_sym; });
         D4_CUDA_CHECK(cudaMemcpyAsync(d_sstate, sstate.data(), sizeof(StreamState) * n, cudaMemcpyHostToDevice, cs));
         cudaEventRecord(ev[0], cs);
         if (!jobs.empty()) {
@@ -534,6 +567,7 @@ class Batch {
             if (perSM < 1) perSM = 1;
             if (const char* e = getenv("D4_CTAS_PER_SM")) perSM = std::max(1, std::min(perSM, atoi(e)));  // A/B knob
             unsigned grid = (unsigned)std::min<uint64_t>(jobs.size(), (uint64_t)g_sms * perSM);
+            if (tracing) grid = 1;
             EngScratch sc;
             sc.maxwords = (maxsym + 31) / 32 + 1;
             D4_CUDA_CHECK(alloc_scratch(sc, grid, maxout));
@@ -720,8 +754,6 @@ const char* deft4cu_last_error(void) { return g_err.c_str(); }
 const char* deft4cu_version(void) { return "deft4cu 0.1 (sm_100a)"; }
 
 // ---- parity-debug trace (engine.cuh g_trace) ---------------------------------------------------------------
-static long long* g_trace_dev = nullptr;
-static uint32_t g_trace_dev_cap = 0;
 int deft4cu_debug_trace_begin(uint32_t cap) {
     int rc = ensure_init();
     if (rc) return rc;
@@ -1005,8 +1037,11 @@ int deft4cu_optimise_deflate_stream(const uint8_t* in, uint64_t len, int merge_b
     *out = nullptr;
     *out_len = 0;
     deft4cu_result r;
+    memset(&r, 0, sizeof r);
+    r.status = DEFT4CU_ERR_PARSE;
     int rc = deft4cu_optimise_batch(&in, &len, 1, merge_blocks ? DEFT4CU_MERGE_BLOCKS : 0, &r);
-    if (rc == DEFT4CU_ERR_CUDA || rc == DEFT4CU_ERR_ARG) return rc;
+    // a parse failure or an unsupported stream keeps the caller's array (Deft.java:25-33); anything else is an error
+    if (rc != DEFT4CU_OK && rc != DEFT4CU_ERR_UNSUPPORTED && rc != DEFT4CU_ERR_PARSE) { host_release(r.out); return rc; }
     if (r.status == ST_OK && r.saved_bits > 0) { *out = r.out; *out_len = r.out_len; }
     else host_release(r.out);
     return DEFT4CU_OK;

@@ -186,7 +186,7 @@ k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __rest
 #ifdef D4_VERIFY
         e.vgerr = gerr; e.vjob = (int)job;
 #endif
-        eng_load(e, b, nullptr);
+        eng_load(e, b, maskpool + b.mask_off);   // zeros after parse; the current symbol list on a repeated optimise call
         RoundLog& lg = logs[jobs[job]];
         int r = 0;
         while (true) {
@@ -254,11 +254,21 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
         Tile& T = *reinterpret_cast<Tile*>(&S);
         __shared__ long long s_rpos, s_rsaved;
         __shared__ int s_stop;
-        if (tid == 0) { s_rpos = 0; s_rsaved = 0; s_stop = 0; }
+        __shared__ uint32_t s_first_alive, s_n_alive;
+        if (tid == 0) {
+            s_rpos = 0; s_rsaved = 0; s_stop = 0;
+            uint32_t fa = nb, na = 0;
+            for (uint32_t k = 0; k < nb; k++) if (B[k].alive) { if (fa == nb) fa = k; na++; }
+            s_first_alive = fa; s_n_alive = na;
+        }
         __syncthreads();
+        const uint32_t first_alive = s_first_alive, n_alive = s_n_alive;
         for (uint32_t t0 = 0; t0 < nb && !s_stop; t0 += RT) {
             const uint32_t cnt = nb - t0 < RT ? nb - t0 : RT;
-            for (uint32_t k = tid; k < cnt; k += ENG_NT) { T.out_len[k] = B[t0 + k].out_len; T.type[k] = B[t0 + k].cand.tab.type; }
+            for (uint32_t k = tid; k < cnt; k += ENG_NT) {
+                T.out_len[k] = B[t0 + k].out_len;
+                T.type[k] = B[t0 + k].alive ? (int)B[t0 + k].cand.tab.type : -1;   // -1: removed by an earlier optimise call
+            }
             for (uint32_t q = tid; q < cnt * RR; q += ENG_NT) T.rr[q / RR][q % RR] = logs[st.blk_base + t0 + q / RR].r[q % RR];
             __syncthreads();
             if (tid == 0) {
@@ -266,7 +276,8 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
                 for (uint32_t kk = 0; kk < cnt; kk++) {
                     const uint32_t k = t0 + kk;
                     const unsigned long long out_len = T.out_len[kk];
-                    if (out_len > 0 || (k == 0 && nb == 1)) {
+                    if (T.type[kk] < 0) continue;
+                    if (out_len > 0 || (k == first_alive && n_alive == 1)) {
                         if (T.type[kk] == 0) {  // stored blocks have no candidates
                             pos += 3;
                             pos += stored_size(out_len, pos);
@@ -301,6 +312,9 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
                     } else {  // empty block: removed, and the reference's loop ends here (H6)
                         saved += blk_size(B[k], pos + 3) + 3;
                         B[k].alive = 0;
+                        // its EOB (an empty Huffman block is one symbol) must not surface inside a later merge of its
+                        // neighbours, whose symbol range spans it (DeflateBlockHuffman.merge, :1233-1271)
+                        if (B[k].cand.tab.type != 0 && B[k].n_sym) sym[B[k].sym_off + B[k].n_sym - 1] = SYM_NOP;
                         s_stop = 1;
                         break;
                     }
@@ -370,13 +384,16 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
                 BlkState& c = B[cur];
                 BlkState& nx = B[s_next];
                 const uint32_t nA = c.n_sym, nB = nx.n_sym;
-                // merged symbol list = A without its EOB + B (DeflateBlockHuffman.merge, :1233-1271)
+                // merged symbol list = A without its EOB + B (DeflateBlockHuffman.merge, :1233-1271).  A removed empty
+                // Huffman block may sit between the two in the pool (its EOB is a NOP by now), so B's symbols start
+                // `gap` symbols after A's first one, not nA.
+                const uint32_t gap = (uint32_t)(nx.sym_off - c.sym_off), span = gap + nB;
                 if (tid == 0) sym[c.sym_off + nA - 1] = SYM_NOP;
                 e.v.sym = sym + c.sym_off;
                 e.v.symout = symout + c.sym_off;
                 e.v.out = out;
-                e.v.n = nA + nB;
-                e.v.nwords = (nA + nB + 31) / 32;
+                e.v.n = span;
+                e.v.nwords = (span + 31) / 32;
                 e.v.ulen = c.out_len + nx.out_len;
                 e.v.out_off = c.out_off;
                 e.begin_block();
@@ -388,7 +405,7 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
                 for (uint32_t i = tid; i < nA; i += ENG_NT)
                     if ((ma[i >> 5] >> (i & 31)) & 1) atomicOr(&m[i >> 5], 1u << (i & 31));
                 for (uint32_t i = tid; i < nB; i += ENG_NT)
-                    if ((mb[i >> 5] >> (i & 31)) & 1) atomicOr(&m[(nA + i) >> 5], 1u << ((nA + i) & 31));
+                    if ((mb[i >> 5] >> (i & 31)) & 1) atomicOr(&m[(gap + i) >> 5], 1u << ((gap + i) & 31));
                 if (tid == 0) { S.c[C_B].tab.type = 2; S.c[C_B].payload = 0; S.c[C_B].hdr.bits = 0; }
                 eng_adopt_mask0(e);
                 e.op_to_fixed(C_B);  // both halves recoded to the fixed code; payload from the histogram
@@ -414,7 +431,7 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
                     __syncthreads();
                     if (tid == 0) {
                         if (S.bestStored) c.cand.tab.type = 0;
-                        c.n_sym = nA + nB;
+                        c.n_sym = span;
                         c.out_len += nx.out_len;
                         nx.alive = 0;
                     }

@@ -122,14 +122,36 @@ def test_c2_text_stream(gpu, oracle, merge):
     assert compare_stream(gpu, oracle, raw, merge) > 0
 
 
+def _oracle_batch(streams, merge):
+    """The oracle on every host core (it is the checker here, never the path under test)."""
+    import multiprocessing as mp
+    from bench import _oracle_out
+    with mp.get_context("spawn").Pool(min(len(streams), os.cpu_count() or 1)) as pool:
+        return pool.map(_oracle_out, [(s, merge) for s in streams], chunksize=1)
+
+
+def _compare_batch(gpu, streams, merge):
+    """One device batch against the oracle, stream by stream: saved bits, output bytes, consumed bytes, checksums."""
+    res = gpu.optimise_batch(streams, merge)
+    ref = _oracle_batch(streams, merge)
+    for k, (raw, r, (saved, out, consumed, crc, adler, ulen)) in enumerate(zip(streams, res, ref)):
+        assert r["status"] == 0, k
+        assert (r["saved_bits"], r["consumed"]) == (saved, consumed), k
+        assert r["out"] == out, k
+        assert (r["crc32"], r["adler32"], r["uncompressed_len"]) == (crc, adler, ulen), k
+        assert zlib.decompress(r["out"], -15) == zlib.decompress(raw, -15), k
+
+
 def test_c3_png_idat_streams(gpu, oracle):
     for raw in W.c3_streams(3):
         compare_stream(gpu, oracle, raw, True, check_model=False)
+    _compare_batch(gpu, W.c3_streams(64, first=2000), True)
 
 
 def test_c4_entry_mix(gpu, oracle):
     for raw in W.c4_streams(12, seed=44):
         compare_stream(gpu, oracle, raw, True, check_model=False)
+    _compare_batch(gpu, W.c4_streams(128, seed=45), True)
 
 
 def test_c5_adversarial(gpu, oracle):
@@ -137,6 +159,135 @@ def test_c5_adversarial(gpu, oracle):
     assert len(streams) >= 10
     for raw in streams:
         compare_stream(gpu, oracle, raw, True, check_model=False)
+
+
+def test_c5_full_size_shapes(gpu, oracle):
+    """The 64 MiB long-match shapes of SURVEY.md 8(d) C5(i): len 258 / dist 1 and dist 32768.  The whole stream is
+    checked through inflate + device checksums + "no larger"; the first 1 MiB of text through the oracle."""
+    rng_period = __import__("numpy").random.default_rng(5).integers(0, 256, 32768, dtype="uint8").tobytes()
+    n = 64 << 20
+    for data in (b"\x41" * n, (rng_period * (n // 32768 + 1))[:n]):
+        for merge in (False, True):
+            raw = _deflate(data, 6, memlevel=9)
+            r = gpu.optimise_batch([raw], merge)[0]
+            assert r["status"] == 0 and r["consumed"] == len(raw)
+            assert len(r["out"]) <= len(raw) and r["size_bits_out"] == r["size_bits_in"] - r["saved_bits"]
+            assert (r["uncompressed_len"], r["crc32"], r["adler32"]) == (n, zlib.crc32(data) & 0xffffffff, zlib.adler32(data) & 0xffffffff)
+            assert zlib.decompress(r["out"], -15) == data
+        compare_stream(gpu, oracle, _deflate(data[:1 << 20], 6, memlevel=9), True, check_model=False)
+
+
+# ---- C2 at sizes the oracle needs minutes for: its outputs are committed as hashes (scripts/make_c2_golden.py) ---------
+@pytest.mark.parametrize("case", ["c2_4MiB_nomerge", "c2_8MiB_nomerge_seed2", "c2_640KiB_merge", "c2_640KiB_nomerge"])
+def test_c2_against_committed_oracle_hashes(gpu, case):
+    import hashlib, json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "c2_oracle_hashes.json")) as f:
+        g = json.load(f)[case]
+    raw = W._c2_stream(g["target_bytes"], g["seed"])
+    assert (len(raw), hashlib.sha256(raw).hexdigest()) == (g["in_len"], g["in_sha256"]), "generator drifted: regenerate the golden"
+    r = gpu.optimise_batch([raw], g["merge"])[0]
+    assert r["status"] == 0
+    assert r["saved_bits"] == g["saved_bits"]
+    assert (len(r["out"]), hashlib.sha256(r["out"]).hexdigest()) == (g["out_len"], g["out_sha256"])
+    assert zlib.decompress(r["out"], -15) == zlib.decompress(raw, -15)
+
+
+# ---- H10: code-length sets zlib rejects but the reference's first-match decoder accepts ----------------------------------
+@pytest.mark.parametrize("name", sorted(W.odd_code_streams()))
+@pytest.mark.parametrize("merge", [False, True])
+def test_odd_code_sets_follow_the_reference(gpu, oracle, name, merge):
+    """Incomplete and over-subscribed code-length sets decode exactly like Huffman.readSymbol (Huffman.java:170-197:
+    by length, first match wins, no validity check), and a block that keeps such a header is written back as is."""
+    raw = W.odd_code_streams()[name]
+    g, o = gpu.DeflateStream(), oracle.OracleDeflateStream()
+    assert o.parse(raw + b"xx") and g.parse(raw + b"xx")
+    assert g.consumed == o.consumed and g.getSizeBits() == o.getSizeBits()
+    assert g.getUncompressedData() == o.getUncompressedData()
+    assert_same_model(g, o)
+    assert g.optimise(merge) == o.optimise(merge)
+    assert g.asBytes() == o.asBytes()
+    assert_same_model(g, o)
+
+
+# ---- DeflateStream.optimise called again on the same object ------------------------------------------------------------
+@pytest.mark.parametrize("seq", [(False, True), (True, True), (False, False, True)])
+def test_repeated_optimise_calls(gpu, oracle, seq):
+    streams = [_deflate(W.c2_text(90_000, seed=31)), W.handmade_streams()["dyn_partialflush_x3"],
+               W.handmade_streams()["empty_blocks_midstream"], W.handmade_streams()["stored_around_65535"],
+               W.c4_streams(3, seed=12)[1]]
+    for raw in streams:
+        g, o = gpu.DeflateStream(), oracle.OracleDeflateStream()
+        assert g.parse(raw) and o.parse(raw)
+        for merge in seq:
+            assert g.optimise(merge) == o.optimise(merge)
+            assert g.asBytes() == o.asBytes()
+            assert g.getSizeBits() == o.getSizeBits()
+        assert_same_model(g, o)
+
+
+# ---- the tie-break contract, candidate by candidate ----------------------------------------------------------------------
+def _split_calls(pairs):
+    calls = []
+    for idx, sz in pairs:
+        if idx == -1:
+            calls.append([sz, {}])
+        else:
+            calls[-1][1][idx] = sz
+    return calls
+
+
+def test_candidate_trace_matches_oracle(gpu, oracle):
+    """Every candidate the selection callback of DeflateStream.optimiseBlock sees (DeflateStream.java:349-368), as
+    (enumeration index, size in bits), for every optimiseBlock call of the stream: the oracle's list and the CUDA
+    enumerator's must agree index by index (H7), including the index bookkeeping of the skipped
+    addOptimisedRecoded(prune) sweep, which logs nothing but advances the index."""
+    import ctypes as C
+    from deft4j_b200 import _native
+    from deft4j_b200.container import getContainerForBytes
+    CAP = 3_000_000
+    OL, GL = oracle.lib(), _native.lib()
+    OL.ora_trace_begin.argtypes = [C.POINTER(C.c_int64), C.c_size_t]
+    OL.ora_trace_end.restype = C.c_size_t
+    raws = []
+    for inp, take in (("asyoulik/asyoulik-gzip.txt.gz", 1), ("apng/ball.png", 3), ("text.png", 3)):
+        data = read_golden(inp)
+        co = getContainerForBytes(data, inp, oracle.OracleDeflateStream)
+        assert co.read(data)
+        raws += [s.asBytes() for s in co.getDeflateStreams()][:take]
+    raws += [_deflate(W.c2_text(5000, seed=3), 6, zlib.Z_FIXED), W.handmade_streams()["edge284"],
+             W.handmade_streams()["dyn_partialflush_dyn"]]
+    for k, raw in enumerate(raws):
+        o = oracle.OracleDeflateStream()
+        assert o.parse(raw)
+        buf = (C.c_int64 * (2 * CAP))()
+        OL.ora_trace_begin(buf, CAP)
+        so = o.optimise(False)
+        n = OL.ora_trace_end()
+        assert n < CAP
+        ref = _split_calls([(buf[2 * i], buf[2 * i + 1]) for i in range(n)])
+        g = gpu.DeflateStream()
+        assert g.parse(raw)
+        assert GL.deft4cu_debug_trace_begin(CAP) == 0
+        sg = g.optimise(False)
+        gbuf = (C.c_int64 * (2 * CAP))()
+        gn = C.c_uint32(0)
+        assert GL.deft4cu_debug_trace_end(gbuf, CAP, C.byref(gn)) == 0
+        assert gn.value < CAP
+        got = _split_calls([(gbuf[2 * i], gbuf[2 * i + 1]) for i in range(gn.value)])
+        assert sg == so
+        assert len(got) == len(ref), (k, len(got), len(ref))
+        for call, ((ri, rc), (gi, gc)) in enumerate(zip(ref, got)):
+            assert ri == gi, (k, call, "incumbent")
+            # the device logs every candidate except the skipped sweep's (whose indices it must still skip over)
+            assert gc, (k, call)
+            for idx, sz in gc.items():
+                assert rc.get(idx) == sz, (k, call, idx, rc.get(idx), sz)
+            assert max(gc) <= max(rc) and len(rc) - len(gc) <= 56 * 4 * 16, (k, call, len(rc), len(gc))
+            # the chosen candidate: first strict minimum over the oracle's full list is in the device's list too
+            best = min(rc.values())
+            first = min(i for i, v in rc.items() if v == best)
+            if best < ri:
+                assert gc.get(first) == best, (k, call, first)
 
 
 @pytest.mark.parametrize("name", sorted(W.handmade_streams()))

@@ -237,6 +237,71 @@ def stored_block(bw, data, final):
     bw.out += data
 
 
+def _canon_codes(lens):
+    """Huffman.buildCodes (base/huffman/Huffman.java:35-64): canonical codes, no validity check — an over-subscribed
+    length set yields codes that do not fit their length (they can never be matched by the first-match decoder)."""
+    count = [0] * 17
+    for l in lens:
+        count[l] += 1
+    count[0] = 0
+    code, nxt = 0, [0] * 17
+    for l in range(1, 17):
+        code = (code + count[l - 1]) << 1
+        nxt[l] = code
+    out = []
+    for l in lens:
+        out.append(nxt[l] if l else 0)
+        if l:
+            nxt[l] += 1
+    return out
+
+
+def dynamic_block(bw, litlen_lens, dist_lens, symbols, final):
+    """A dynamic block with an explicit (possibly incomplete or over-subscribed) pair of code-length sets.  The
+    header spells every length plainly (no 16/17/18 runs) with a flat 4-bit code over lengths 0..15."""
+    bw.bits(1 if final else 0, 1)
+    bw.bits(2, 2)
+    nl, nd = max(257, len(litlen_lens)), max(1, len(dist_lens))
+    L = list(litlen_lens) + [0] * (nl - len(litlen_lens))
+    D = list(dist_lens) + [0] * (nd - len(dist_lens))
+    bw.bits(nl - 257, 5); bw.bits(nd - 1, 5); bw.bits(19 - 4, 4)
+    order = [16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15]
+    for s in order:
+        bw.bits(4 if s < 16 else 0, 3)
+    for l in L + D:
+        bw.code(l, 4)
+    lc, dc = _canon_codes(L), _canon_codes(D)
+    for s in symbols + [256]:
+        if isinstance(s, int):
+            bw.code(lc[s], L[s])
+            continue
+        length, dist = s
+        i = 28 if length == 258 else max(k for k in range(28) if _LEN_BASE[k] <= length)
+        bw.code(lc[257 + i], L[257 + i]); bw.bits(length - _LEN_BASE[i], _LEN_EB[i])
+        d = max(k for k in range(30) if _DIST_BASE[k] <= dist)
+        bw.code(dc[d], D[d]); bw.bits(dist - _DIST_BASE[d], _DIST_EB[d])
+
+
+def odd_code_streams():
+    """Code-length sets zlib rejects but the reference's first-match decoder accepts: an incomplete
+    litlen code, an over-subscribed litlen code (the surplus code never matches), an over-subscribed distance code."""
+    out = {}
+    L = [0] * 257
+    L[65], L[66], L[256] = 1, 3, 2                      # Kraft 1/2 + 1/8 + 1/4 < 1
+    bw = BitWriter(); dynamic_block(bw, L, [0], [65, 66, 65, 65, 66] * 6, True); out["incomplete_litlen"] = bw.done()
+    L = [0] * 258
+    L[256], L[65], L[66], L[67], L[257] = 1, 2, 2, 2, 3  # Kraft 1/2 + 3/4 + 1/8 > 1: 67 and 257 get codes that never match
+    bw = BitWriter(); dynamic_block(bw, L, [0], [65, 66, 66, 65] * 9, True); out["oversubscribed_litlen"] = bw.done()
+    L = [0] * 258
+    L[65], L[66], L[256], L[257] = 2, 2, 2, 2
+    D = [1, 1, 1]                                        # three 1-bit distance codes: the third never matches
+    bw = BitWriter(); dynamic_block(bw, L, D, [65, 66, 65, (3, 1), (3, 2), 66, (3, 1)] * 5, True); out["oversubscribed_dist"] = bw.done()
+    bw = BitWriter()
+    fixed_block(bw, [72, 105] * 30, False); dynamic_block(bw, L, D, [65, (3, 2), 66] * 8, False); fixed_block(bw, [33] * 9, True)
+    out["odd_code_midstream"] = bw.done()
+    return out
+
+
 def handmade_streams():
     """Shapes outside zlib's repertoire: distance 32768 / length 258, the 284+31 edge case, empty blocks mid-stream
     (SURVEY.md H6), stored blocks around 65535 (H5/H12), a lone EOB."""
@@ -253,4 +318,15 @@ def handmade_streams():
     bw = BitWriter(); fixed_block(bw, [], True); out["lone_eob"] = bw.done()
     bw = BitWriter(); stored_block(bw, b"", True); out["empty_stored_only"] = bw.done()
     bw = BitWriter(); fixed_block(bw, [0] + [(258, 1)] * 300, False); fixed_block(bw, [(258, 1)] * 300 + [255], True); out["rle_two_fixed"] = bw.done()
+    # an empty FIXED block (what Z_PARTIAL_FLUSH emits) first in the list of empties, between two blocks the merge
+    # phase then joins: its EOB sits between their symbols in any pooled layout
+    words = [int(x) for x in rng.integers(97, 110, 400)]
+    bw = BitWriter(); fixed_block(bw, words[:200] + [(20, 150)] * 4, False); fixed_block(bw, [], False)
+    fixed_block(bw, words[200:] + [(9, 33)] * 6, True); out["fixed_emptyfixed_fixed"] = bw.done()
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
+    t = c2_text(24_000, seed=77)
+    out["dyn_partialflush_dyn"] = co.compress(t[:12_000]) + co.flush(zlib.Z_PARTIAL_FLUSH) + co.compress(t[12_000:]) + co.flush()
+    co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
+    out["dyn_partialflush_x3"] = (co.compress(t[:6_000]) + co.flush(zlib.Z_PARTIAL_FLUSH) + co.compress(t[6_000:12_000]) +
+                                   co.flush(zlib.Z_PARTIAL_FLUSH) + co.compress(t[12_000:]) + co.flush())
     return out
