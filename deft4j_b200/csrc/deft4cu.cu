@@ -464,44 +464,35 @@ class Batch {
         return DEFT4CU_OK;
     }
 
-    // per-CTA engine scratch (mask pool, interned tables, recode cache, pass memo values)
+    // per-CTA engine scratch: the pools of masks / tables / headers, cost arrays, per-symbol views (engine.cuh)
     cudaError_t alloc_scratch(EngScratch& sc, unsigned grid, uint64_t maxu) {
         cudaError_t e;
-        // literal-cost prefix sums need 4 bytes per decoded byte of the longest block per CTA: used when that fits 4 GiB
-        sc.P = nullptr;
-        sc.maxp = 0;
-        sc.prefix_ratio = 24;
-        if (const char* pr = getenv("D4_PREFIX_RATIO")) sc.prefix_ratio = (uint32_t)atoi(pr);
-        const uint64_t need = ((maxu + 64 + ENG_NT * 16 + 15) & ~15ull);
-        if (!getenv("D4_NO_PREFIX") && need < (1ull << 31) && need * 4 * grid <= (4ull << 30)) {
-            sc.maxp = (uint32_t)need;
-            if ((e = dalloc(&sc.P, (size_t)grid * need, cs)) != cudaSuccess) return e;
-        }
-        if ((e = dalloc(&sc.masks, (size_t)grid * (MAXM + NCAND) * sc.maxwords, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.tabs, (size_t)grid * MAXT, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.recode, (size_t)grid * MAXM, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.pvals, (size_t)grid * MEMO_P, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.g, (size_t)grid, cs)) != cudaSuccess) return e;
-        // cost arrays: as many per CTA as a 6 GiB budget allows (2 .. DCN_MAX)
         const size_t maxn = (size_t)sc.maxwords * 32;
-        sc.dcn = (int)std::max<size_t>(2, std::min<size_t>(DCN_MAX, (6ull << 30) / (2 * maxn * grid)));
-        if ((e = dalloc(&sc.dc, (size_t)grid * sc.dcn * maxn, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.hists, (size_t)grid * (MAXM + NCAND) * 320, cs)) != cudaSuccess) return e;
+        sc.maxtiles = (uint32_t)(maxu / DC_TILE + 4);
+        if ((e = dalloc(&sc.masks, (size_t)grid * (MAXM + 2) * sc.maxwords, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.tabs, (size_t)grid * (MAXT + ENG_NW), cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.hdrs, (size_t)grid * MAXH, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.hists, (size_t)grid * (MAXM + 2) * 320, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.tabHash, (size_t)grid * MAXT, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.dc, (size_t)grid * DCN * maxn, cs)) != cudaSuccess) return e;
         if ((e = dalloc(&sc.kind, (size_t)grid * maxn, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.meta, (size_t)grid * maxn, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.smctr, 256, cs)) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(sc.smctr, 0, 256 * sizeof(unsigned), cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.minfo, (size_t)grid * maxn, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.tileFirst, (size_t)grid * sc.maxtiles, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.trialAll, (size_t)grid * MAXT * 56, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.recs, (size_t)grid * 2, cs)) != cudaSuccess) return e;
+        if ((e = dalloc(&sc.slowWs, (size_t)grid * ENG_NW, cs)) != cudaSuccess) return e;
         if (getenv("D4_POISON")) {
-            cudaMemsetAsync(sc.masks, 0xFF, sizeof(uint32_t) * (size_t)grid * (MAXM + NCAND) * sc.maxwords, cs);
-            cudaMemsetAsync(sc.tabs, 0xFF, sizeof(Tab) * (size_t)grid * MAXT, cs);
-            cudaMemsetAsync(sc.recode, 0xFF, sizeof(Cand) * (size_t)grid * MAXM, cs);
-            cudaMemsetAsync(sc.pvals, 0xFF, sizeof(PVal) * (size_t)grid * MEMO_P, cs);
+            cudaMemsetAsync(sc.masks, 0xFF, sizeof(uint32_t) * (size_t)grid * (MAXM + 2) * sc.maxwords, cs);
+            cudaMemsetAsync(sc.tabs, 0xFF, sizeof(Tab) * (size_t)grid * (MAXT + ENG_NW), cs);
+            cudaMemsetAsync(sc.hdrs, 0xFF, sizeof(Hdr) * (size_t)grid * MAXH, cs);
+            cudaMemsetAsync(sc.dc, 0x7F, sizeof(short) * (size_t)grid * DCN * maxn, cs);
         }
         return cudaSuccess;
     }
     void free_scratch(EngScratch& sc) {
-        dfree(sc.masks, cs); dfree(sc.tabs, cs); dfree(sc.recode, cs); dfree(sc.pvals, cs); dfree(sc.g, cs);
-        dfree(sc.dc, cs); dfree(sc.hists, cs); dfree(sc.kind, cs); dfree(sc.meta, cs); dfree(sc.P, cs); dfree(sc.smctr, cs);
+        dfree(sc.masks, cs); dfree(sc.tabs, cs); dfree(sc.hdrs, cs); dfree(sc.hists, cs); dfree(sc.tabHash, cs);
+        dfree(sc.dc, cs); dfree(sc.kind, cs); dfree(sc.minfo, cs); dfree(sc.tileFirst, cs); dfree(sc.trialAll, cs);
+        dfree(sc.recs, cs); dfree(sc.slowWs, cs);
     }
 
     // ---- optimise: phase A over blocks, then per-stream replay/merge/layout ----------------------------
@@ -568,7 +559,7 @@ class Batch {
             if (const char* e = getenv("D4_CTAS_PER_SM")) perSM = std::max(1, std::min(perSM, atoi(e)));  // A/B knob
             unsigned grid = (unsigned)std::min<uint64_t>(jobs.size(), (uint64_t)g_sms * perSM);
             if (tracing) grid = 1;
-            EngScratch sc;
+            EngScratch sc{};
             sc.maxwords = (maxsym + 31) / 32 + 1;
             D4_CUDA_CHECK(alloc_scratch(sc, grid, maxout));
             LAUNCH(k_opt_blocks, grid, ENG_NT, cs, d_jobs, (uint32_t)jobs.size(), d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, d_counter, d_gerr);
@@ -604,7 +595,8 @@ class Batch {
         const int gerr = gerrv[0];
         if (gerr == 13 || gerr == 14) {
             char msg[256];
-            snprintf(msg, sizeof msg, gerr == 14 ? "engine verify: job %d opcode %d slot %d claims payload %d, true %d (cta %d candIndex %d of %zu)" : "engine self-check: block %d round %d winner idx %d claims payload %d, true %d (cta %d job %d of %zu)",
+            snprintf(msg, sizeof msg, "engine self-check: block %d round %d winner idx %d selected size %d, materialised size %d (check %d: 1 "
+                     "incumbent != previous winner, 2 payload, 3 size; previous %d; %zu jobs)",
                      gerrv[1], gerrv[2], gerrv[3], gerrv[4], gerrv[5], gerrv[6], gerrv[7], jobs.size());
             set_error(msg);
             return DEFT4CU_ERR_CUDA;
@@ -612,6 +604,7 @@ class Batch {
         if (gerr) {
             set_error(gerr == ERR_ROUNDS ? "optimiser hit an internal limit: more than 64 optimiseBlock rounds on one block"
                       : gerr == ERR_POOL ? "optimiser: internal table pool overflow"
+                      : gerr == ERR_INTERNAL ? "optimiser: enumerator/executor protocol error (internal)"
                                          : "optimiser: a Huffman tree could not be balanced (the reference throws here)");
             D4_CUDA_CHECK(cudaMemsetAsync(d_gerr, 0, sizeof(int), cs));
             for (uint32_t i = 0; i < n; i++) if (sstate[i].selected) sstate[i].status = ST_UNSUPPORTED;

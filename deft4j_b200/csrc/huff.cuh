@@ -186,6 +186,79 @@ D4_DEV int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, Tree
     return huff_tree_ws(freq, n, limit, lens, ws);
 }
 
+// ---- the litlen tree on the fast path ---------------------------------------------------------------------------------
+// HuffmanTree (huffman/HuffmanTree.java:36-73) with the PriorityQueue mechanics of huff_tree_ws, for the common case that
+// the tree needs no depth limiting: 32-bit heap keys (weight << 10 | node id), parent links only, depths by walking up.
+// Returns 0 and the code lengths, or 2 when the tree is deeper than `limit` (the caller then runs huff_tree_ws, whose
+// limiter needs the full node arrays).  freq[] is overwritten (parent[] lives in the same storage).
+D4_DEV_BIG int huff_tree_fast(uint32_t* freq, int n, int limit, uint8_t* lens, uint32_t* heap, uint16_t* value) {
+    uint16_t* parent = reinterpret_cast<uint16_t*>(freq);
+    int hs = 0;
+    auto add = [&](uint32_t x) {
+        int k = hs++;
+        while (k > 0) {
+            const int p = (k - 1) >> 1;
+            const uint32_t e = heap[p];
+            if ((x >> 10) >= (e >> 10)) break;
+            heap[k] = e;
+            k = p;
+        }
+        heap[k] = x;
+    };
+    auto poll = [&]() {
+        const uint32_t result = heap[0];
+        const int s = --hs;
+        const uint32_t x = heap[s];
+        if (s > 0) {
+            int k = 0;
+            const int half = s >> 1;
+            while (k < half) {
+                int child = 2 * k + 1;
+                uint32_t c = heap[child];
+                const int r = child + 1;
+                if (r < s) {
+                    const uint32_t cr = heap[r];
+                    if ((c >> 10) > (cr >> 10)) { c = cr; child = r; }
+                }
+                if ((x >> 10) <= (c >> 10)) break;
+                heap[k] = c;
+                k = child;
+            }
+            heap[k] = x;
+        }
+        return result;
+    };
+    int nleaf = 0;
+    for (int i = 0; i < n; i++) {
+        const uint32_t f = freq[i];
+        if (f > 0) { value[nleaf] = (uint16_t)i; add((f << 10) | (uint32_t)nleaf); nleaf++; }
+    }
+    int index = 0;
+    while (hs < 2) {  // dummy leaves (HuffmanTree.java:50-58)
+        if (index >= n || freq[index] == 0) { value[nleaf] = (uint16_t)index; add((1u << 10) | (uint32_t)nleaf); nleaf++; }
+        index++;
+    }
+    // from here on freq[] is dead and parent[] takes its storage
+    int nn = nleaf;
+    const int total = hs;
+    for (int i = 0; i < total - 1; i++) {
+        const uint32_t l = poll(), r = poll();
+        const int id = nn++;
+        parent[l & 1023u] = (uint16_t)id;
+        parent[r & 1023u] = (uint16_t)id;
+        add((((l >> 10) + (r >> 10)) << 10) | (uint32_t)id);
+    }
+    const int root = (int)(poll() & 1023u);
+    int maxDepth = 0;
+    for (int l = 0; l < nleaf; l++) {
+        int d = 0;
+        for (int node = l; node != root; node = parent[node]) d++;
+        if (d > maxDepth) maxDepth = d;
+        if (value[l] < n) lens[value[l]] = (uint8_t)d;
+    }
+    return maxDepth > limit ? 2 : 0;
+}
+
 using TreeWsCL = TreeWs<21, 46>;
 
 // ---- header model ---------------------------------------------------------------------------------

@@ -75,86 +75,16 @@ __global__ void k_init_state(const BlockRec* __restrict__ recs, const uint64_t* 
     b.size_bits = (long long)(r.end_bit - r.hdr_bit) - 3;
 }
 
-struct EngScratch {       // global scratch, one slice per CTA
-    uint32_t* masks;      // (MAXM + NCAND) * maxwords
-    Tab* tabs;            // MAXT
-    Cand* recode;         // MAXM
-    PVal* pvals;          // MEMO_P
-    EngG* g;              // 1
-    short* dc;            // dcn * maxwords * 32
-    uint32_t* hists;      // (MAXM + NCAND) * 320
-    uint8_t* kind;        // maxwords * 32
-    uint32_t* meta;       // maxwords * 32
-    uint32_t* P;          // maxp per CTA, or nullptr
-    uint32_t maxp;
-    uint32_t prefix_ratio;
-    uint32_t maxwords;
-    int dcn;
-    unsigned* smctr;      // 256 zeroed counters: CTAs landing on the same SM draw distinct leader-warp rotations
-};
-
-__device__ inline void eng_init(Eng& e, EngSmem* S, const EngScratch& sc, int cta) {
-    e.S = S;
-    // Serial sections (Huffman trees, header models) run in logical thread 0.  A warp's scheduler is fixed by
-    // (warp id % 4), so if every CTA of an SM used its physical warp 0 all serial code of the SM would queue on one
-    // scheduler while three idle: each CTA rotates its logical warps by a distinct amount instead.
-    __shared__ int s_rot;
-    if (threadIdx.x == 0) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        s_rot = (int)(atomicAdd(&sc.smctr[smid & 255u], 1u) & 3u);
-    }
-    __syncthreads();
-    e.tid = (int)((threadIdx.x + 32u * (unsigned)s_rot) & (ENG_NT - 1));
-    e.maxwords = sc.maxwords;
-    e.masks = sc.masks + (size_t)cta * (MAXM + NCAND) * sc.maxwords;
-    e.tabs = sc.tabs + (size_t)cta * MAXT;
-    e.recode = sc.recode + (size_t)cta * MAXM;
-    e.pvals = sc.pvals + (size_t)cta * MEMO_P;
-    e.G = sc.g + cta;
-    e.maxn = sc.maxwords * 32;
-    e.dcn = sc.dcn;
-    e.dc = sc.dc + (size_t)cta * sc.dcn * e.maxn;
-    e.hists = sc.hists + (size_t)cta * (MAXM + NCAND) * 320;
-    e.kind = sc.kind + (size_t)cta * e.maxn;
-    e.meta = sc.meta + (size_t)cta * e.maxn;
-    e.maxp = sc.maxp;
-    e.prefixRatio = sc.prefix_ratio;
-    e.P = sc.P ? sc.P + (size_t)cta * sc.maxp : nullptr;
-    if (threadIdx.x == 0) S->err = 0;
-    __syncthreads();
-}
-
-// the mask in pool slot 0 (written by the caller) becomes mask id 0 of a new block, held by C_B
-__device__ inline void eng_adopt_mask0(Eng& e) {
-    __syncthreads();
-    const unsigned long long h = e.hash_words(e.maskp(0), (int)e.v.nwords);
-    if (e.tid == 0) { e.G->maskHash[0] = h; e.S->recodeValid[0] = 0; e.S->nMasks = 1; e.S->c[C_B].mid = 0; }
-    for (uint32_t i = e.tid; i < e.v.n; i += ENG_NT) {
-        const uint32_t s = e.v.sym[i];
-        const bool mt = sym_is_match(s);
-        e.kind[i] = mt ? (uint8_t)(sym_lensym(s) - 256) : (uint8_t)0;
-        if (mt) {
-            const int ds = dist_sym(sym_dist(s));
-            e.meta[i] = (s & 0x1FF) | ((uint32_t)ds << 9) | ((uint32_t)(len_ebits_of(sym_lensym(s)) + dist_ebits_of(ds)) << 14);
-        }
-    }
-    __syncthreads();
-    e.pass_hist_full(0);
-    for (int k = e.tid; k < 320; k += ENG_NT) e.hists[k] = e.S->hist[k];
-    __syncthreads();
-}
-
-// load BlkState b into candidate slot C_B with the given mask source (pool words, or nullptr = zeros)
-__device__ inline void eng_load(Eng& e, const BlkState& b, const uint32_t* maskSrc) {
-    e.begin_block();
-    const uint32_t* s = (const uint32_t*)&b.cand;
-    uint32_t* d = (uint32_t*)&e.S->c[C_B];
-    for (int k = e.tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
-    uint32_t* m = e.maskp(0);
-    for (uint32_t k = e.tid; k < e.v.nwords; k += ENG_NT) m[k] = maskSrc ? maskSrc[k] : 0u;
-    eng_adopt_mask0(e);
-    e.intern_tab(C_B);
+// the view of block b for the engine
+__device__ inline void eng_view(Eng& e, const BlkState& b, const uint32_t* sym, const uint32_t* symout, const uint8_t* out,
+                                uint32_t n, uint64_t ulen) {
+    e.v.sym = sym + b.sym_off;
+    e.v.symout = symout + b.sym_off;
+    e.v.out = out;
+    e.v.n = n;
+    e.v.nwords = (n + 31) / 32;
+    e.v.ulen = ulen;
+    e.v.out_off = b.out_off;
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -175,58 +105,60 @@ k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __rest
         const uint32_t job = s_job;
         __syncthreads();
         if (job >= njobs) break;
+        P0();
         BlkState& b = bs[jobs[job]];
-        e.v.sym = sym + b.sym_off;
-        e.v.symout = symout + b.sym_off;
-        e.v.out = out;
-        e.v.n = b.n_sym;
-        e.v.nwords = (b.n_sym + 31) / 32;
-        e.v.ulen = b.out_len;
-        e.v.out_off = b.out_off;
-#ifdef D4_VERIFY
-        e.vgerr = gerr; e.vjob = (int)job;
-#endif
-        eng_load(e, b, maskpool + b.mask_off);   // zeros after parse; the current symbol list on a repeated optimise call
+        eng_view(e, b, sym, symout, out, b.n_sym, b.out_len);
+        e.load_block(b.cand, maskpool + b.mask_off, false);   // zeros after parse; the current symbol list on a repeated call
         RoundLog& lg = logs[jobs[job]];
         int r = 0;
+        long long prevBest = -1;
         while (true) {
             e.optimise_block(-1);
+            if (S.err) break;
             if (tid == 0 && r < MAXR) {
-                RoundRec rr; rr.sizeI = S.sizeI; rr.sizeC1 = S.sizeC1; rr.restMin = S.restMin; rr.best = S.bestSize;
+                RoundRec rr; rr.sizeI = S.en.sizeI; rr.sizeC1 = S.en.sizeC1; rr.restMin = S.en.restMin; rr.best = S.en.bestSize;
                 lg.r[r] = rr;
             }
-            const bool improved = S.bestSize < S.sizeI;
+            // self-checks: this round's incumbent is the previous round's winner; the winner's payload recomputed from
+            // its symbol list; a winning header trial sized exactly as the size-only evaluation said
+            const bool improved = S.en.bestSize < S.en.sizeI;
+            bool bad = prevBest >= 0 && S.en.sizeI != prevBest;
+            int badWhat = 1;
             __syncthreads();
-            if (improved && !S.bestStored) {  // self-check: the winner's payload recomputed from its symbol list
-                e.pass_hist_full(S.c[C_BEST].mid);
-                const long long truePay = e.hist_payload(S.c[C_BEST].tab);
-                if (truePay != S.c[C_BEST].payload && tid == 0) {
-                    if (atomicMax(gerr, 13) < 13) {
-                        gerr[1] = (int)jobs[job]; gerr[2] = r; gerr[3] = (int)S.bestIndex;
-                        gerr[4] = (int)S.c[C_BEST].payload; gerr[5] = (int)truePay; gerr[6] = (int)blockIdx.x; gerr[7] = (int)job;
-                    }
-                }
-                __syncthreads();
+            if (improved) {
+                e.pass_hist_full(SLOT_BEST);
+                const long long truePay = e.hist_payload(S.hist, e.recs[1].tab);
+                if (truePay != e.recs[1].payload) { bad = true; badWhat = 2; }
+                if (cand_size(e.recs[1]) != S.en.bestSize) { bad = true; badWhat = 3; }
             }
+            if (bad && tid == 0) {
+                if (atomicMax(gerr, 13) < 13) {
+                    gerr[1] = (int)jobs[job]; gerr[2] = r; gerr[3] = (int)S.en.bestIndex;
+                    gerr[4] = (int)S.en.bestSize; gerr[5] = (int)cand_size(e.recs[1]); gerr[6] = badWhat; gerr[7] = (int)prevBest;
+                }
+            }
+            __syncthreads();
+            prevBest = S.en.bestSize;
             r++;
             if (!improved) break;
             if (r >= MAXR) { if (tid == 0) S.err = ERR_ROUNDS; break; }
-            e.copy(C_B, C_BEST);
+            e.advance_to_best();
         }
         __syncthreads();
-        // write the fix-point back (C_B holds it: the last round did not improve)
-        {
-            const uint32_t* s = (const uint32_t*)&S.c[C_B];
+        // write the fix-point back: recs[0] / slot B hold it once a round has improved (the last round never does)
+        if (r > 1 && !S.err) {
+            const uint32_t* s = (const uint32_t*)&e.recs[0];
             uint32_t* d = (uint32_t*)&b.cand;
             for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
-            const uint32_t* m = e.maskp(S.c[C_B].mid);
+            const uint32_t* m = e.maskp(SLOT_B);
             uint32_t* pm = maskpool + b.mask_off;
             for (uint32_t k = tid; k < e.v.nwords; k += ENG_NT) pm[k] = m[k];
-            if (tid == 0) b.nrounds = r;
         }
+        if (tid == 0) b.nrounds = r;
         __syncthreads();
         if (S.err) { if (tid == 0) { atomicMax(gerr, S.err); S.err = 0; } }
         __syncthreads();
+        P1(PR_BLOCK);
     }
 }
 
@@ -389,48 +321,45 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
                 // `gap` symbols after A's first one, not nA.
                 const uint32_t gap = (uint32_t)(nx.sym_off - c.sym_off), span = gap + nB;
                 if (tid == 0) sym[c.sym_off + nA - 1] = SYM_NOP;
-                e.v.sym = sym + c.sym_off;
-                e.v.symout = symout + c.sym_off;
-                e.v.out = out;
-                e.v.n = span;
-                e.v.nwords = (span + 31) / 32;
-                e.v.ulen = c.out_len + nx.out_len;
-                e.v.out_off = c.out_off;
-                e.begin_block();
-                uint32_t* m = e.maskp(0);
-                for (uint32_t k = tid; k < e.v.nwords; k += ENG_NT) m[k] = 0;
-                __syncthreads();
-                const uint32_t* ma = maskpool + c.mask_off;
-                const uint32_t* mb = maskpool + nx.mask_off;
-                for (uint32_t i = tid; i < nA; i += ENG_NT)
-                    if ((ma[i >> 5] >> (i & 31)) & 1) atomicOr(&m[i >> 5], 1u << (i & 31));
-                for (uint32_t i = tid; i < nB; i += ENG_NT)
-                    if ((mb[i >> 5] >> (i & 31)) & 1) atomicOr(&m[(gap + i) >> 5], 1u << ((gap + i) & 31));
-                if (tid == 0) { S.c[C_B].tab.type = 2; S.c[C_B].payload = 0; S.c[C_B].hdr.bits = 0; }
-                eng_adopt_mask0(e);
-                e.op_to_fixed(C_B);  // both halves recoded to the fixed code; payload from the histogram
+                eng_view(e, c, sym, symout, out, span, c.out_len + nx.out_len);
+                // the merged mask is assembled in the pool region of A, which has room for the union (the regions of A, a
+                // removed block in between and B are adjacent); B's own region is left alone until the merge is accepted
+                {
+                    uint32_t* m = e.maskp(SLOT_BEST);   // scratch until the round materialises its winner
+                    for (uint32_t k = tid; k < e.v.nwords; k += ENG_NT) m[k] = 0;
+                    __syncthreads();
+                    const uint32_t* ma = maskpool + c.mask_off;
+                    const uint32_t* mb = maskpool + nx.mask_off;
+                    for (uint32_t i = tid; i < nA; i += ENG_NT)
+                        if ((ma[i >> 5] >> (i & 31)) & 1) atomicOr(&m[i >> 5], 1u << (i & 31));
+                    for (uint32_t i = tid; i < nB; i += ENG_NT)
+                        if ((mb[i >> 5] >> (i & 31)) & 1) atomicOr(&m[(gap + i) >> 5], 1u << ((gap + i) & 31));
+                    __syncthreads();
+                    // both halves recoded to the fixed code; payload from the histogram (DeflateBlockHuffman.merge)
+                    e.load_block(c.cand, m, true);
+                }
                 const long long pos = s_pos;
                 e.optimise_block(stored_size(e.v.ulen, pos));
                 if (tid == 0) {
                     long long curSize = blk_size(c, pos);
                     long long nextSize = blk_size(nx, pos + curSize + 3);
-                    long long cs = curSize + 3 + nextSize - S.bestSize;
+                    long long cs = curSize + 3 + nextSize - S.en.bestSize;
                     s_do = cs > 0 ? 5 : 6;
                     if (cs > 0) s_saved += cs;
                 }
                 __syncthreads();
                 if (s_do == 5) {  // accept
-                    if (!S.bestStored) {
-                        const uint32_t* s = (const uint32_t*)&S.c[C_BEST];
+                    if (!S.en.bestStored) {
+                        const uint32_t* s = (const uint32_t*)&e.recs[1];
                         uint32_t* d = (uint32_t*)&c.cand;
                         for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
-                        const uint32_t* bm = e.maskp(S.c[C_BEST].mid);
+                        const uint32_t* bm = e.maskp(SLOT_BEST);
                         uint32_t* pm = maskpool + c.mask_off;
                         for (uint32_t k = tid; k < e.v.nwords; k += ENG_NT) pm[k] = bm[k];
                     }
                     __syncthreads();
                     if (tid == 0) {
-                        if (S.bestStored) c.cand.tab.type = 0;
+                        if (S.en.bestStored) c.cand.tab.type = 0;
                         c.n_sym = span;
                         c.out_len += nx.out_len;
                         nx.alive = 0;

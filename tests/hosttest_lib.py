@@ -10,7 +10,7 @@ _lib = None
 
 
 def build():
-    srcs = [os.path.join(_SRC, f) for f in ("hosttest.cu", "huff.cuh", "common.cuh")]
+    srcs = [os.path.join(_SRC, f) for f in ("hosttest.cu", "huff.cuh", "common.cuh", "enum.cuh")]
     if (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs if os.path.exists(s)):
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         subprocess.check_call([nvcc, "-O2", "-std=c++17", "--shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
