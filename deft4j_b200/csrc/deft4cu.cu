@@ -464,36 +464,18 @@ class Batch {
         return DEFT4CU_OK;
     }
 
-    // per-CTA engine scratch: the pools of masks / tables / headers, cost arrays, per-symbol views (engine.cuh)
-    cudaError_t alloc_scratch(EngScratch& sc, unsigned grid, uint64_t maxu) {
-        cudaError_t e;
-        const size_t maxn = (size_t)sc.maxwords * 32;
-        sc.maxtiles = (uint32_t)(maxu / DC_TILE + 4);
-        if ((e = dalloc(&sc.masks, (size_t)grid * (MAXM + 2) * sc.maxwords, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.tabs, (size_t)grid * (MAXT + ENG_NW), cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.hdrs, (size_t)grid * MAXH, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.hists, (size_t)grid * (MAXM + 2) * 320, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.tabHash, (size_t)grid * MAXT, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.dc, (size_t)grid * DCN * maxn, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.kind, (size_t)grid * maxn, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.minfo, (size_t)grid * maxn, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.tileFirst, (size_t)grid * sc.maxtiles, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.trialAll, (size_t)grid * MAXT * 56, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.recs, (size_t)grid * 2, cs)) != cudaSuccess) return e;
-        if ((e = dalloc(&sc.slowWs, (size_t)grid * ENG_NW, cs)) != cudaSuccess) return e;
-        if (getenv("D4_POISON")) {
-            cudaMemsetAsync(sc.masks, 0xFF, sizeof(uint32_t) * (size_t)grid * (MAXM + 2) * sc.maxwords, cs);
-            cudaMemsetAsync(sc.tabs, 0xFF, sizeof(Tab) * (size_t)grid * (MAXT + ENG_NW), cs);
-            cudaMemsetAsync(sc.hdrs, 0xFF, sizeof(Hdr) * (size_t)grid * MAXH, cs);
-            cudaMemsetAsync(sc.dc, 0x7F, sizeof(short) * (size_t)grid * DCN * maxn, cs);
-        }
+    // per-CTA engine scratch: one contiguous, 2 MiB aligned slab per CTA (engine.cuh eng_scratch_layout)
+    unsigned char* scratch_raw = nullptr;
+    cudaError_t alloc_scratch(EngScratch& sc, unsigned grid, uint32_t maxwords, uint64_t maxu) {
+        const size_t stride = eng_scratch_layout(sc, maxwords, maxu);
+        const size_t align = (size_t)2 << 20;
+        cudaError_t e = dalloc(&scratch_raw, stride * grid + align, cs);
+        if (e != cudaSuccess) return e;
+        sc.slab = (unsigned char*)(((uintptr_t)scratch_raw + align - 1) & ~(uintptr_t)(align - 1));
+        if (getenv("D4_POISON")) cudaMemsetAsync(sc.slab, 0x7F, stride * grid, cs);
         return cudaSuccess;
     }
-    void free_scratch(EngScratch& sc) {
-        dfree(sc.masks, cs); dfree(sc.tabs, cs); dfree(sc.hdrs, cs); dfree(sc.hists, cs); dfree(sc.tabHash, cs);
-        dfree(sc.dc, cs); dfree(sc.kind, cs); dfree(sc.minfo, cs); dfree(sc.tileFirst, cs); dfree(sc.trialAll, cs);
-        dfree(sc.recs, cs); dfree(sc.slowWs, cs);
-    }
+    void free_scratch(EngScratch&) { dfree(scratch_raw, cs); }
 
     // ---- optimise: phase A over blocks, then per-stream replay/merge/layout ----------------------------
     int optimise(uint32_t flags, const std::vector<uint8_t>& selected) {
@@ -560,8 +542,7 @@ class Batch {
             unsigned grid = (unsigned)std::min<uint64_t>(jobs.size(), (uint64_t)g_sms * perSM);
             if (tracing) grid = 1;
             EngScratch sc{};
-            sc.maxwords = (maxsym + 31) / 32 + 1;
-            D4_CUDA_CHECK(alloc_scratch(sc, grid, maxout));
+            D4_CUDA_CHECK(alloc_scratch(sc, grid, (maxsym + 31) / 32 + 1, maxout));
             LAUNCH(k_opt_blocks, grid, ENG_NT, cs, d_jobs, (uint32_t)jobs.size(), d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, d_counter, d_gerr);
             free_scratch(sc);
             dfree(d_jobs, cs); dfree(d_counter, cs);
@@ -569,7 +550,6 @@ class Batch {
         cudaEventRecord(ev[1], cs);
         {
             EngScratch sc{};
-            sc.maxwords = (maxstream + 31) / 32 + 2;
             int perSM = 0;
             cudaFuncSetAttribute(k_finish, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             D4_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_finish, ENG_NT, 0));
@@ -578,7 +558,7 @@ class Batch {
             unsigned* d_counter = nullptr;
             D4_CUDA_CHECK(dalloc(&d_counter, 1, cs));
             D4_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, 4, cs));
-            if (merge) D4_CUDA_CHECK(alloc_scratch(sc, grid, maxstream_out));
+            if (merge) D4_CUDA_CHECK(alloc_scratch(sc, grid, (maxstream + 31) / 32 + 2, maxstream_out));
             if (n) LAUNCH(k_finish, grid, ENG_NT, cs, d_sstate, n, d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, merge, d_counter, d_gerr);
             if (merge) free_scratch(sc);
             dfree(d_counter, cs);

@@ -55,11 +55,12 @@ struct BlkView {
     uint64_t out_off; // pool offset of the block's first decoded byte
 };
 
-constexpr int DC_TILE = 2048;     // decoded bytes per cost-array tile (8 per thread)
+constexpr int DC_TILE = 512;      // decoded bytes per cost-array tile: one 16-byte load per lane of a warp
 constexpr int DCN = 8;            // cost arrays kept per block (round-robin eviction)
 constexpr int WS_BYTES = 3072;    // per-warp workspace for trees / header work
+constexpr int HQS = 4608, HQL = 1024;   // queue of freshly replaced matches (all / long ones) for the histogram update
 constexpr int SLOT_B = MAXM, SLOT_BEST = MAXM + 1;   // extra mask / histogram slots: the records of B and of the winner
-static_assert(DC_TILE == ENG_NT * 8, "one 8-byte load per thread and tile");
+static_assert(DC_TILE == 32 * 16 && DC_TILE > 258, "a tile is one warp-wide 128-bit load and no match spans more than two tiles");
 
 // cycle accounting per engine phase (-DD4_PROF builds only; read back with deft4cu_debug_prof): thread 0's clock64
 // deltas, [cat] = cycles, [32 + cat] = calls
@@ -74,53 +75,90 @@ __device__ unsigned long long g_prof[64];
 #define PCOUNT(cat, k)
 #endif
 enum { PR_BLOCK = 0, PR_ROUND, PR_SWEEP, PR_SELECT, PR_PASS, PR_DC, PR_RECODE, PR_TREES, PR_HDR_DEFAULT, PR_HDROP, PR_TRIALS,
-       PR_LOAD, PR_MATERIAL, PR_REBASE, PR_INTERN_MASK, PR_INTERN_TAB, PR_FIXED, PR_SLOWTREE, PR_SEGMENTED, PR_HIST };
+       PR_LOAD, PR_MATERIAL, PR_REBASE, PR_INTERN_MASK, PR_INTERN_TAB, PR_FIXED, PR_SLOWTREE, PR_SEGMENTED, PR_HIST,
+       PR_PASS_MAIN, PR_PASS_HQ, PR_LEAST_APPLY, PR_PASS_LEAST };
 
 struct EngSmem {
     SymState sym;
-    Enumer en;
+    Enumer en;            // the selection sweep (thread 0) and the first discovery sweeper
+    Enumer enx[3];        // the other discovery sweepers (one seed of the enumeration each)
     TraceSink tsink;
     unsigned long long maskHash[MAXM];
     uint32_t hist[320];          // pass histogram delta / block histogram; [0,19) header pair frequencies
     int leastSum[32], leastCnt[32];
     unsigned leastBlocked, leastSeen;
+    int leastRem[2], leastSize[2];   // the length symbol each mode removes and its cost sum
     unsigned long long red;
     unsigned long long hred[ENG_NW];
     long long recPay[ENG_NW];
     uint32_t wt[ENG_NW];
     int redAny, redAny2, tmpIdx, err;
-    int sweepDone, segImproved, segmentedRound;
-    int carryIdx[2], carryRef[2];   // cost-array build: the match that straddles a tile boundary (double buffered by tile parity)
-    uint32_t carryPart[2];
+    int sweepOk[4], segImproved, segmentedRound;
     unsigned char tabDc[MAXT];   // tabid -> cost-array slot (0xFF: none)
     unsigned short dcOwner[DCN]; // slot -> tabid (0xFFFF: free)
     int dcNext;
-    uint8_t ctab[256 + 32 + 32]; // cost-array build: literal lengths, length-symbol lengths, distance lengths
-    union {
+    uint32_t ctab[256];          // cost-array build: literal code lengths (0x10000 = no code: counted apart)
+    uint8_t refL[32], refD[32];  // cost of a match's length symbol / distance symbol incl. extra bits
+    union alignas(16) {
         unsigned char ws[ENG_NW][WS_BYTES];
-        uint32_t P[DC_TILE + 1]; // cost-array build: packed (cost | uncodable count << 16) exclusive prefix of one tile
+        uint32_t P[ENG_NW][DC_TILE + 4 + 36]; // cost-array build: per warp, packed (cost | uncodable count << 16) prefixes of one tile + lane bases
         struct { Hdr hdr; TreeWsCL ws; } mat;   // winner materialisation (thread 0)
+        struct { uint32_t nS, nL; uint32_t qs[HQS]; uint32_t ql[HQL]; } hq;   // passes: matches that were just replaced
     } u;
 };
 
-struct EngScratch {       // global scratch, one slice per CTA
-    uint32_t* masks;      // (MAXM + 2) * maxwords
-    Tab* tabs;            // MAXT + ENG_NW (staging)
-    Hdr* hdrs;            // MAXH
-    uint32_t* hists;      // (MAXM + 2) * 320
-    unsigned long long* tabHash;   // MAXT
-    short* dc;            // DCN * maxwords * 32
-    uint8_t* kind;        // maxwords * 32
-    uint32_t* minfo;      // maxwords * 32
-    uint32_t* tileFirst;  // maxtiles
-    int* trialAll;        // MAXT * 56
-    Cand* recs;           // 2: B and the winner
-    TreeWs<290, 584>* slowWs;   // ENG_NW
+// Global scratch: ONE contiguous slab per CTA (2 MiB aligned) holding all of its pools and views, so that a CTA's working
+// set sits in a handful of pages (twelve separate arrays indexed by CTA cost a TLB miss on almost every access).
+// The engine state of the CTA.  A file-scope __shared__ object (every kernel that uses the engine gets its own copy), so
+// that the compiler knows the address space of every access (LDS / STS / ATOMS instead of generic LD / ST / ATOM).
+__shared__ EngSmem g_es;
+#define ES (&g_es)
+
+struct EngScratch {
+    unsigned char* slab;
+    size_t stride;        // bytes per CTA
+    // byte offsets inside a CTA's slab
+    size_t oMasks;        // (MAXM + 2) * maxwords u32
+    size_t oTabs;         // MAXT + ENG_NW (staging) Tab
+    size_t oHdrs;         // MAXH Hdr
+    size_t oHists;        // (MAXM + 2) * 320 u32
+    size_t oTabHash;      // MAXT u64
+    size_t oDc;           // DCN * maxwords * 32 short
+    size_t oKind;         // maxwords * 32 u8
+    size_t oMinfo;        // maxwords * 32 u32
+    size_t oTileFirst;    // maxtiles u32
+    size_t oTrialAll;     // MAXT * 56 int
+    size_t oRecs;         // 2 Cand: B and the winner
+    size_t oSlowWs;       // ENG_NW TreeWs<290, 584>
     uint32_t maxwords, maxtiles;
 };
+// lays the slab out; returns the stride
+inline size_t eng_scratch_layout(EngScratch& sc, uint32_t maxwords, uint64_t maxu) {
+    sc.maxwords = maxwords;
+    sc.maxtiles = (uint32_t)(maxu / DC_TILE + 4);
+    const size_t maxn = (size_t)maxwords * 32;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
+    // the small, hot arrays first
+    sc.oRecs = take(2 * sizeof(Cand));
+    sc.oTabHash = take(sizeof(unsigned long long) * MAXT);
+    sc.oTabs = take(sizeof(Tab) * (MAXT + ENG_NW));
+    sc.oTileFirst = take(4 * (size_t)sc.maxtiles);
+    sc.oKind = take(maxn);
+    sc.oMinfo = take(4 * maxn);
+    sc.oDc = take(2 * maxn * DCN);
+    sc.oMasks = take(4 * (size_t)(MAXM + 2) * maxwords);
+    sc.oHists = take(4 * (size_t)(MAXM + 2) * 320);
+    sc.oHdrs = take(sizeof(Hdr) * MAXH);
+    sc.oTrialAll = take(4 * (size_t)MAXT * 56);
+    sc.oSlowWs = take(sizeof(TreeWs<290, 584>) * ENG_NW);
+    sc.stride = (o + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    return sc.stride;
+}
 
 struct Eng {
-    EngSmem* S;
+    // cost-array values that are not costs: a match with a byte that has no code, a symbol that is not a match
+    static constexpr short DC_BLOCKED = 0x7FFF, DC_NOT_MATCH = 0x7FFE;
     BlkView v;
     uint32_t* masks;
     uint32_t maxwords, maxn;
@@ -149,10 +187,10 @@ struct Eng {
             h += x;
         }
         for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
-        if ((tid & 31) == 0) S->hred[tid >> 5] = h;
+        if ((tid & 31) == 0) ES->hred[tid >> 5] = h;
         __syncthreads();
         unsigned long long r = 0;
-        for (int k = 0; k < ENG_NW; k++) r += S->hred[k];
+        for (int k = 0; k < ENG_NW; k++) r += ES->hred[k];
         __syncthreads();
         return r | 1ull;
     }
@@ -172,7 +210,7 @@ struct Eng {
     __device__ __noinline__ int intern_tab_warp(int st, int lane) {
         const uint32_t* q = (const uint32_t*)&tabs[MAXT + st];
         const unsigned long long h = hash_words_warp(q, (int)(sizeof(Tab) / 4), lane);
-        const int nT = S->sym.nTabs;
+        const int nT = ES->sym.nTabs;
         int hit = -1;
         for (int k0 = 0; k0 < nT && hit < 0; k0 += 32) {
             const int k = k0 + lane;
@@ -187,41 +225,69 @@ struct Eng {
             }
         }
         if (hit < 0) {
-            if (nT >= MAXT) { if (lane == 0) S->sym.overflow = 1; return 0; }
+            if (nT >= MAXT) { if (lane == 0) ES->sym.overflow = 1; return 0; }
             hit = nT;
             uint32_t* a = (uint32_t*)&tabs[hit];
             for (int w = lane; w < (int)(sizeof(Tab) / 4); w += 32) a[w] = q[w];
-            if (lane == 0) { tabHash[hit] = h; S->sym.trialState[hit] = ST_EMPTY; S->sym.nTabs = nT + 1; }
+            if (lane == 0) { tabHash[hit] = h; ES->sym.trialState[hit] = ST_EMPTY; ES->sym.nTabs = nT + 1; }
             __syncwarp();
         }
         return hit;
     }
 
-    // the mask just written into pool slot nMasks -> its id (an equal older mask wins, so equal symbol lists reached
-    // along different paths share their memo entries)
-    __device__ __noinline__ int intern_mask() {
+    // Mask hash = sum over the non-zero mask bytes of a mix of (byte, byte index): the passes accumulate it while they
+    // write the mask, so interning needs no extra walk.
+    static __device__ __forceinline__ unsigned long long mask_byte_hash(uint32_t byteval, uint32_t byteidx) {
+        if (!byteval) return 0ull;
+        unsigned long long x = (unsigned long long)byteval | ((unsigned long long)byteidx << 8);
+        x *= 0x9E3779B97F4A7C15ull; x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+        return x;
+    }
+    __device__ __noinline__ unsigned long long cta_sum64(unsigned long long h) {
+        for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+        __syncthreads();
+        if ((tid & 31) == 0) ES->hred[tid >> 5] = h;
+        __syncthreads();
+        unsigned long long r = 0;
+        for (int k = 0; k < ENG_NW; k++) r += ES->hred[k];
+        return r;
+    }
+    __device__ __noinline__ unsigned long long mask_hash_cta(const uint32_t* m) {
+        unsigned long long h = 0;
+        for (uint32_t k = tid; k < v.nwords; k += ENG_NT) {
+            const uint32_t w = m[k];
+            if (!w) continue;
+#pragma unroll
+            for (int q = 0; q < 4; q++) h += mask_byte_hash((w >> (8 * q)) & 0xffu, 4 * k + q);
+        }
+        return cta_sum64(h);
+    }
+
+    // the mask just written into pool slot nMasks (hash h) -> its id (an equal older mask wins, so equal symbol lists
+    // reached along different paths share their memo entries)
+    __device__ __noinline__ int intern_mask(unsigned long long h) {
         P0();
-        const int fresh = S->sym.nMasks;
+        const int fresh = ES->sym.nMasks;
         const uint32_t* q = maskp(fresh);
-        const unsigned long long h = hash_words(q, (int)v.nwords);
-        if (tid == 0) { S->tmpIdx = -1; S->redAny2 = 0; }
+        __syncthreads();
+        if (tid == 0) { ES->tmpIdx = -1; ES->redAny2 = 0; }
         __syncthreads();
         for (int k = tid; k < fresh; k += ENG_NT)
-            if (S->maskHash[k] == h) atomicMax(&S->tmpIdx, k);
+            if (ES->maskHash[k] == h) atomicMax(&ES->tmpIdx, k);
         __syncthreads();
-        int hit = S->tmpIdx;
+        int hit = ES->tmpIdx;
         if (hit >= 0) {
             const uint32_t* a = maskp(hit);
             bool diff = false;
             for (uint32_t k = tid; k < v.nwords; k += ENG_NT) diff |= a[k] != q[k];
-            if (diff) S->redAny2 = 1;
+            if (diff) ES->redAny2 = 1;
             __syncthreads();
-            if (S->redAny2) hit = -1;
+            if (ES->redAny2) hit = -1;
         }
         __syncthreads();
         if (hit < 0) {
             hit = fresh;
-            if (tid == 0) { S->maskHash[fresh] = h; S->sym.rc[fresh].state = ST_EMPTY; S->sym.nMasks = fresh + 1; }
+            if (tid == 0) { ES->maskHash[fresh] = h; ES->sym.rc[fresh].state = ST_EMPTY; ES->sym.nMasks = fresh + 1; }
         }
         __syncthreads();
         P1(PR_INTERN_MASK);
@@ -229,11 +295,12 @@ struct Eng {
     }
 
     // ---- block load -----------------------------------------------------------------------------------------------
-    // per-symbol views the passes read: kind (0 = not a match, else length symbol - 256) and, for matches,
-    // minfo = len-3 | dist symbol << 9 | extra bits << 14 | (start offset in its cost tile) << 19; tileFirst[t] = first
-    // symbol that starts in tile t.  Tiles count from the 8-byte boundary at or below the block's first decoded byte.
+    // per-symbol views the passes read: kind (0 = not a match, else length symbol - 256) and
+    // minfo = len-3 | dist symbol << 9 | kind << 14 | (start offset in its cost tile) << 19 (0 for non-matches);
+    // tileFirst[t] = first symbol that starts in tile t.  Tiles count from the 16-byte boundary at or below the block's
+    // first decoded byte.
     __device__ __noinline__ void build_views() {
-        const uint32_t a0 = (uint32_t)(v.out_off & ~7ull);
+        const uint32_t a0 = (uint32_t)(v.out_off & ~15ull);
         const uint32_t ntiles = (uint32_t)(((v.out_off - a0) + v.ulen) / DC_TILE) + 2;
         for (uint32_t t = tid; t < ntiles; t += ENG_NT) tileFirst[t] = v.n;
         __syncthreads();
@@ -241,37 +308,37 @@ struct Eng {
             const uint32_t s = v.sym[i];
             const uint32_t rel = v.symout[i] - a0;
             const bool mt = sym_is_match(s);
-            kind[i] = mt ? (uint8_t)(sym_lensym(s) - 256) : (uint8_t)0;
-            if (mt) {
-                const int ds = dist_sym(sym_dist(s));
-                minfo[i] = (s & 0x1FF) | ((uint32_t)ds << 9) | ((uint32_t)(len_ebits_of(sym_lensym(s)) + dist_ebits_of(ds)) << 14) |
-                           ((rel & (DC_TILE - 1)) << 19);
-            }
+            const uint32_t kq = mt ? (uint32_t)(sym_lensym(s) - 256) : 0u;
+            kind[i] = (uint8_t)kq;
+            minfo[i] = mt ? ((s & 0x1FF) | ((uint32_t)dist_sym(sym_dist(s)) << 9) | (kq << 14) | ((rel & (DC_TILE - 1)) << 19)) : 0u;
             const uint32_t ti = rel / DC_TILE;
-            const int tprev = i ? (int)((v.symout[i - 1] - a0) / DC_TILE) : -1;
+            const int tprev = i ? (int)((v.symout[i - 1] - a0) / DC_TILE) : -1;   // a symbol is shorter than a tile: ti - tprev <= 1
             if ((int)ti != tprev) tileFirst[ti] = i;
         }
-        for (uint32_t i = v.n + tid; i < v.nwords * 32; i += ENG_NT) kind[i] = 0;
+        for (uint32_t i = v.n + tid; i < v.nwords * 32; i += ENG_NT) {
+            kind[i] = 0; minfo[i] = 0;
+            for (int sl = 0; sl < DCN; sl++) dc[(size_t)sl * maxn + i] = DC_NOT_MATCH;   // the rows' tails never change
+        }
         __syncthreads();
     }
 
-    // histogram of the symbol list with mask `mid` into S->hist, from the symbols
+    // histogram of the symbol list with mask `mid` into ES->hist, from the symbols
     __device__ __noinline__ void pass_hist_full(int mid) {
         P0();
         const uint32_t* m = maskp(mid);
-        for (int k = tid; k < 320; k += ENG_NT) S->hist[k] = 0;
+        for (int k = tid; k < 320; k += ENG_NT) ES->hist[k] = 0;
         __syncthreads();
         for (uint32_t i = tid; i < v.n; i += ENG_NT) {
             uint32_t s = v.sym[i];
             if (!sym_is_match(s)) {
-                if (s <= 256) atomicAdd(&S->hist[s], 1u);
+                if (s <= 256) atomicAdd(&ES->hist[s], 1u);
             } else if (!((m[i >> 5] >> (i & 31)) & 1)) {
-                atomicAdd(&S->hist[sym_lensym(s)], 1u);
-                atomicAdd(&S->hist[288 + dist_sym(sym_dist(s))], 1u);
+                atomicAdd(&ES->hist[sym_lensym(s)], 1u);
+                atomicAdd(&ES->hist[288 + dist_sym(sym_dist(s))], 1u);
             } else {
                 const uint8_t* p = v.out + v.symout[i];
                 int len = sym_len(s);
-                for (int k = 0; k < len; k++) atomicAdd(&S->hist[p[k]], 1u);
+                for (int k = 0; k < len; k++) atomicAdd(&ES->hist[p[k]], 1u);
             }
         }
         __syncthreads();
@@ -292,12 +359,12 @@ struct Eng {
             else bits = 0;
             acc += (long long)f * bits;
         }
-        if (tid == 0) S->red = 0;
+        if (tid == 0) ES->red = 0;
         __syncthreads();
         for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-        if ((tid & 31) == 0 && acc) atomicAdd(&S->red, (unsigned long long)acc);
+        if ((tid & 31) == 0 && acc) atomicAdd(&ES->red, (unsigned long long)acc);
         __syncthreads();
-        const long long r = (long long)S->red;
+        const long long r = (long long)ES->red;
         __syncthreads();
         return r;
     }
@@ -305,17 +372,17 @@ struct Eng {
     // pools forgotten; tab 0 = the fixed code
     __device__ __noinline__ void reset_pools() {
         __syncthreads();
-        sym_reset(S->sym, tid, ENG_NT);
-        for (int k = tid; k < MAXT; k += ENG_NT) S->tabDc[k] = 0xFF;
-        if (tid < DCN) S->dcOwner[tid] = 0xFFFF;
-        if (tid == 0) S->dcNext = 0;
+        sym_reset(ES->sym, tid, ENG_NT);
+        for (int k = tid; k < MAXT; k += ENG_NT) ES->tabDc[k] = 0xFF;
+        if (tid < DCN) ES->dcOwner[tid] = 0xFFFF;
+        if (tid == 0) ES->dcNext = 0;
         Tab& f = tabs[TAB_FIXED];
         for (int k = tid; k < MAX_LL; k += ENG_NT) f.L[k] = (k < 286) ? ((k <= 143) ? 8 : (k <= 255) ? 9 : (k <= 279) ? 7 : 8) : 0;
         if (tid < MAX_D) f.D[tid] = tid < 30 ? 5 : 0;
         if (tid == 0) { f.nL = 286; f.nD = 30; f.type = 1; f.pad[0] = f.pad[1] = f.pad[2] = 0; }
         __syncthreads();
         const unsigned long long h = hash_words((const uint32_t*)&f, (int)(sizeof(Tab) / 4));
-        if (tid == 0) { tabHash[0] = h; S->sym.nTabs = 1; }
+        if (tid == 0) { tabHash[0] = h; ES->sym.nTabs = 1; }
         __syncthreads();
     }
 
@@ -330,8 +397,8 @@ struct Eng {
         uint32_t* h0 = histp(0);
         for (int k = tid; k < 320; k += ENG_NT) h0[k] = hs[k];
         __syncthreads();
-        const unsigned long long h = hash_words(m0, (int)v.nwords);
-        if (tid == 0) { S->maskHash[0] = h; S->sym.nMasks = 1; }
+        const unsigned long long h = mask_hash_cta(m0);
+        if (tid == 0) { ES->maskHash[0] = h; ES->sym.nMasks = 1; }
         const Cand& src = recs[0];
         SC b;
         b.mid = 0; b.ok = 1; b.hid = -1; b.tabid = TAB_FIXED; b.type = 1;
@@ -347,14 +414,14 @@ struct Eng {
             __syncthreads();
             if (tid < 32) {
                 const int t = intern_tab_warp(0, tid);
-                if (tid == 0) S->tmpIdx = t;
+                if (tid == 0) ES->tmpIdx = t;
             }
             __syncthreads();
-            b.tabid = (short)S->tmpIdx; b.type = 2; b.hid = 0;
-            if (tid == 0) { S->sym.hbits[0] = src.hdr.bits; S->sym.nHdrs = 1; }
+            b.tabid = (short)ES->tmpIdx; b.type = 2; b.hid = 0;
+            if (tid == 0) { ES->sym.hbits[0] = (unsigned short)src.hdr.bits; ES->sym.nHdrs = 1; }
         }
         b.payload = pay;
-        if (tid == 0) { S->en.B = b; S->en.blockType = b.type; }
+        if (tid == 0) { ES->en.B = b; ES->en.blockType = b.type; }
         __syncthreads();
     }
 
@@ -371,279 +438,482 @@ struct Eng {
         build_views();
         pass_hist_full(SLOT_B);
         uint32_t* hb = histp(SLOT_B);
-        for (int k = tid; k < 320; k += ENG_NT) hb[k] = S->hist[k];
+        for (int k = tid; k < 320; k += ENG_NT) hb[k] = ES->hist[k];
         __syncthreads();
         adopt_B(toFixed);
         if (tid == 0) {
-            S->en.S = &S->sym;
-            S->en.trialAll = trialAll;
-            S->tsink.buf = g_trace; S->tsink.cap = g_trace_cap; S->tsink.n = &g_trace_n;
-            S->en.trace = g_trace ? &S->tsink : nullptr;
-            S->en.storedOK = v.ulen <= 65535;
+            ES->en.trialAll = trialAll;
+            ES->tsink.buf = g_trace; ES->tsink.cap = g_trace_cap; ES->tsink.n = &g_trace_n;
+            ES->en.trace = g_trace ? &ES->tsink : nullptr;
+            ES->en.storedOK = v.ulen <= 65535;
         }
         __syncthreads();
         P1(PR_LOAD);
     }
 
     // ---- cost arrays ------------------------------------------------------------------------------------------------
-    static constexpr short DC_BLOCKED = 0x7FFF;
 
     // dc[i] = (literal cost of match i's bytes) - (cost of the match) under table `t`, DC_BLOCKED when a byte has no code
     // (DeflateBlockHuffman.java:238-246).  It does not depend on the mask, so every replace / least pass under the same
-    // tables reads it.  One coalesced pass over the decoded bytes, see the file header.
+    // tables reads it.  ONE coalesced pass over the block's decoded bytes: every warp streams its own run of 512-byte
+    // tiles (a 128-bit load per lane, code lengths looked up in shared memory, a warp-wide prefix sum into its slice of
+    // shared memory) and every match that starts in a tile takes P[end] - P[start]; the one match that crosses the
+    // tile's end is finished from the next tile.  No CTA barrier inside.
     __device__ __noinline__ const short* ensure_dc(int t) {
-        int slot = S->tabDc[t];
+        int slot = ES->tabDc[t];
         if (slot != 0xFF) return dc + (size_t)slot * maxn;
         P0();
         __syncthreads();  // every thread has seen the miss before thread 0 records the new slot
         if (tid == 0) {
-            slot = S->dcNext;
-            S->dcNext = (slot + 1) % DCN;
-            const int owner = S->dcOwner[slot];
-            if (owner != 0xFFFF) S->tabDc[owner] = 0xFF;
-            S->dcOwner[slot] = (unsigned short)t;
-            S->tabDc[t] = (unsigned char)slot;
-            S->tmpIdx = slot;
-            S->carryIdx[0] = S->carryIdx[1] = -1;
+            slot = ES->dcNext;
+            ES->dcNext = (slot + 1) % DCN;
+            const int owner = ES->dcOwner[slot];
+            if (owner != 0xFFFF) ES->tabDc[owner] = 0xFF;
+            ES->dcOwner[slot] = (unsigned short)t;
+            ES->tabDc[t] = (unsigned char)slot;
+            ES->tmpIdx = slot;
         }
         const Tab& tb = tabs[t];
-        for (int k = tid; k < 256 + 32 + 32; k += ENG_NT) S->ctab[k] = k < 256 ? tb.L[k] : k < 288 ? (k - 256 + 256 < MAX_LL ? tb.L[k] : 0) : tb.D[k - 288];
+        for (int k = tid; k < 256 + 32 + 32; k += ENG_NT) {
+            if (k < 256) { const uint32_t c = tb.L[k]; ES->ctab[k] = c ? c : 0x10000u; }
+            else if (k < 288) ES->refL[k - 256] = (uint8_t)(tb.L[k] + (k > 256 && k < 286 ? len_ebits_of(k) : 0));
+            else ES->refD[k - 288] = (uint8_t)(tb.D[k - 288] + (k - 288 < 30 ? dist_ebits_of(k - 288) : 0));
+        }
         __syncthreads();
-        slot = S->tmpIdx;
+        slot = ES->tmpIdx;
         short* d = dc + (size_t)slot * maxn;
-        const uint32_t a0 = (uint32_t)(v.out_off & ~7ull);
+        const uint32_t a0 = (uint32_t)(v.out_off & ~15ull);
         const uint32_t head = (uint32_t)(v.out_off - a0);
         const uint32_t endRel = head + (uint32_t)v.ulen;
         const uint8_t* base = v.out + a0;
         const int lane = tid & 31, wid = tid >> 5;
-        uint32_t* P = S->u.P;
+        uint32_t* P = ES->u.P[wid];
         const uint32_t ntiles = endRel / DC_TILE + 1;
-        for (uint32_t T = 0; T < ntiles; T++) {
-            const uint32_t idx = T * DC_TILE + 8u * (uint32_t)tid;
-            uint32_t x[8];
-            uint32_t tot = 0;
-            if (idx < endRel) {
-                const uint2 q = *(const uint2*)(base + idx);
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const uint32_t bt = ((k < 4 ? q.x : q.y) >> (8 * (k & 3))) & 0xffu;
-                    const uint32_t j = idx + k;
-                    const uint32_t c = S->ctab[bt];
-                    x[k] = (j >= head && j < endRel) ? (c ? c : 0x10000u) : 0u;
-                    tot += x[k];
+        const uint32_t per = (ntiles + ENG_NW - 1) / ENG_NW;
+        const uint32_t T0 = (uint32_t)wid * per, T1 = min(ntiles, T0 + per);
+        // Software pipeline, one tile deep: while tile T is processed, the bytes of T+1, the symbol range of T+2 and the
+        // first DC_PRE * 32 symbol records of T+1 are already in flight; the match that crosses from T into T+1 travels in
+        // lane 0's registers.  P[k] holds the prefix of byte k relative to its lane's first byte, LB[l] the prefix of lane
+        // l's first byte: the prefix at byte k is LB[k / 16] + P[k] (P[DC_TILE] = 0, LB[32] = tile total).
+        constexpr int DC_PRE = 4;
+        uint32_t* LB = P + DC_TILE + 4;
+        int carryIdx = -1, carryRef = 0;
+        uint32_t carryPart = 0, carryEnd = 0;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        uint32_t i0 = 0, i1 = 0, i2 = 0;       // symbols of the current tile: [i0, i1); of the next one: [i1, i2)
+        uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        if (T0 < T1) {
+            const uint32_t idx = T0 * DC_TILE + 16u * (uint32_t)lane;
+            if (idx < endRel) q = *(const uint4*)(base + idx);
+            i0 = tileFirst[T0]; i1 = tileFirst[T0 + 1];
+            i2 = (T0 + 1 < T1) ? tileFirst[T0 + 2] : i1;
+            const uint32_t i = i0 + (uint32_t)lane;
+            m0 = i < i1 ? minfo[i] : 0u; m1 = i + 32 < i1 ? minfo[i + 32] : 0u;
+            m2 = i + 64 < i1 ? minfo[i + 64] : 0u; m3 = i + 96 < i1 ? minfo[i + 96] : 0u;
+        }
+        if (lane == 0) P[DC_TILE] = 0;
+#define D4_PFX(k) (LB[(k) >> 4] + P[(k)])
+        // one symbol record: a match inside the tile gets its cost, the one that crosses the tile's end is remembered
+#define D4_DC_ONE(i_, m_, in_)                                                                                   \
+        do {                                                                                                     \
+            const uint32_t mm = (m_);                                                                            \
+            const int kq = (int)((mm >> 14) & 31);                                                               \
+            if (!kq) { if (in_) d[(i_)] = DC_NOT_MATCH; }                                                        \
+            else {                                                                                               \
+                const uint32_t s0 = (mm >> 19) & (DC_TILE - 1), e = s0 + (mm & 0x1FF) + 3;                       \
+                const int ref = ES->refL[kq] + ES->refD[(mm >> 9) & 31];                                         \
+                if (e <= DC_TILE) {                                                                              \
+                    const uint32_t y = D4_PFX(e) - D4_PFX(s0);                                                   \
+                    d[(i_)] = (y >> 16) ? DC_BLOCKED : (short)((int)(y & 0xffffu) - ref);                        \
+                } else { nIdx = (int)(i_); nRef = ref; nPart = LB[32] - D4_PFX(s0); nEnd = e - DC_TILE; }        \
+            }                                                                                                    \
+        } while (0)
+        // one tile past the warp's run finishes its last crossing match
+        for (uint32_t T = T0; T <= T1 && T <= ntiles; T++) {
+            const bool extra = T >= T1;
+            if (extra && __shfl_sync(0xffffffffu, carryIdx, 0) < 0) break;
+            const uint32_t idx = T * DC_TILE + 16u * (uint32_t)lane;
+            const uint4 cur = q;
+            const uint32_t ci0 = i0, ci1 = i1;
+            const uint32_t c0 = m0, c1 = m1, c2 = m2, c3 = m3;
+            if (T + 1 <= T1 && T + 1 <= ntiles) {   // next tile: its bytes, its first symbol records, the range after it
+                const uint32_t nidx = idx + DC_TILE;
+                q = (nidx < endRel) ? *(const uint4*)(base + nidx) : make_uint4(0, 0, 0, 0);
+                i0 = ci1; i1 = i2;
+                i2 = (T + 2 < T1) ? tileFirst[T + 3] : i1;
+                if (T + 1 < T1) {
+                    const uint32_t i = i0 + (uint32_t)lane;
+                    m0 = i < i1 ? minfo[i] : 0u; m1 = i + 32 < i1 ? minfo[i + 32] : 0u;
+                    m2 = i + 64 < i1 ? minfo[i + 64] : 0u; m3 = i + 96 < i1 ? minfo[i + 96] : 0u;
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; k++) x[k] = 0;
             }
-            uint32_t incl = tot;
+            // per-byte costs -> lane-relative exclusive prefixes straight into shared memory, 4 at a time
+            uint32_t run = 0;
+            const bool inside = T * DC_TILE >= head && (T + 1) * DC_TILE <= endRel;   // no per-byte bounds inside the block
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const uint32_t w = g == 0 ? cur.x : g == 1 ? cur.y : g == 2 ? cur.z : cur.w;
+                uint4 o;
+                uint32_t x0 = ES->ctab[w & 0xffu], x1 = ES->ctab[(w >> 8) & 0xffu], x2 = ES->ctab[(w >> 16) & 0xffu], x3 = ES->ctab[w >> 24];
+                if (!inside) {
+                    const uint32_t j = idx + 4 * g;
+                    if (!(j >= head && j < endRel)) x0 = 0;
+                    if (!(j + 1 >= head && j + 1 < endRel)) x1 = 0;
+                    if (!(j + 2 >= head && j + 2 < endRel)) x2 = 0;
+                    if (!(j + 3 >= head && j + 3 < endRel)) x3 = 0;
+                }
+                o.x = run; run += x0;
+                o.y = run; run += x1;
+                o.z = run; run += x2;
+                o.w = run; run += x3;
+                *(uint4*)(P + 16 * lane + 4 * g) = o;
+            }
+            uint32_t incl = run;
 #pragma unroll
             for (int dd = 1; dd < 32; dd <<= 1) {
                 const uint32_t y = __shfl_up_sync(0xffffffffu, incl, dd);
                 if (lane >= dd) incl += y;
             }
-            if (lane == 31) S->wt[wid] = incl;
-            __syncthreads();
-            uint32_t wbase = 0, total = 0;
-#pragma unroll
-            for (int k = 0; k < ENG_NW; k++) { const uint32_t y = S->wt[k]; if (k < wid) wbase += y; total += y; }
-            uint32_t run = wbase + incl - tot;
-#pragma unroll
-            for (int k = 0; k < 8; k++) { P[8 * tid + k] = run; run += x[k]; }
-            if (tid == ENG_NT - 1) P[DC_TILE] = total;
-            __syncthreads();
-            // the match that started in the previous tile and ends in this one
-            const int cp = (int)((T + 1) & 1), cq = (int)(T & 1);   // previous tile's carry slot, this tile's
-            if (tid == 0 && S->carryIdx[cp] >= 0) {
-                const int ci = S->carryIdx[cp];
-                const uint32_t mi = minfo[ci];
-                const uint32_t e = ((mi >> 19) & (DC_TILE - 1)) + (mi & 0x1FF) + 3 - DC_TILE;
-                const uint32_t y = S->carryPart[cp] + P[e];
-                d[ci] = (y >> 16) ? DC_BLOCKED : (short)((int)(y & 0xffffu) - S->carryRef[cp]);
-                S->carryIdx[cp] = -1;
+            LB[lane] = incl - run;
+            if (lane == 31) LB[32] = incl;
+            __syncwarp();
+            if (lane == 0 && carryIdx >= 0) {
+                const uint32_t y = carryPart + D4_PFX(carryEnd);
+                d[carryIdx] = (y >> 16) ? DC_BLOCKED : (short)((int)(y & 0xffffu) - carryRef);
+                carryIdx = -1;
             }
-            const uint32_t i0 = tileFirst[T], i1 = tileFirst[T + 1];
-            for (uint32_t i = i0 + tid; i < i1; i += ENG_NT) {
-                const int kq = kind[i];
-                if (!kq) continue;
-                const uint32_t mi = minfo[i];
-                const uint32_t s = (mi >> 19) & (DC_TILE - 1), e = s + (mi & 0x1FF) + 3;
-                const int ref = S->ctab[256 + kq] + S->ctab[288 + ((mi >> 9) & 31)] + (int)((mi >> 14) & 31);
-                if (e <= DC_TILE) {
-                    const uint32_t y = P[e] - P[s];
-                    d[i] = (y >> 16) ? DC_BLOCKED : (short)((int)(y & 0xffffu) - ref);
-                } else {   // at most one match per tile crosses its end
-                    S->carryIdx[cq] = (int)i; S->carryRef[cq] = ref; S->carryPart[cq] = P[DC_TILE] - P[s];
+            if (!extra) {
+                int nIdx = -1, nRef = 0;
+                uint32_t nPart = 0, nEnd = 0;
+                const uint32_t ib = ci0 + (uint32_t)lane;
+                D4_DC_ONE(ib, c0, ib < ci1);
+                D4_DC_ONE(ib + 32, c1, ib + 32 < ci1);
+                D4_DC_ONE(ib + 64, c2, ib + 64 < ci1);
+                D4_DC_ONE(ib + 96, c3, ib + 96 < ci1);
+                for (uint32_t i = ib + 32u * DC_PRE; i < ci1; i += 32) { const uint32_t mx = minfo[i]; D4_DC_ONE(i, mx, true); }   // many short symbols
+                // hand the crossing match (if any) to lane 0
+                const unsigned who = __ballot_sync(0xffffffffu, nIdx >= 0);
+                if (who) {
+                    const int src = __ffs((int)who) - 1;
+                    carryIdx = __shfl_sync(0xffffffffu, nIdx, src);
+                    carryRef = __shfl_sync(0xffffffffu, nRef, src);
+                    carryPart = __shfl_sync(0xffffffffu, nPart, src);
+                    carryEnd = __shfl_sync(0xffffffffu, nEnd, src);
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
+#undef D4_DC_ONE
+#undef D4_PFX
+        __syncthreads();
         P1(PR_DC);
         return d;
     }
 
-    // match i leaves the symbol list and its bytes enter it as literals: histogram delta in S->hist
+    // match i leaves the symbol list and its bytes enter it as literals: histogram delta in ES->hist
     __device__ __forceinline__ void hist_delta_replace(uint32_t i) {
         const uint32_t s = v.sym[i];
-        atomicSub(&S->hist[sym_lensym(s)], 1u);
-        atomicSub(&S->hist[288 + dist_sym(sym_dist(s))], 1u);
+        atomicSub(&ES->hist[sym_lensym(s)], 1u);
+        atomicSub(&ES->hist[288 + dist_sym(sym_dist(s))], 1u);
         const uint8_t* p = v.out + v.symout[i];
         const int len = sym_len(s);
-        for (int k = 0; k < len; k++) atomicAdd(&S->hist[p[k]], 1u);
+        for (int k = 0; k < len; k++) atomicAdd(&ES->hist[p[k]], 1u);
     }
-    // hists[dst] = hists[src] + S->hist (the delta of the matches that were just replaced)
+    // The same for every match a pass has just replaced, with the whole CTA: the pass queues the matches, then a thread
+    // per short match (its bytes loaded eight at a time) and a warp per long one apply the delta.
+    // all 32 lanes call this together with the matches (bits of `nbits`, symbols i0 ..) each of them replaced in this step:
+    // one shared-memory atomic per warp and step instead of one per match
+    __device__ __forceinline__ void hq_push_warp(uint32_t nbits, uint32_t i0, int lane) {
+        const uint32_t cnt = (uint32_t)__popc(nbits);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, dd); if (lane >= dd) incl += y; }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (!total) return;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ES->u.hq.nS, total);
+        base = __shfl_sync(0xffffffffu, base, 0) + incl - cnt;
+        for (uint32_t b = nbits; b; b &= b - 1, base++) {
+            const uint32_t i = i0 + (uint32_t)__ffs((int)b) - 1;
+            if (base < HQS) ES->u.hq.qs[base] = i; else hist_delta_replace(i);
+        }
+    }
+    __device__ __noinline__ void hq_apply() {
+        __syncthreads();
+        const uint32_t nS = min(ES->u.hq.nS, (uint32_t)HQS);
+        for (uint32_t j = tid; j < nS; j += ENG_NT) {
+            const uint32_t i = ES->u.hq.qs[j];
+            const uint32_t mi = minfo[i];
+            const uint32_t so = v.symout[i];
+            const int len = (int)(mi & 0x1FF) + 3;
+            atomicSub(&ES->hist[256 + ((mi >> 14) & 31)], 1u);
+            atomicSub(&ES->hist[288 + ((mi >> 9) & 31)], 1u);
+            if (len > 24) {
+                const uint32_t k = atomicAdd(&ES->u.hq.nL, 1u);
+                if (k < HQL) { ES->u.hq.ql[k] = i; continue; }
+            }
+            const uint8_t* p = v.out + so;
+            for (int k = 0; k < len; k += 8) {
+                uint32_t b[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) b[q] = (k + q < len) ? (uint32_t)p[k + q] : 256u;
+#pragma unroll
+                for (int q = 0; q < 8; q++) if (b[q] < 256u) atomicAdd(&ES->hist[b[q]], 1u);
+            }
+        }
+        __syncthreads();
+        const uint32_t nL = min(ES->u.hq.nL, (uint32_t)HQL);
+        const int lane = tid & 31;
+        for (uint32_t j = (uint32_t)(tid >> 5); j < nL; j += ENG_NW) {
+            const uint32_t i = ES->u.hq.ql[j];
+            const int len = (int)(minfo[i] & 0x1FF) + 3;
+            const uint8_t* p = v.out + v.symout[i];
+            for (int k = lane; k < len; k += 32) atomicAdd(&ES->hist[p[k]], 1u);
+        }
+        __syncthreads();
+    }
+    // hists[dst] = hists[src] + ES->hist (the delta of the matches that were just replaced)
     __device__ __forceinline__ void hist_store_delta(int dst, int src) {
         const uint32_t* hs = histp(src);
         uint32_t* hd = histp(dst);
-        for (int k = tid; k < 320; k += ENG_NT) hd[k] = hs[k] + S->hist[k];
+        for (int k = tid; k < 320; k += ENG_NT) hd[k] = hs[k] + ES->hist[k];
     }
 
-    // replaceBackrefsWithLiteralsIfSmaller(prune) for memo slot `slot` = (mid, tabid)
-    __device__ __noinline__ void pass_replace(int slot, int mid, int tabid, bool prune) {
-        if (S->sym.nMasks >= MAXM) { if (tid == 0) S->sym.overflow = 1; __syncthreads(); return; }
-        const short* d = ensure_dc(tabid);
-        for (int k = tid; k < 320; k += ENG_NT) S->hist[k] = 0;
-        if (tid == 0) { S->red = 0; S->redAny = 0; }
-        __syncthreads();
-        const uint32_t* m = maskp(mid);
-        const int fresh = S->sym.nMasks;
-        uint32_t* md = maskp(fresh);
-        long long saved = 0;
-        const int lane = tid & 31;
-        {   // 8 consecutive symbols (one mask byte) per thread; loads batched
-            const uint8_t* mb = (const uint8_t*)m;
-            uint8_t* mdb = (uint8_t*)md;
-            bool any = false;
-            for (uint32_t i0 = (uint32_t)tid * 8; i0 < v.nwords * 32; i0 += ENG_NT * 8) {
-                const uint2 kk = *(const uint2*)(kind + i0);
-                const uint4 dq = *(const uint4*)(d + i0);
-                const uint32_t ob = mb[i0 >> 3];
-                const uint32_t dw[4] = {dq.x, dq.y, dq.z, dq.w};
-                uint32_t nbits = 0;
+    // 16 cost-array entries (eight words) -> bit u set when entry u is negative (or, with `le`, not positive)
+    static __device__ __forceinline__ uint32_t neg_bits16(const uint32_t w[8], bool le) {
+        uint32_t r = 0;
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int k = (int)(((u < 4 ? kk.x : kk.y) >> (8 * (u & 3))) & 0xff);
-                    const int x = (int)(short)((u & 1) ? (dw[u >> 1] >> 16) : (dw[u >> 1] & 0xffff));
-                    if (k && !((ob >> u) & 1) && (prune ? x <= 0 : x < 0)) { saved -= x; nbits |= 1u << u; }
+        for (int q = 0; q < 8; q++) {
+            uint32_t sgn = w[q] & 0x80008000u;
+            if (le) sgn |= ~(((w[q] & 0x7FFF7FFFu) + 0x7FFF7FFFu) | w[q]) & 0x80008000u;   // halfwords equal to zero
+            r |= (((sgn >> 15) & 1u) | ((sgn >> 30) & 2u)) << (2 * q);
+        }
+        return r;
+    }
+    // new mask bytes (two per step) -> stored, and the mask hash moves by the bytes that changed
+    __device__ __forceinline__ unsigned long long store_mask16(uint8_t* mdb, uint32_t i0, uint32_t oldb, uint32_t nbits) {
+        const uint32_t nb = oldb | nbits;
+        *(uint16_t*)(mdb + (i0 >> 3)) = (uint16_t)nb;
+        unsigned long long h = 0;
+        if (nbits & 0xffu) h += mask_byte_hash(nb & 0xffu, i0 >> 3) - mask_byte_hash(oldb & 0xffu, i0 >> 3);
+        if (nbits >> 8) h += mask_byte_hash(nb >> 8, (i0 >> 3) + 1) - mask_byte_hash(oldb >> 8, (i0 >> 3) + 1);
+        return h;
+    }
+
+    // replaceBackrefsWithLiteralsIfSmaller(prune) for memo slot `slot` = (mid, tabid).  16 symbols per thread and step:
+    // candidates are the negative (prune: non-positive) cost-array entries that the mask does not cover yet - read off
+    // the sign bits of eight words; a symbol that is not a match or has an uncodable byte holds a large positive value.
+    __device__ __noinline__ void pass_replace(int slot, int mid, int tabid, bool prune) {
+        if (ES->sym.nMasks >= MAXM) { if (tid == 0) ES->sym.overflow = 1; __syncthreads(); return; }
+        const short* d = ensure_dc(tabid);
+        P0();
+        for (int k = tid; k < 320; k += ENG_NT) ES->hist[k] = 0;
+        if (tid == 0) { ES->red = 0; ES->redAny = 0; ES->u.hq.nS = 0; ES->u.hq.nL = 0; }
+        __syncthreads();
+        const int fresh = ES->sym.nMasks;
+        const uint8_t* mb = (const uint8_t*)maskp(mid);
+        uint8_t* mdb = (uint8_t*)maskp(fresh);
+        long long saved = 0;
+        unsigned long long hsh = 0;
+        const int lane = tid & 31;
+        {
+            const uint32_t end = v.nwords * 32;
+            uint32_t i0 = (uint32_t)tid * 16;
+            uint4 da = make_uint4(0, 0, 0, 0), db = da;
+            uint32_t ob = 0;
+            if (i0 < end) { da = *(const uint4*)(d + i0); db = *(const uint4*)(d + i0 + 8); ob = *(const uint16_t*)(mb + (i0 >> 3)); }
+            bool any = false;
+            while (i0 - (uint32_t)lane * 16 < end) {   // per warp: every lane stays in the loop for the warp-wide queue push
+                const bool act = i0 < end;
+                const uint32_t w[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+                const uint32_t cob = ob;
+                const uint32_t nx = i0 + ENG_NT * 16;
+                if (nx < end) { da = *(const uint4*)(d + nx); db = *(const uint4*)(d + nx + 8); ob = *(const uint16_t*)(mb + (nx >> 3)); }
+                uint32_t nbits = 0;
+                if (act) {
+                    nbits = neg_bits16(w, prune) & ~cob;
+                    if (nbits) {
+#pragma unroll
+                        for (int u = 0; u < 16; u++)
+                            if ((nbits >> u) & 1) saved -= (int)(short)((u & 1) ? (w[u >> 1] >> 16) : (w[u >> 1] & 0xffff));
+                    }
+                    hsh += store_mask16(mdb, i0, cob, nbits);
                 }
-                mdb[i0 >> 3] = (uint8_t)(ob | nbits);
-                for (uint32_t b = nbits; b; b &= b - 1) hist_delta_replace(i0 + (uint32_t)__ffs((int)b) - 1);
-                any |= nbits != 0;
+                if (__any_sync(0xffffffffu, nbits != 0)) { hq_push_warp(nbits, i0, lane); any |= nbits != 0; }
+                i0 = nx;
             }
-            if (any) S->redAny = 1;
+            if (any) ES->redAny = 1;
         }
         for (int dd = 16; dd > 0; dd >>= 1) saved += __shfl_xor_sync(0xffffffffu, saved, dd);
-        if (lane == 0 && saved) atomicAdd(&S->red, (unsigned long long)saved);
+        if (lane == 0 && saved) atomicAdd(&ES->red, (unsigned long long)saved);
+        const unsigned long long h = ES->maskHash[mid] + cta_sum64(hsh);   // (also the barrier after the loop)
         __syncthreads();
+        P1(PR_PASS_MAIN);
         int newmid = mid;
-        if (S->redAny) {
-            newmid = intern_mask();
+        if (ES->redAny) {
+            { P0(); hq_apply(); P1(PR_PASS_HQ); }
+            newmid = intern_mask(h);
             if (newmid == fresh) hist_store_delta(newmid, mid);
         }
         if (tid == 0) {
-            PSlot& p = S->sym.pm[slot];
-            p.mid = (unsigned short)newmid; p.delta = (long long)S->red; p.state = ST_DONE;
+            PSlot& p = ES->sym.pm[slot];
+            p.mid = (unsigned short)newmid; p.delta = (long long)ES->red; p.state = ST_DONE;
         }
         __syncthreads();
     }
 
-    // removeDistLitLeastExpensive(mode) for memo slot `slot`
-    __device__ __noinline__ void pass_least(int slot, int mid, int tabid, int mode) {
-        if (S->sym.nMasks >= MAXM) { if (tid == 0) S->sym.overflow = 1; __syncthreads(); return; }
+    // removeDistLitLeastExpensive (DeflateBlockHuffman.java:373-458) on (mid, tabid) for memo slot slot0 (mode 0: least
+    // cost sum) and / or slot1 (mode 1: least count); a slot < 0 is not wanted.  The statistics are the same for both
+    // modes, so a state that asks for both pays one pass over the symbols.
+    __device__ __noinline__ void pass_least(int slot0, int slot1, int mid, int tabid) {
+        if (ES->sym.nMasks + 2 > MAXM) { if (tid == 0) ES->sym.overflow = 1; __syncthreads(); return; }
         const short* d = ensure_dc(tabid);
-        if (tid < 32) { S->leastSum[tid] = 0; S->leastCnt[tid] = 0; }
-        if (tid == 0) { S->leastBlocked = 0; S->leastSeen = 0; }
-        for (int k = tid; k < 320; k += ENG_NT) S->hist[k] = 0;
+        P0();
+        if (tid < 32) { ES->leastSum[tid] = 0; ES->leastCnt[tid] = 0; }
+        if (tid == 0) { ES->leastBlocked = 0; ES->leastSeen = 0; }
         __syncthreads();
-        const uint32_t* m = maskp(mid);
         const int lane = tid & 31;
         // per length symbol: sum of (literal - match) cost, count, blocked (:386-420); lanes of a warp that hold the same
         // length symbol are summed with one shared-memory atomic
-        const uint8_t* mbytes = (const uint8_t*)m;
-        // the warp-wide votes below need every lane of a warp in the loop: the bound is per warp, loads are guarded
-        for (uint32_t wb = (uint32_t)(tid >> 5) * 256; wb < v.nwords * 32; wb += ENG_NT * 8) {
-            const uint32_t i0 = wb + (uint32_t)lane * 8;
-            const bool inr = i0 < v.nwords * 32;
-            const uint2 kk = inr ? *(const uint2*)(kind + i0) : make_uint2(0, 0);
-            const uint4 dq = inr ? *(const uint4*)(d + i0) : make_uint4(0, 0, 0, 0);
-            const uint32_t ob = inr ? mbytes[i0 >> 3] : 0u;
-            const uint32_t dw[4] = {dq.x, dq.y, dq.z, dq.w};
+        const uint8_t* mbytes = (const uint8_t*)maskp(mid);
+        const uint32_t end = v.nwords * 32;
+        {   // the warp-wide votes below need every lane of a warp in the loop: the bound is per warp, loads are guarded
+            uint32_t wb = (uint32_t)(tid >> 5) * 256;
+            uint2 kk = make_uint2(0, 0);
+            uint4 dq = make_uint4(0, 0, 0, 0);
+            uint32_t ob = 0;
+            { const uint32_t i0 = wb + (uint32_t)lane * 8; if (i0 < end) { kk = *(const uint2*)(kind + i0); dq = *(const uint4*)(d + i0); ob = mbytes[i0 >> 3]; } }
+            while (wb < end) {
+                const uint2 ckk = kk;
+                const uint4 cdq = dq;
+                const uint32_t cob = ob;
+                const uint32_t nwb = wb + ENG_NT * 8;
+                kk = make_uint2(0, 0); dq = make_uint4(0, 0, 0, 0); ob = 0;
+                { const uint32_t n0 = nwb + (uint32_t)lane * 8; if (n0 < end) { kk = *(const uint2*)(kind + n0); dq = *(const uint4*)(d + n0); ob = mbytes[n0 >> 3]; } }
+                const uint32_t dw[4] = {cdq.x, cdq.y, cdq.z, cdq.w};
+                // live matches of this lane, one bit per symbol
+                uint32_t liveBits = 0;
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int k = (int)(((u < 4 ? kk.x : kk.y) >> (8 * (u & 3))) & 0xff);
-                const bool live = k && !((ob >> u) & 1);
-                const int x = live ? (int)(short)((u & 1) ? (dw[u >> 1] >> 16) : (dw[u >> 1] & 0xffff)) : 0;
-                const bool blocked = live && x == DC_BLOCKED;
-                const int bin = live ? k - 1 : 31;
-                const unsigned grp = __match_any_sync(0xffffffffu, bin);
-                // one group reduction carries both the count (bits 24+) and the biased cost sum (x >= -64, 32 lanes)
-                const unsigned packed = __reduce_add_sync(grp, (live && !blocked) ? (1u << 24) + (unsigned)(x + 64) : 0u);
-                const int cn = (int)(packed >> 24);
-                const int xs = (int)(packed & 0xFFFFFFu) - 64 * cn;
-                const unsigned anyBlocked = __ballot_sync(0xffffffffu, blocked) & grp;
-                if (live && lane == __ffs(grp) - 1) {
-                    atomicOr(&S->leastSeen, 1u << bin);
-                    if (anyBlocked) atomicOr(&S->leastBlocked, 1u << bin);
-                    if (cn) { atomicAdd(&S->leastSum[bin], xs); atomicAdd(&S->leastCnt[bin], cn); }
+                for (int u = 0; u < 8; u++) liveBits |= ((((u < 4 ? ckk.x : ckk.y) >> (8 * (u & 3))) & 0xff) ? 1u : 0u) << u;
+                liveBits &= ~cob;
+                unsigned pending = __ballot_sync(0xffffffffu, liveBits != 0);
+                if (pending) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        if (!__any_sync(0xffffffffu, (liveBits >> u) & 1)) continue;
+                        const int k = (int)(((u < 4 ? ckk.x : ckk.y) >> (8 * (u & 3))) & 0xff);
+                        const bool live = (liveBits >> u) & 1;
+                        const int x = live ? (int)(short)((u & 1) ? (dw[u >> 1] >> 16) : (dw[u >> 1] & 0xffff)) : 0;
+                        const bool blocked = live && x == DC_BLOCKED;
+                        const int bin = live ? k - 1 : 31;
+                        const unsigned grp = __match_any_sync(0xffffffffu, bin);
+                        // one group reduction carries both the count (bits 24+) and the biased cost sum (x >= -64, 32 lanes)
+                        const unsigned packed = __reduce_add_sync(grp, (live && !blocked) ? (1u << 24) + (unsigned)(x + 64) : 0u);
+                        const int cn = (int)(packed >> 24);
+                        const int xs = (int)(packed & 0xFFFFFFu) - 64 * cn;
+                        const unsigned anyBlocked = __ballot_sync(0xffffffffu, blocked) & grp;
+                        if (live && lane == __ffs(grp) - 1) {
+                            atomicOr(&ES->leastSeen, 1u << bin);
+                            if (anyBlocked) atomicOr(&ES->leastBlocked, 1u << bin);
+                            if (cn) { atomicAdd(&ES->leastSum[bin], xs); atomicAdd(&ES->leastCnt[bin], cn); }
+                        }
+                    }
                 }
+                wb = nwb;
             }
         }
         __syncthreads();
         if (tid == 0) {
-            int rem = -1, remSize = 0, remFreq = 0;
-            for (int i = 0; i < 32; i++) {
-                if (!((S->leastBlocked >> i) & 1) && ((S->leastSeen >> i) & 1)) {
-                    bool doRem = mode == 1 ? S->leastCnt[i] < remFreq : S->leastSum[i] < remSize;
-                    if (rem == -1 || doRem) { rem = i; remSize = S->leastSum[i]; remFreq = S->leastCnt[i]; }
+            for (int mode = 0; mode < 2; mode++) {
+                int rem = -1, remSize = 0, remFreq = 0;
+                for (int i = 0; i < 32; i++) {
+                    if (!((ES->leastBlocked >> i) & 1) && ((ES->leastSeen >> i) & 1)) {
+                        bool doRem = mode == 1 ? ES->leastCnt[i] < remFreq : ES->leastSum[i] < remSize;
+                        if (rem == -1 || doRem) { rem = i; remSize = ES->leastSum[i]; remFreq = ES->leastCnt[i]; }
+                    }
                 }
+                ES->leastRem[mode] = rem; ES->leastSize[mode] = remSize;
             }
-            S->tmpIdx = rem;
-            S->red = (unsigned long long)(long long)remSize;
         }
         __syncthreads();
-        const int rem = S->tmpIdx;
-        int newmid = mid;
-        if (rem >= 0) {
-            const int fresh = S->sym.nMasks;
-            uint32_t* md = maskp(fresh);
-            uint8_t* mdb = (uint8_t*)md;
-            for (uint32_t i0 = (uint32_t)tid * 8; i0 < v.nwords * 32; i0 += ENG_NT * 8) {
-                const uint2 kk = *(const uint2*)(kind + i0);
-                const uint32_t ob = mbytes[i0 >> 3];
-                uint32_t nbits = 0;
+        P1(PR_PASS_LEAST);
+        int doneMid = -1, doneRem = -2;
+        for (int mode = 0; mode < 2; mode++) {
+            const int slot = mode ? slot1 : slot0;
+            if (slot < 0) continue;
+            const int rem = ES->leastRem[mode];
+            int newmid = mid;
+            if (rem >= 0 && rem == doneRem) newmid = doneMid;   // both modes remove the same length symbol
+            else if (rem >= 0) {
+                P0();
+                for (int k = tid; k < 320; k += ENG_NT) ES->hist[k] = 0;
+                if (tid == 0) { ES->u.hq.nS = 0; ES->u.hq.nL = 0; }
+                __syncthreads();
+                const int fresh = ES->sym.nMasks;
+                uint8_t* mdb = (uint8_t*)maskp(fresh);
+                unsigned long long hsh = 0;
+                const uint32_t pat = (uint32_t)(rem + 1) * 0x01010101u;
+                uint32_t i0 = (uint32_t)tid * 16;
+                uint4 kq = make_uint4(0, 0, 0, 0);
+                uint32_t ob = 0;
+                if (i0 < end) { kq = *(const uint4*)(kind + i0); ob = *(const uint16_t*)(mbytes + (i0 >> 3)); }
+                while (i0 - (uint32_t)lane * 16 < end) {
+                    const bool act = i0 < end;
+                    const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w};
+                    const uint32_t cob = ob;
+                    const uint32_t nx = i0 + ENG_NT * 16;
+                    if (nx < end) { kq = *(const uint4*)(kind + nx); ob = *(const uint16_t*)(mbytes + (nx >> 3)); }
+                    uint32_t nbits = 0;
+                    if (act) {
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int k = (int)(((u < 4 ? kk.x : kk.y) >> (8 * (u & 3))) & 0xff);
-                    if (k == rem + 1) nbits |= 1u << u;
+                        for (int q = 0; q < 4; q++) {   // bytes equal to the length symbol -> one bit each
+                            const uint32_t x = kw[q] ^ pat;
+                            const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+                            nbits |= (((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u)) << (4 * q);
+                        }
+                        nbits &= ~cob;
+                        hsh += store_mask16(mdb, i0, cob, nbits);
+                    }
+                    if (__any_sync(0xffffffffu, nbits != 0)) hq_push_warp(nbits, i0, lane);
+                    i0 = nx;
                 }
-                mdb[i0 >> 3] = (uint8_t)(ob | nbits);
-                for (uint32_t b = nbits & ~ob; b; b &= b - 1) hist_delta_replace(i0 + (uint32_t)__ffs((int)b) - 1);
+                const unsigned long long h = ES->maskHash[mid] + cta_sum64(hsh);
+                hq_apply();
+                newmid = intern_mask(h);
+                if (newmid == fresh) hist_store_delta(newmid, mid);
+                doneMid = newmid; doneRem = rem;
+                P1(PR_LEAST_APPLY);
+            }
+            if (tid == 0) {
+                PSlot& p = ES->sym.pm[slot];
+                p.mid = (unsigned short)newmid; p.delta = -(long long)ES->leastSize[mode]; p.state = ST_DONE;
             }
             __syncthreads();
-            newmid = intern_mask();
-            if (newmid == fresh) hist_store_delta(newmid, mid);
         }
-        if (tid == 0) {
-            PSlot& p = S->sym.pm[slot];
-            p.mid = (unsigned short)newmid; p.delta = -(long long)S->red; p.state = ST_DONE;
-        }
-        __syncthreads();
     }
 
     __device__ __noinline__ void exec_passes() {
-        const int nq = S->sym.nqPass;
+        const int nq = ES->sym.nqPass;
         if (!nq) return;
         P0();
         for (int q = 0; q < nq; q++) {
-            const int slot = S->sym.qPass[q];
-            const unsigned key = S->sym.pm[slot].key;
+            const int slot = ES->sym.qPass[q];
+            const unsigned key = ES->sym.pm[slot].key;
             const int mid = pm_key_mid(key), tabid = pm_key_tab(key), op = pm_key_op(key);
+            if (ES->sym.pm[slot].state == ST_DONE) continue;   // done together with its sibling (least passes)
             if (op == OP_FIXED) {   // recodeToFixedHuffman: the fixed-code payload is a function of the symbol list alone
                 const long long pay = hist_payload(histp(mid), tabs[TAB_FIXED]);
-                if (tid == 0) { PSlot& p = S->sym.pm[slot]; p.delta = pay; p.mid = (unsigned short)mid; p.state = ST_DONE; }
+                if (tid == 0) { PSlot& p = ES->sym.pm[slot]; p.delta = pay; p.mid = (unsigned short)mid; p.state = ST_DONE; }
                 __syncthreads();
             } else if (op <= OP_REPLACE_PRUNE) pass_replace(slot, mid, tabid, op == OP_REPLACE_PRUNE);
-            else pass_least(slot, mid, tabid, op - OP_LEAST0);
+            else {
+                // the other mode on the same state, when it is waiting too
+                const unsigned sib = pm_key(mid, tabid, op == OP_LEAST0 ? OP_LEAST1 : OP_LEAST0);
+                int other = -1;
+                for (int r = q + 1; r < nq; r++)
+                    if (ES->sym.pm[ES->sym.qPass[r]].key == sib && ES->sym.pm[ES->sym.qPass[r]].state != ST_DONE) { other = ES->sym.qPass[r]; break; }
+                pass_least(op == OP_LEAST0 ? slot : other, op == OP_LEAST0 ? other : slot, mid, tabid);
+            }
         }
         // a pass that could not run (mask pool full) leaves its slot pending: the round restarts after a reset
         PCOUNT(PR_PASS, nq - 1);
@@ -651,9 +921,8 @@ struct Eng {
     }
 
     // ---- recodeHuffman, one warp per request ------------------------------------------------------------------------
-    // runs of equal code lengths of a Tab, cut by one warp: ballot + popcount compaction
-    struct RunListW : RunList { uint16_t start[MAX_PAIRS]; };
-    static __device__ __forceinline__ void runlist_warp(const Tab& t, RunListW& rl, int lane) {
+    // runs of equal code lengths of a Tab, cut by one warp: ballot + popcount compaction (`start`: MAX_PAIRS scratch)
+    static __device__ __forceinline__ void runlist_warp(const Tab& t, RunList& rl, uint16_t* start, int lane) {
         const int nL = t.nL, n = t.nL + t.nD;
         int cnt = 0;
         for (int i0 = 0; i0 < n; i0 += 32) {
@@ -665,20 +934,22 @@ struct Eng {
             if (st) {
                 const int k = cnt + __popc(bal & ((1u << lane) - 1u));
                 rl.val[k] = (uint8_t)vv;
-                rl.start[k] = (uint16_t)i;
+                start[k] = (uint16_t)i;
             }
             cnt += __popc(bal);
         }
         __syncwarp();
-        for (int k = lane; k < cnt; k += 32) rl.len[k] = (uint16_t)((k + 1 < cnt ? rl.start[k + 1] : n) - rl.start[k]);
+        for (int k = lane; k < cnt; k += 32) rl.len[k] = (uint16_t)((k + 1 < cnt ? start[k + 1] : n) - start[k]);
         if (lane == 0) rl.n = (uint16_t)cnt;
         __syncwarp();
     }
 
     // header code of the pair frequencies f[0..19) (Huffman.ofRLEPacked), trimmed on from `ncl`, and the header size:
     // sum of pair bits = sum_s freq[s] * CL[s] + 2 f16 + 3 f17 + 7 f18.  One thread.
-    __device__ __forceinline__ void hdr_code_from_freq(const uint32_t* f, uint8_t* CL, int ncl, int* nclOut, int* bitsOut, TreeWsCLc& ws) {
-        if (huff_tree_ws(f, 19, 7, CL, ws)) S->err = ERR_TREE;
+    __device__ __noinline__ void hdr_code_from_freq(const uint32_t* f, uint8_t* CL, int ncl, int* nclOut, int* bitsOut, unsigned char* wsb) {
+        // fast path in 100 bytes, the full algorithm (compact workspace) behind it
+        TreeWsTiny ws{reinterpret_cast<uint16_t*>(wsb), wsb + 48, reinterpret_cast<TreeWsCLc*>(wsb + 104)};
+        if (huff_tree_ws(f, 19, 7, CL, ws)) ES->err = ERR_TREE;
         ncl = trim_ncl(CL, ncl);
         int bits = 5 + 5 + 4 + 3 * ncl + 2 * (int)f[16] + 3 * (int)f[17] + 7 * (int)f[18];
         for (int k = 0; k < 19; k++) bits += (int)f[k] * CL[k];
@@ -689,14 +960,15 @@ struct Eng {
     // rewriteHeader with the default strategy (DeflateBlockHuffman.java:480-577) for table `t` into header `h` (both
     // global), by one warp: runs -> pairs per run -> exclusive scan -> every run writes its pairs
     __device__ __noinline__ void hdr_default_warp(const Tab& t, Hdr& h, unsigned char* wsb, int lane) {
-        RunListW& rl = *reinterpret_cast<RunListW*>(wsb);
+        RunList& rl = *reinterpret_cast<RunList*>(wsb);
+        uint16_t* start = reinterpret_cast<uint16_t*>(wsb + 964);         // MAX_PAIRS
         uint16_t* off = reinterpret_cast<uint16_t*>(wsb + 1608);          // MAX_PAIRS + 2
         uint32_t* f19 = reinterpret_cast<uint32_t*>(wsb + 2256);          // 19 (+ CL staging)
         uint8_t* cl = wsb + 2336;                                          // 19
-        TreeWsCLc& tw = *reinterpret_cast<TreeWsCLc*>(wsb + 2368);
-        static_assert(sizeof(RunListW) <= 1608 && 2368 + sizeof(TreeWsCLc) <= WS_BYTES, "warp workspace layout");
+        unsigned char* tw = wsb + 2368;
+        static_assert(sizeof(RunList) <= 964 && 964 + 2 * MAX_PAIRS <= 1608 && 2368 + 104 + sizeof(TreeWsCLc) <= WS_BYTES, "warp workspace layout");
         if (lane < 19) f19[lane] = 0;
-        runlist_warp(t, rl, lane);
+        runlist_warp(t, rl, start, lane);
         const int R = rl.n;
         for (int r = lane; r < R; r += 32) {
             int cnt = 0;
@@ -734,7 +1006,7 @@ struct Eng {
     }
 
     __device__ __noinline__ void recode_one(int mid, int w, int lane, int hid) {
-        unsigned char* wsb = S->u.ws[w];
+        unsigned char* wsb = ES->u.ws[w];
         uint32_t* heap = reinterpret_cast<uint32_t*>(wsb);                 // 294 words (also the distance tree workspace)
         uint32_t* freq = reinterpret_cast<uint32_t*>(wsb + 1184);          // 320 words; the litlen tree's parent[] later
         uint16_t* value = reinterpret_cast<uint16_t*>(wsb + 2464);         // 292
@@ -745,6 +1017,9 @@ struct Eng {
         for (int k = lane; k < MAX_LL; k += 32) T.L[k] = 0;
         T.D[lane] = 0;
         __syncwarp();
+        P0();
+        uint32_t nr = 0;
+        int nl = 286;
         if (lane == 0) {
             // trailing zero-frequency trimming + the distance special cases (DeflateBlockHuffman.java:683-740)
             const uint32_t* df = freq + 288;
@@ -756,20 +1031,40 @@ struct Eng {
             else if (nz <= 1) { T.nD = (uint16_t)nd; T.D[nd - 1] = 1; }         // handleOne
             else {
                 T.nD = (uint16_t)nd;
-                if (huff_tree<32, 68>(df, nd, 15, T.D, *reinterpret_cast<TreeWs<32, 68>*>(wsb))) S->err = ERR_TREE;
+                int deepD = 16;
+                if (!bigWeights) {   // same fast path as the litlen tree (the distance counts die with it: parent[] overlays them)
+                    uint16_t* valD = reinterpret_cast<uint16_t*>(wsb + 512);
+                    const uint32_t nrD = huff_tree_fast_build(freq + 288, nd, heap, valD);
+                    deepD = huff_tree_fast_depths(reinterpret_cast<const uint16_t*>(freq + 288), valD, nd, nrD, T.D, 0, 1);
+                }
+                if (deepD > 15) {
+                    for (int k = 0; k < MAX_D; k++) T.D[k] = 0;
+                    if (huff_tree<32, 68>(hs + 288, nd, 15, T.D, *reinterpret_cast<TreeWs<32, 68>*>(wsb))) ES->err = ERR_TREE;
+                }
             }
-            int nl = 286;
             while (nl > 0 && freq[nl - 1] == 0) nl--;
             T.nL = (uint16_t)nl;
-            int rc = bigWeights ? 2 : huff_tree_fast(freq, nl, 15, T.L, heap, value);
-            if (rc == 2) {   // deeper than 15 (or weights too large for the fast keys): the full algorithm with its limiter
-                PCOUNT(PR_SLOWTREE, 1);
-                for (int k = 0; k < nl; k++) T.L[k] = 0;
-                if (huff_tree<290, 584>(hs, nl, 15, T.L, slowWs[w])) S->err = ERR_TREE;
-            }
             T.type = 2; T.pad[0] = T.pad[1] = T.pad[2] = 0;
+            if (!bigWeights) nr = huff_tree_fast_build(freq, nl, heap, value);
+        }
+        nr = __shfl_sync(0xffffffffu, nr, 0);
+        nl = __shfl_sync(0xffffffffu, nl, 0);
+        int deep = 16;
+        if (!bigWeights) {   // code lengths: every lane walks some leaves up to the root
+            deep = huff_tree_fast_depths(reinterpret_cast<const uint16_t*>(freq), value, nl, nr, T.L, lane, 32);
+            for (int dd = 16; dd > 0; dd >>= 1) deep = max(deep, __shfl_xor_sync(0xffffffffu, deep, dd));
+        }
+        if (deep > 15) {   // deeper than 15 (or weights too large for the fast keys): the full algorithm with its limiter
+            __syncwarp();
+            for (int k = lane; k < MAX_LL; k += 32) T.L[k] = 0;
+            __syncwarp();
+            if (lane == 0) {
+                PCOUNT(PR_SLOWTREE, 1);
+                if (huff_tree<290, 584>(hs, nl, 15, T.L, slowWs[w])) ES->err = ERR_TREE;
+            }
         }
         __syncwarp();
+        P1(PR_TREES);
         // payload = histogram . (code length + extra bits) (recodeToHuffmanInternal, :759-770)
         long long acc = 0;
         for (int k = lane; k < 318; k += 32) {
@@ -783,38 +1078,40 @@ struct Eng {
             acc += (long long)f * bits;
         }
         for (int dd = 16; dd > 0; dd >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, dd);
-        if (lane == 0) S->recPay[w] = acc;
+        if (lane == 0) ES->recPay[w] = acc;
+        const long long p1_ = clock64();
         hdr_default_warp(T, hdrs[hid], wsb, lane);
-        if (lane == 0) S->sym.hbits[hid] = hdrs[hid].bits;
+        { const long long p0_ = p1_; (void)p0_; P1(PR_HDR_DEFAULT); }
+        if (lane == 0) ES->sym.hbits[hid] = (unsigned short)hdrs[hid].bits;
         __syncwarp();
     }
 
     __device__ __noinline__ void exec_recodes() {
-        const int nq = S->sym.nqRec;
+        const int nq = ES->sym.nqRec;
         if (!nq) return;
         P0();
         const int w = tid >> 5, lane = tid & 31;
-        const int h0 = S->sym.nHdrs;
+        const int h0 = ES->sym.nHdrs;
         __syncthreads();
         for (int base = 0; base < nq; base += ENG_NW) {
             const int r = base + w;
             const bool mine = r < nq && h0 + r < MAXH;
-            if (mine) recode_one(S->sym.qRec[r], w, lane, h0 + r);
+            if (mine) recode_one(ES->sym.qRec[r], w, lane, h0 + r);
             __syncthreads();
             if (w == 0) {   // intern the staged tables one after the other (two requests may produce the same table)
                 for (int k = 0; k < ENG_NW && base + k < nq; k++) {
-                    if (h0 + base + k >= MAXH) { if (lane == 0) S->sym.overflow = 1; continue; }
+                    if (h0 + base + k >= MAXH) { if (lane == 0) ES->sym.overflow = 1; continue; }
                     const int t = intern_tab_warp(k, lane);
-                    if (lane == 0 && !S->sym.overflow) {
-                        RSlot& rs = S->sym.rc[S->sym.qRec[base + k]];
-                        rs.tabid = (unsigned short)t; rs.hid = (unsigned short)(h0 + base + k); rs.payload = S->recPay[k]; rs.state = ST_DONE;
+                    if (lane == 0 && !ES->sym.overflow) {
+                        RSlot& rs = ES->sym.rc[ES->sym.qRec[base + k]];
+                        rs.tabid = (unsigned short)t; rs.hid = (unsigned short)(h0 + base + k); rs.payload = ES->recPay[k]; rs.state = ST_DONE;
                     }
                     __syncwarp();
                 }
             }
             __syncthreads();
         }
-        if (tid == 0) S->sym.nHdrs = min(MAXH, h0 + nq);
+        if (tid == 0) ES->sym.nHdrs = min(MAXH, h0 + nq);
         __syncthreads();
         PCOUNT(PR_RECODE, nq - 1);
         P1(PR_RECODE);
@@ -854,13 +1151,13 @@ struct Eng {
     }
 
     __device__ __noinline__ void hdrop_one(int src, int op, int dst, int w, int lane) {
-        unsigned char* wsb = S->u.ws[w];
+        unsigned char* wsb = ES->u.ws[w];
         uint16_t* in = reinterpret_cast<uint16_t*>(wsb);                  // 320
         uint16_t* out = reinterpret_cast<uint16_t*>(wsb + 640);           // 320
         uint32_t* f19 = reinterpret_cast<uint32_t*>(wsb + 1280);          // 19
         uint8_t* cl = wsb + 1360;                                          // 19 old
         uint8_t* cl2 = wsb + 1392;                                         // 19 new
-        TreeWsCLc& tw = *reinterpret_cast<TreeWsCLc*>(wsb + 1424);
+        unsigned char* tw = wsb + 1424;
         const Hdr& hs = hdrs[src];
         Hdr& hd = hdrs[dst];
         const int np = hs.np;
@@ -894,58 +1191,69 @@ struct Eng {
         __syncwarp();
         for (int k = lane; k < npo; k += 32) hd.pairs[k] = pairs[k];
         if (lane < 19) hd.CL[lane] = cl2[lane];
-        if (lane == 0) { hd.np = (uint16_t)npo; hd.ncl = (uint8_t)ncl; hd.bits = bits; S->sym.hbits[dst] = bits; }
+        if (lane == 0) { hd.np = (uint16_t)npo; hd.ncl = (uint8_t)ncl; hd.bits = bits; ES->sym.hbits[dst] = (unsigned short)bits; }
         __syncwarp();
     }
 
     __device__ __noinline__ void exec_hdrops() {
-        const int nq = S->sym.nqHdr;
+        const int nq = ES->sym.nqHdr;
         if (!nq) return;
         P0();
         const int w = tid >> 5, lane = tid & 31;
-        const int h0 = S->sym.nHdrs;
+        const int h0 = ES->sym.nHdrs;
         __syncthreads();
         for (int r = w; r < nq; r += ENG_NW) {
-            const int src = S->sym.qHdr[r] >> 2, op = S->sym.qHdr[r] & 3;
-            if (h0 + r >= MAXH) { if (lane == 0) S->sym.overflow = 1; continue; }
+            const int src = ES->sym.qHdr[r] >> 2, op = ES->sym.qHdr[r] & 3;
+            if (h0 + r >= MAXH) { if (lane == 0) ES->sym.overflow = 1; continue; }
             hdrop_one(src, op, h0 + r, w, lane);
-            if (lane == 0) S->sym.hop[src][op] = (unsigned short)(h0 + r + 1);
+            if (lane == 0) ES->sym.hop[src][op] = (unsigned short)(h0 + r + 1);
         }
         __syncthreads();
-        if (tid == 0) S->sym.nHdrs = min(MAXH, h0 + nq);
+        if (tid == 0) ES->sym.nHdrs = min(MAXH, h0 + nq);
         __syncthreads();
         PCOUNT(PR_HDROP, nq - 1);
         P1(PR_HDROP);
     }
 
     // ---- the 56 header strategy trials of the queued tables ----------------------------------------------------------
+    // TRIAL_GROUP tables at a time: a warp cuts each table into runs (shared memory), then 28 threads per table evaluate
+    // one rewrite strategy each for both prune values; the two header-code trees of a thread run in its own 100 bytes of
+    // shared memory (huff_tree_tiny; the full algorithm in local memory only when a tree is deeper than 7)
+    static constexpr int TRIAL_GROUP = (ENG_NT / 28) < 6 ? (ENG_NT / 28) : 6;
+    static constexpr int TRIAL_RL = 964, TRIAL_WS0 = ((TRIAL_GROUP * TRIAL_RL + 127) / 128) * 128;
+    static_assert(TRIAL_WS0 + TRIAL_GROUP * 28 * TINY_WS_BYTES <= ENG_NW * WS_BYTES && TRIAL_WS0 + TRIAL_GROUP * 640 <= ENG_NW * WS_BYTES,
+                  "trial workspaces fit the shared union");
     __device__ __noinline__ void exec_trials() {
-        const int nq = S->sym.nqTrial;
+        const int nq = ES->sym.nqTrial;
         if (!nq) return;
         P0();
         const int w = tid >> 5, lane = tid & 31;
-        constexpr int GROUP = (ENG_NT / 28) < ENG_NW ? (ENG_NT / 28) : ENG_NW;
-        for (int base = 0; base < nq; base += GROUP) {
-            const int cnt = nq - base < GROUP ? nq - base : GROUP;
-            if (w < cnt) runlist_warp(tabs[S->sym.qTrial[base + w]], *reinterpret_cast<RunListW*>(S->u.ws[w]), lane);
+        unsigned char* ub = &ES->u.ws[0][0];
+        for (int base = 0; base < nq; base += TRIAL_GROUP) {
+            const int cnt = nq - base < TRIAL_GROUP ? nq - base : TRIAL_GROUP;
+            if (w < cnt)
+                runlist_warp(tabs[ES->sym.qTrial[base + w]], *reinterpret_cast<RunList*>(ub + w * TRIAL_RL),
+                             reinterpret_cast<uint16_t*>(ub + TRIAL_WS0 + w * 640), lane);
             __syncthreads();
             if (tid < cnt * 28) {
                 const int b = tid / 28, c = tid % 28;
-                const int t = S->sym.qTrial[base + b];
+                const int t = ES->sym.qTrial[base + b];
                 // c_trial_flags order: [0,20) and [40,48) are the rewrite strategies without prune, +20 / +8 with it
                 const int kF = c < 20 ? c : 40 + (c - 20), kT = c < 20 ? 20 + c : 48 + (c - 20);
-                TreeWsCLc ws;
+                TreeWsCLc slow;
+                unsigned char* tw = ub + TRIAL_WS0 + tid * TINY_WS_BYTES;
+                TreeWsTiny ws{reinterpret_cast<uint16_t*>(tw), tw + 48, &slow};
                 int a = 0, bp = 0;
-                if (trial_sizes(*reinterpret_cast<RunListW*>(S->u.ws[b]), c_trial_flags[kF], &a, &bp, ws)) S->err = ERR_TREE;
+                if (trial_sizes(*reinterpret_cast<RunList*>(ub + b * TRIAL_RL), c_trial_flags[kF], &a, &bp, ws)) ES->err = ERR_TREE;
                 trialAll[t * 56 + kF] = a;
                 trialAll[t * 56 + kT] = bp;
             }
             __syncthreads();
             if (tid < cnt) {
-                const int t = S->sym.qTrial[base + tid];
+                const int t = ES->sym.qTrial[base + tid];
                 int best = 0x7fffffff, arg = 0;
                 for (int k = 0; k < 56; k++) { const int bts = trialAll[t * 56 + k]; if (bts < best) { best = bts; arg = k; } }
-                S->sym.trialBits[t] = best; S->sym.trialArg[t] = (unsigned char)arg; S->sym.trialState[t] = ST_DONE;
+                ES->sym.trialBits[t] = (unsigned short)best; ES->sym.trialArg[t] = (unsigned char)arg; ES->sym.trialState[t] = ST_DONE;
             }
             __syncthreads();
         }
@@ -953,21 +1261,50 @@ struct Eng {
         P1(PR_TRIALS);
     }
 
-    // everything the last sweep asked for.  Header trials feed nothing but the selection, so they wait until a batch is
-    // worth the threads (or nothing else is left to do).
+    // the PENDING entries of the memo tables -> this step's request lists
+    __device__ __noinline__ void collect_requests() {
+        __syncthreads();
+        if (tid == 0) { ES->sym.nqPass = ES->sym.nqRec = ES->sym.nqHdr = ES->sym.nqTrial = 0; }
+        __syncthreads();
+        for (int k = tid; k < PMEMO; k += ENG_NT)
+            if (ES->sym.pm[k].key != 0 && ES->sym.pm[k].state != ST_DONE) {
+                const int i = atomicAdd(&ES->sym.nqPass, 1);
+                if (i < QPASS) ES->sym.qPass[i] = (unsigned short)k;
+            }
+        for (int k = tid; k < ES->sym.nMasks; k += ENG_NT)
+            if (ES->sym.rc[k].state == ST_PENDING) {
+                const int i = atomicAdd(&ES->sym.nqRec, 1);
+                if (i < QREC) ES->sym.qRec[i] = (unsigned short)k;
+            }
+        for (int k = tid; k < ES->sym.nHdrs * 3; k += ENG_NT)
+            if (ES->sym.hop[k / 3][k % 3] == 0xFFFF) {
+                const int i = atomicAdd(&ES->sym.nqHdr, 1);
+                if (i < QHDR) ES->sym.qHdr[i] = (unsigned short)(((k / 3) << 2) | (k % 3));
+            }
+        for (int k = tid; k < ES->sym.nTabs; k += ENG_NT)
+            if (ES->sym.trialState[k] == ST_PENDING) {
+                const int i = atomicAdd(&ES->sym.nqTrial, 1);
+                if (i < QTRIAL) ES->sym.qTrial[i] = (unsigned short)k;
+            }
+        __syncthreads();
+        if (tid == 0) {   // what did not fit stays PENDING and is picked up by the next step
+            ES->sym.nqPass = min(ES->sym.nqPass, QPASS); ES->sym.nqRec = min(ES->sym.nqRec, QREC);
+            ES->sym.nqHdr = min(ES->sym.nqHdr, QHDR); ES->sym.nqTrial = min(ES->sym.nqTrial, QTRIAL);
+        }
+        __syncthreads();
+    }
+
+    // everything the last sweeps asked for.  Header trials feed nothing but the selection, so they wait until a batch
+    // is worth the threads (or nothing else is left to do).
     __device__ __noinline__ void execute() {
         __syncthreads();
         exec_passes();
         exec_recodes();
         exec_hdrops();
-        const bool others = S->sym.nqPass + S->sym.nqRec + S->sym.nqHdr > 0;
-        const bool doTrials = S->sym.nqTrial && (!others || S->sym.nqTrial >= 2 * ENG_NW);
+        const bool others = ES->sym.nqPass + ES->sym.nqRec + ES->sym.nqHdr > 0;
+        const bool doTrials = ES->sym.nqTrial && (!others || ES->sym.nqTrial >= 2 * TRIAL_GROUP);
         __syncthreads();
         if (doTrials) exec_trials();
-        if (tid == 0) {
-            S->sym.nqPass = S->sym.nqRec = S->sym.nqHdr = 0;
-            if (doTrials) S->sym.nqTrial = 0;
-        }
         __syncthreads();
     }
 
@@ -993,10 +1330,10 @@ struct Eng {
         if (c.type == 2) {
             if (arg >= 0) {   // a header strategy trial won: optimiseBlockDynBlock (DeflateStream.java:184-198) for real
                 if (tid == 0) {
-                    if (hdr_trial(dst.tab, c_trial_flags[arg], S->u.mat.hdr, S->u.mat.ws)) S->err = ERR_TREE;
+                    if (hdr_trial(dst.tab, c_trial_flags[arg], ES->u.mat.hdr, ES->u.mat.ws)) ES->err = ERR_TREE;
                 }
                 __syncthreads();
-                const uint32_t* hs = (const uint32_t*)&S->u.mat.hdr;
+                const uint32_t* hs = (const uint32_t*)&ES->u.mat.hdr;
                 uint32_t* hd = (uint32_t*)&dst.hdr;
                 for (int k = tid; k < (int)(sizeof(Hdr) / 4); k += ENG_NT) hd[k] = hs[k];
             } else {
@@ -1014,73 +1351,78 @@ struct Eng {
     // sweeps + execution until the part `seg` of the enumeration is resolved, then the selection sweep.  Returns false on
     // a pool overflow (nothing selected).
     __device__ __noinline__ bool run_segment(unsigned seg) {
-        if (tid == 0) { S->sym.doneMulti = 0; S->sym.doneRun = 0; S->sym.doneAor = 0; }
+        if (tid == 0) { ES->sym.doneMulti = 0; ES->sym.doneRun = 0; ES->sym.doneAor = 0; }
         __syncthreads();
+        constexpr int NSW = ENG_NW < 4 ? ENG_NW : 4;   // discovery sweepers: lane 0 of the first warps, one seed (or two) each
+        bool selecting = false;                        // the last turn of the loop is the selection sweep (thread 0 alone)
         for (int it = 0;; it++) {
-            if (tid == 0) {
+            const int t = tid >> 5;
+            if ((tid & 31) == 0 && t < NSW && (!selecting || t == 0)) {   // the one call site of the (inlined) sweep
                 P0();
-                S->sweepDone = S->en.sweep(false, seg) ? 1 : 0;
-                P1(PR_SWEEP);
+                Enumer& en = t == 0 ? ES->en : ES->enx[t - 1];
+                if (t) { en.B = ES->en.B; en.blockType = ES->en.blockType; en.storedOK = ES->en.storedOK; en.storedSize = ES->en.storedSize; en.trace = nullptr; en.trialAll = nullptr; en.internalError = 0; }
+                const unsigned before = ES->en.bestIndex;
+                const bool ok = en.sweep(ES->sym, selecting, seg, selecting ? 0 : t * 4 / NSW, selecting ? 4 : (t + 1) * 4 / NSW);
+                ES->sweepOk[t] = ok && !en.internalError ? 1 : 0;
+                if (selecting) {
+                    ES->segImproved = ES->en.bestIndex != before && !ES->en.bestStored;
+                    if (ES->en.internalError || ES->en.poisoned) ES->err = ERR_INTERNAL;
+                    P1(PR_SELECT);
+                } else { P1(PR_SWEEP); }
             }
             __syncthreads();
-            if (S->sym.overflow) return false;
-            if (S->sweepDone) break;
-            const bool nothing = S->sym.nqPass + S->sym.nqRec + S->sym.nqHdr + S->sym.nqTrial == 0;
-            if (nothing || it > 4096 || S->en.internalError) { if (tid == 0) S->err = ERR_INTERNAL; __syncthreads(); return false; }
+            if (selecting) return true;
+            if (ES->sym.overflow) return false;
+            collect_requests();
+            bool done = true;
+            for (int k = 0; k < NSW; k++) done = done && ES->sweepOk[k];
+            const bool nothing = ES->sym.nqPass + ES->sym.nqRec + ES->sym.nqHdr + ES->sym.nqTrial == 0;
+            if (done && nothing) { selecting = true; continue; }
+            if (nothing || it > 4096) { if (tid == 0) ES->err = ERR_INTERNAL; __syncthreads(); return false; }
             execute();
-            if (S->sym.overflow) return false;
+            if (ES->sym.overflow) return false;
         }
-        if (tid == 0) {
-            P0();
-            const unsigned before = S->en.bestIndex;
-            S->en.sweep(true, seg);
-            S->segImproved = S->en.bestIndex != before && !S->en.bestStored;
-            if (S->en.internalError || S->en.poisoned) S->err = ERR_INTERNAL;
-            P1(PR_SELECT);
-        }
-        __syncthreads();
-        return true;
     }
 
     // DeflateStream.optimiseBlock (:343-490) for B.  storedSize < 0: no stored candidate is compared (phase A resolves
-    // it afterwards from sizeI / sizeC1 / restMin).  Result: S->en.bestSize / bestStored / sizeI / sizeC1 / restMin /
+    // it afterwards from sizeI / sizeC1 / restMin).  Result: ES->en.bestSize / bestStored / sizeI / sizeC1 / restMin /
     // bestIndex, and the winning Huffman candidate (B itself when nothing is smaller) materialised in recs[1].
     __device__ __noinline__ void optimise_block(long long storedSize) {
         P0();
         __syncthreads();
-        if (tid == 0) { S->en.storedSize = storedSize; S->en.begin_round(); S->segmentedRound = 0; }
+        if (tid == 0) { ES->en.storedSize = storedSize; ES->en.begin_round(ES->sym); ES->segmentedRound = 0; }
         __syncthreads();
         bool ok = run_segment(Enumer::SEG_ALL);
         if (ok) {
-            materialise(S->en.best, S->en.bestArg, 1);
-        } else if (!S->err) {
+            materialise(ES->en.best, ES->en.bestArg, 1);
+        } else if (!ES->err) {
             // a pool filled up: the same round again in four segments, with the pools reset (and B re-adopted) in between;
             // the running best lives in recs[1]
             PCOUNT(PR_SEGMENTED, 1);
-            materialise(S->en.B, -1, 0);
+            materialise(ES->en.B, -1, 0);
             __syncthreads();
-            if (tid == 0) { S->en.begin_round(); S->segmentedRound = 1; }   // the winner's ids belong to pools that are gone
+            if (tid == 0) { ES->en.begin_round(ES->sym); ES->segmentedRound = 1; }   // the winner's ids belong to pools that are gone
             __syncthreads();
             const unsigned segs[4] = {Enumer::SEG_HEAD | Enumer::SEG_MULTI_H, Enumer::SEG_MULTI_O, Enumer::SEG_FIXED | Enumer::SEG_LEAST0,
                                       Enumer::SEG_LEAST1};
             bool haveBest = false;
             for (int k = 0; k < 4; k++) {
-                const long long bs = S->en.bestSize;
-                const unsigned bi = S->en.bestIndex, ci = S->en.candIndex;
-                const int bst = S->en.bestStored;
-                const long long rm = S->en.restMin, c1 = S->en.sizeC1;
+                const long long bs = ES->en.bestSize;
+                const unsigned bi = ES->en.bestIndex, ci = ES->en.candIndex;
+                const int bst = ES->en.bestStored;
+                const long long rm = ES->en.restMin, c1 = ES->en.sizeC1;
                 __syncthreads();
                 adopt_B(false);
                 if (tid == 0) {   // adopt_B rewrote B's ids; the selection state carries over
-                    S->en.bestSize = bs; S->en.bestIndex = bi; S->en.candIndex = ci; S->en.bestStored = bst;
-                    S->en.restMin = rm; S->en.sizeC1 = c1;
+                    ES->en.bestSize = bs; ES->en.bestIndex = bi; ES->en.candIndex = ci; ES->en.bestStored = bst;
+                    ES->en.restMin = rm; ES->en.sizeC1 = c1;
                 }
                 __syncthreads();
-                if (!run_segment(segs[k])) { if (tid == 0 && !S->err) S->err = ERR_POOL; __syncthreads(); break; }
-                if (S->segImproved) { materialise(S->en.best, S->en.bestArg, 1); haveBest = true; }
+                if (!run_segment(segs[k])) { if (tid == 0 && !ES->err) ES->err = ERR_POOL; __syncthreads(); break; }
+                if (ES->segImproved) { materialise(ES->en.best, ES->en.bestArg, 1); haveBest = true; }
                 __syncthreads();
             }
-            if (!haveBest && !S->err) { adopt_B(false); materialise(S->en.B, -1, 1); }
+            if (!haveBest && !ES->err) { adopt_B(false); materialise(ES->en.B, -1, 1); }
         }
         __syncthreads();
         P1(PR_ROUND);
@@ -1091,8 +1433,8 @@ struct Eng {
     __device__ __noinline__ void advance_to_best() {
         P0();
         __syncthreads();
-        const bool keep = !S->segmentedRound && !S->sym.overflow && S->sym.nMasks <= MAXM / 2 && S->sym.nTabs <= MAXT / 2 && S->sym.nHdrs + 1 <= MAXH / 2 &&
-                          S->sym.nP <= PMEMO * 3 / 8 && S->en.bestIndex != 0xffffffffu;
+        const bool keep = !ES->segmentedRound && !ES->sym.overflow && ES->sym.nMasks <= MAXM / 2 && ES->sym.nTabs <= MAXT / 2 && ES->sym.nHdrs + 1 <= MAXH / 2 &&
+                          ES->sym.nP <= PMEMO * 3 / 8 && ES->en.bestIndex != 0xffffffffu;
         // recs[0] := recs[1], slot B := slot BEST
         {
             const uint32_t* s = (const uint32_t*)&recs[1];
@@ -1107,22 +1449,22 @@ struct Eng {
         }
         __syncthreads();
         if (keep) {
-            SC b = S->en.best;
-            if (b.type == 2 && S->en.bestArg >= 0) {   // the trial header only exists in the record: give it an id
-                const int hid = S->sym.nHdrs;
+            SC b = ES->en.best;
+            if (b.type == 2 && ES->en.bestArg >= 0) {   // the trial header only exists in the record: give it an id
+                const int hid = ES->sym.nHdrs;
                 const uint32_t* hs = (const uint32_t*)&recs[0].hdr;
                 uint32_t* hd = (uint32_t*)&hdrs[hid];
                 for (int k = tid; k < (int)(sizeof(Hdr) / 4); k += ENG_NT) hd[k] = hs[k];
                 __syncthreads();
                 if (tid == 0) {
-                    S->sym.hbits[hid] = recs[0].hdr.bits;
-                    S->sym.nHdrs = hid + 1;
-                    S->sym.hop[hid][0] = S->sym.hop[hid][1] = S->sym.hop[hid][2] = 0;
+                    ES->sym.hbits[hid] = (unsigned short)recs[0].hdr.bits;
+                    ES->sym.nHdrs = hid + 1;
+                    ES->sym.hop[hid][0] = ES->sym.hop[hid][1] = ES->sym.hop[hid][2] = 0;
                 }
                 b.hid = (short)hid;
             }
             __syncthreads();
-            if (tid == 0) { S->en.B = b; S->en.blockType = b.type; }
+            if (tid == 0) { ES->en.B = b; ES->en.blockType = b.type; }
             __syncthreads();
         } else {
             adopt_B(false);
@@ -1131,25 +1473,25 @@ struct Eng {
     }
 };
 
-__device__ inline void eng_init(Eng& e, EngSmem* S, const EngScratch& sc, int cta) {
-    e.S = S;
+__device__ inline void eng_init(Eng& e, const EngScratch& sc, int cta) {
     e.tid = (int)threadIdx.x;
     e.maxwords = sc.maxwords;
     e.maxn = sc.maxwords * 32;
-    e.masks = sc.masks + (size_t)cta * (MAXM + 2) * sc.maxwords;
-    e.tabs = sc.tabs + (size_t)cta * (MAXT + ENG_NW);
-    e.hdrs = sc.hdrs + (size_t)cta * MAXH;
-    e.hists = sc.hists + (size_t)cta * (MAXM + 2) * 320;
-    e.tabHash = sc.tabHash + (size_t)cta * MAXT;
-    e.dc = sc.dc + (size_t)cta * DCN * e.maxn;
-    e.kind = sc.kind + (size_t)cta * e.maxn;
-    e.minfo = sc.minfo + (size_t)cta * e.maxn;
-    e.tileFirst = sc.tileFirst + (size_t)cta * sc.maxtiles;
-    e.trialAll = sc.trialAll + (size_t)cta * MAXT * 56;
-    e.recs = sc.recs + (size_t)cta * 2;
-    e.slowWs = sc.slowWs + (size_t)cta * ENG_NW;
+    unsigned char* base = sc.slab + (size_t)cta * sc.stride;
+    e.masks = reinterpret_cast<uint32_t*>(base + sc.oMasks);
+    e.tabs = reinterpret_cast<Tab*>(base + sc.oTabs);
+    e.hdrs = reinterpret_cast<Hdr*>(base + sc.oHdrs);
+    e.hists = reinterpret_cast<uint32_t*>(base + sc.oHists);
+    e.tabHash = reinterpret_cast<unsigned long long*>(base + sc.oTabHash);
+    e.dc = reinterpret_cast<short*>(base + sc.oDc);
+    e.kind = base + sc.oKind;
+    e.minfo = reinterpret_cast<uint32_t*>(base + sc.oMinfo);
+    e.tileFirst = reinterpret_cast<uint32_t*>(base + sc.oTileFirst);
+    e.trialAll = reinterpret_cast<int*>(base + sc.oTrialAll);
+    e.recs = reinterpret_cast<Cand*>(base + sc.oRecs);
+    e.slowWs = reinterpret_cast<TreeWs<290, 584>*>(base + sc.oSlowWs);
     e.bigWeights = false;
-    if (threadIdx.x == 0) S->err = 0;
+    if (threadIdx.x == 0) ES->err = 0;
     __syncthreads();
 }
 

@@ -44,11 +44,25 @@ int host_huff_tree_compact(const uint32_t* freq, int n, int limit, uint8_t* lens
     return huff_tree_ws(freq, n, limit, lens, ws);
 }
 
+// the fast header-code tree (falls back to the compact full algorithm when deeper than the limit); *fellBack tells which
+int host_huff_tree_tiny(const uint32_t* freq, int n, int limit, uint8_t* lens, int* fellBack) {
+    static uint16_t heap[32];
+    static uint8_t parent[64];
+    static TreeWsCLc slow;
+    const int rc = huff_tree_tiny(freq, n, limit, lens, heap, parent);
+    *fellBack = rc == 2;
+    if (rc != 2) return rc;
+    return huff_tree_ws(freq, n, limit, lens, slow);
+}
+
 // size-only evaluation of one rewrite strategy for both prune values (trial_sizes over the run list)
 int host_trial_sizes(const uint8_t* lit, int nlit, const uint8_t* dist, int ndist, int flags, int32_t* no_prune, int32_t* prune) {
     static Tab t;
     static RunList rl;
-    static TreeWsCL ws;    // the workspace the engine's trial threads use
+    static uint16_t heap[32];
+    static uint8_t parent[64];
+    static TreeWsCLc slow;
+    TreeWsTiny ws{heap, parent, &slow};    // the workspace the engine's trial threads use
     for (int i = 0; i < MAX_LL; i++) t.L[i] = i < nlit ? lit[i] : 0;
     for (int i = 0; i < MAX_D; i++) t.D[i] = i < ndist ? dist[i] : 0;
     t.nL = (uint16_t)nlit; t.nD = (uint16_t)ndist; t.type = 2;
@@ -136,7 +150,7 @@ struct HostEngine {
         if ((int)hdrs.size() >= MAXH) { S.overflow = 1; return 0; }
         hdrs.push_back(h);
         const int id = (int)hdrs.size() - 1;
-        S.hbits[id] = h.bits;
+        S.hbits[id] = (unsigned short)h.bits;
         S.hop[id][0] = S.hop[id][1] = S.hop[id][2] = 0;
         S.nHdrs = (int)hdrs.size();
         return id;
@@ -259,7 +273,10 @@ struct HostEngine {
     }
     void exec_trial(int t) {
         static RunList rl;
-        static TreeWsCLc ws;
+        static uint16_t heap[32];
+        static uint8_t parent[64];
+        static TreeWsCLc slow;
+        TreeWsTiny ws{heap, parent, &slow};
         runlist_build(tabs[t], rl);
         if ((int)trialAll.size() < MAXT * 56) trialAll.assign(MAXT * 56, 0);
         for (int c = 0; c < 28; c++) {
@@ -270,8 +287,20 @@ struct HostEngine {
         }
         int best = 0x7fffffff, arg = 0;
         for (int k = 0; k < 56; k++) if (trialAll[t * 56 + k] < best) { best = trialAll[t * 56 + k]; arg = k; }
-        S.trialBits[t] = best; S.trialArg[t] = (unsigned char)arg; S.trialState[t] = ST_DONE;
+        S.trialBits[t] = (unsigned short)best; S.trialArg[t] = (unsigned char)arg; S.trialState[t] = ST_DONE;
         en.trialAll = trialAll.data();
+    }
+    // the PENDING entries of the memo tables -> this step's request lists (the kernel does the same with all threads)
+    void collect() {
+        S.nqPass = S.nqRec = S.nqHdr = S.nqTrial = 0;
+        for (int k = 0; k < PMEMO; k++)
+            if (S.pm[k].key != 0 && S.pm[k].state != ST_DONE && S.nqPass < QPASS) S.qPass[S.nqPass++] = (unsigned short)k;
+        for (int k = 0; k < S.nMasks; k++)
+            if (S.rc[k].state == ST_PENDING && S.nqRec < QREC) S.qRec[S.nqRec++] = (unsigned short)k;
+        for (int k = 0; k < S.nHdrs * 3; k++)
+            if (S.hop[k / 3][k % 3] == 0xFFFF && S.nqHdr < QHDR) S.qHdr[S.nqHdr++] = (unsigned short)(((k / 3) << 2) | (k % 3));
+        for (int k = 0; k < S.nTabs; k++)
+            if (S.trialState[k] == ST_PENDING && S.nqTrial < QTRIAL) S.qTrial[S.nqTrial++] = (unsigned short)k;
     }
     void execute() {
         for (int q = 0; q < S.nqPass; q++) exec_pass(S.qPass[q]);
@@ -280,8 +309,6 @@ struct HostEngine {
         const bool others = S.nqPass + S.nqRec + S.nqHdr > 0;
         const bool doTrials = S.nqTrial && (!others || S.nqTrial >= 16);
         if (doTrials) for (int q = 0; q < S.nqTrial; q++) exec_trial(S.qTrial[q]);
-        S.nqPass = S.nqRec = S.nqHdr = 0;
-        if (doTrials) S.nqTrial = 0;
     }
     void materialise(const SC& c, int arg, int which) {
         recMask[which] = masks[c.mid];
@@ -298,23 +325,25 @@ struct HostEngine {
         S.doneMulti = 0; S.doneRun = 0; S.doneAor = 0;
         for (int it = 0;; it++) {
             nSweeps++;
-            const bool done = en.sweep(false, seg);
+            bool done = true;
+            for (int m = 0; m < 4; m++) done = en.sweep(S, false, seg, m, m + 1) && done;   // one seed per sweeping thread
             if (S.overflow) return false;
-            if (done) break;
+            collect();
             const bool nothing = S.nqPass + S.nqRec + S.nqHdr + S.nqTrial == 0;
+            if (done && nothing) break;
             if (nothing || it > 4096 || en.internalError) { err = 16; return false; }
             execute();
             if (S.overflow) return false;
         }
         const unsigned before = en.bestIndex;
-        en.sweep(true, seg);
+        en.sweep(S, true, seg);
         segImproved = en.bestIndex != before && !en.bestStored;
         if (en.internalError || en.poisoned) err = 16;
         return true;
     }
     void optimise_block(long long storedSize, bool forceSegmented) {
         en.storedSize = storedSize;
-        en.begin_round();
+        en.begin_round(S);
         segmentedRound = false;
         bool ok = !forceSegmented && run_segment(Enumer::SEG_ALL);
         if (ok) { materialise(en.best, en.bestArg, 1); return; }
@@ -322,7 +351,7 @@ struct HostEngine {
         nSegmented++;
         segmentedRound = true;   // the winner's ids belong to pools that are gone
         materialise(en.B, -1, 0);
-        en.begin_round();
+        en.begin_round(S);
         const unsigned segs[4] = {Enumer::SEG_HEAD | Enumer::SEG_MULTI_H, Enumer::SEG_MULTI_O, Enumer::SEG_FIXED | Enumer::SEG_LEAST0, Enumer::SEG_LEAST1};
         bool haveBest = false;
         for (int k = 0; k < 4; k++) {
@@ -375,7 +404,6 @@ void* host_engine_load(const uint32_t* sym, const uint32_t* symout, uint32_t n, 
     h.ncl = (uint8_t)ncl; h.bits = hdrBits;
     e->recPay[0] = payload;
     e->recMask[0].assign(n, 0);
-    e->en.S = &e->S;
     e->en.trialAll = nullptr;
     e->en.trace = nullptr;
     e->en.storedOK = ulen <= 65535;

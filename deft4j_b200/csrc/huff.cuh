@@ -188,10 +188,13 @@ D4_DEV int huff_tree(const uint32_t* freq, int n, int limit, uint8_t* lens, Tree
 
 // ---- the litlen tree on the fast path ---------------------------------------------------------------------------------
 // HuffmanTree (huffman/HuffmanTree.java:36-73) with the PriorityQueue mechanics of huff_tree_ws, for the common case that
-// the tree needs no depth limiting: 32-bit heap keys (weight << 10 | node id), parent links only, depths by walking up.
-// Returns 0 and the code lengths, or 2 when the tree is deeper than `limit` (the caller then runs huff_tree_ws, whose
-// limiter needs the full node arrays).  freq[] is overwritten (parent[] lives in the same storage).
-D4_DEV_BIG int huff_tree_fast(uint32_t* freq, int n, int limit, uint8_t* lens, uint32_t* heap, uint16_t* value) {
+// the tree needs no depth limiting: 32-bit heap keys (weight << 10 | node id), parent links only.
+//   huff_tree_fast_build : the merge loop (one thread).  freq[] is overwritten: parent[] lives in the same storage.
+//                          Returns nleaf | root << 16.
+//   huff_tree_fast_depths: code length of every leaf by walking up to the root; `lane` of `nlanes` takes every nlanes-th
+//                          leaf (a warp does this side by side).  Returns the deepest leaf seen by this lane.
+// A tree deeper than the limit is rebuilt by huff_tree_ws, whose limiter needs the full node arrays.
+D4_DEV_BIG uint32_t huff_tree_fast_build(uint32_t* freq, int n, uint32_t* heap, uint16_t* value) {
     uint16_t* parent = reinterpret_cast<uint16_t*>(freq);
     int hs = 0;
     auto add = [&](uint32_t x) {
@@ -248,15 +251,121 @@ D4_DEV_BIG int huff_tree_fast(uint32_t* freq, int n, int limit, uint8_t* lens, u
         parent[r & 1023u] = (uint16_t)id;
         add((((l >> 10) + (r >> 10)) << 10) | (uint32_t)id);
     }
-    const int root = (int)(poll() & 1023u);
+    const uint32_t root = poll() & 1023u;
+    return (uint32_t)nleaf | (root << 16);
+}
+D4_DEV int huff_tree_fast_depths(const uint16_t* parent, const uint16_t* value, int n, uint32_t nleafRoot, uint8_t* lens, int lane,
+                                 int nlanes) {
+    const int nleaf = (int)(nleafRoot & 0xFFFF), root = (int)(nleafRoot >> 16);
     int maxDepth = 0;
-    for (int l = 0; l < nleaf; l++) {
+    for (int l = lane; l < nleaf; l += nlanes) {
         int d = 0;
         for (int node = l; node != root; node = parent[node]) d++;
         if (d > maxDepth) maxDepth = d;
         if (value[l] < n) lens[value[l]] = (uint8_t)d;
     }
+    return maxDepth;
+}
+// both steps in one thread: 0 and the code lengths, or 2 when the tree is deeper than `limit`
+D4_DEV int huff_tree_fast(uint32_t* freq, int n, int limit, uint8_t* lens, uint32_t* heap, uint16_t* value) {
+    const uint32_t nr = huff_tree_fast_build(freq, n, heap, value);
+    return huff_tree_fast_depths(reinterpret_cast<const uint16_t*>(freq), value, n, nr, lens, 0, 1) > limit ? 2 : 0;
+}
+
+// ---- the header code on the fast path -----------------------------------------------------------------------------------
+// The same for the 19-symbol header code (limit 7) when the weights add up to less than 1024 (they count RLE pairs of at
+// most 320 code lengths): 16-bit heap keys (weight << 6 | node id) and byte parent links — 96 bytes of workspace, small
+// enough to give every thread of a CTA its own in shared memory.  The leaf -> symbol map is not stored: real leaves are the
+// symbols with freq > 0 in order, dummies follow at the first indices with freq == 0 (HuffmanTree.java:41-58).
+// Returns 0 and the code lengths, or 2 when the tree is deeper than `limit` (the caller runs huff_tree_ws instead).
+D4_DEV int huff_tree_tiny(const uint32_t* freq, int n, int limit, uint8_t* lens, uint16_t* heap, uint8_t* parent) {
+    int hs = 0;
+    auto add = [&](uint32_t x) {
+        int k = hs++;
+        while (k > 0) {
+            const int p = (k - 1) >> 1;
+            const uint32_t e = heap[p];
+            if ((x >> 6) >= (e >> 6)) break;
+            heap[k] = (uint16_t)e;
+            k = p;
+        }
+        heap[k] = (uint16_t)x;
+    };
+    auto poll = [&]() {
+        const uint32_t result = heap[0];
+        const int s = --hs;
+        const uint32_t x = heap[s];
+        if (s > 0) {
+            int k = 0;
+            const int half = s >> 1;
+            while (k < half) {
+                int child = 2 * k + 1;
+                uint32_t c = heap[child];
+                const int r = child + 1;
+                if (r < s) {
+                    const uint32_t cr = heap[r];
+                    if ((c >> 6) > (cr >> 6)) { c = cr; child = r; }
+                }
+                if ((x >> 6) <= (c >> 6)) break;
+                heap[k] = (uint16_t)c;
+                k = child;
+            }
+            heap[k] = (uint16_t)x;
+        }
+        return result;
+    };
+    int nleaf = 0;
+    for (int i = 0; i < n; i++) {
+        lens[i] = 0;
+        if (freq[i] > 0) { add((freq[i] << 6) | (uint32_t)nleaf); nleaf++; }
+    }
+    const int nreal = nleaf;
+    int index = 0;
+    while (hs < 2) {
+        if (index >= n || freq[index] == 0) { add((1u << 6) | (uint32_t)nleaf); nleaf++; }
+        index++;
+    }
+    int nn = nleaf;
+    const int total = hs;
+    for (int i = 0; i < total - 1; i++) {
+        const uint32_t l = poll(), r = poll();
+        const int id = nn++;
+        parent[l & 63u] = (uint8_t)id;
+        parent[r & 63u] = (uint8_t)id;
+        add((((l >> 6) + (r >> 6)) << 6) | (uint32_t)id);
+    }
+    const int root = (int)(poll() & 63u);
+    int maxDepth = 0, leaf = 0;
+    for (int i = 0; i < n; i++) {          // real leaves, in insertion order
+        if (freq[i] == 0) continue;
+        int d = 0;
+        for (int node = leaf; node != root; node = parent[node]) d++;
+        if (d > maxDepth) maxDepth = d;
+        lens[i] = (uint8_t)d;
+        leaf++;
+    }
+    for (int i = 0; leaf < nleaf; i++) {   // dummies: they receive a code when their index is inside the alphabet (H3)
+        if (i < n && freq[i] != 0) continue;
+        int d = 0;
+        for (int node = leaf; node != root; node = parent[node]) d++;
+        if (d > maxDepth) maxDepth = d;
+        if (i < n) lens[i] = (uint8_t)d;
+        leaf++;
+    }
+    (void)nreal;
     return maxDepth > limit ? 2 : 0;
+}
+constexpr int TINY_WS_BYTES = 100;   // heap u16[24] at +0, parent u8[46] at +48; 25 words: conflict-free across a warp
+// workspace adaptor: the fast path in `tiny` (shared memory on the device), the full algorithm in `slow` when needed
+struct TreeWsTiny {
+    uint16_t* heap;
+    uint8_t* parent;
+    TreeWsCLc* slow;
+};
+D4_DEV int huff_tree_ws(const uint32_t* freq, int n, int limit, uint8_t* lens, TreeWsTiny& ws) {
+    const int rc = huff_tree_tiny(freq, n, limit, lens, ws.heap, ws.parent);
+    if (rc != 2) return rc;
+    return huff_tree_ws(freq, n, limit, lens, *ws.slow);
 }
 
 using TreeWsCL = TreeWs<21, 46>;

@@ -94,10 +94,10 @@ __global__ void __launch_bounds__(ENG_NT, D4_ENG_MINB)
 k_opt_blocks(const uint32_t* __restrict__ jobs, uint32_t njobs, BlkState* __restrict__ bs, RoundLog* __restrict__ logs,
              const uint32_t* __restrict__ sym, const uint32_t* __restrict__ symout, const uint8_t* __restrict__ out,
              uint32_t* __restrict__ maskpool, EngScratch sc, unsigned* __restrict__ counter, int* __restrict__ gerr) {
-    __shared__ EngSmem S;
+    EngSmem& S = g_es;
     __shared__ uint32_t s_job;
     Eng e;
-    eng_init(e, &S, sc, blockIdx.x);
+    eng_init(e, sc, blockIdx.x);
     const int tid = threadIdx.x;
     while (true) {
         if (tid == 0) s_job = atomicAdd(counter, 1u);
@@ -439,10 +439,10 @@ __global__ void __launch_bounds__(ENG_NT, D4_ENG_MINB)
 k_finish(StreamState* __restrict__ streams, uint32_t nstreams, BlkState* __restrict__ bs, const RoundLog* __restrict__ logs,
          uint32_t* __restrict__ sym, const uint32_t* __restrict__ symout, const uint8_t* __restrict__ out,
          uint32_t* __restrict__ maskpool, EngScratch sc, int merge, unsigned* __restrict__ counter, int* __restrict__ gerr) {
-    __shared__ EngSmem S;
+    EngSmem& S = g_es;
     __shared__ uint32_t s_job;
     Eng e;
-    if (merge) eng_init(e, &S, sc, blockIdx.x);
+    if (merge) eng_init(e, sc, blockIdx.x);
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_job = atomicAdd(counter, 1u);

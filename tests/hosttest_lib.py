@@ -72,3 +72,16 @@ def huff_tree_compact(freq, limit):
     L.host_huff_tree_compact.argtypes = [C.POINTER(C.c_uint32), C.c_int, C.c_int, C.POINTER(C.c_uint8)]
     rc = L.host_huff_tree_compact(f, n, limit, lens)
     return rc, list(lens)
+
+
+def huff_tree_tiny(freq, limit):
+    """The fast header-code tree of the trial threads (16-bit keys, byte parents, no stored leaf map); returns
+    (rc, lens, fell back to the full algorithm)."""
+    n = len(freq)
+    f = (C.c_uint32 * n)(*freq)
+    lens = (C.c_uint8 * n)()
+    fb = C.c_int(0)
+    L = lib()
+    L.host_huff_tree_tiny.argtypes = [C.POINTER(C.c_uint32), C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int)]
+    rc = L.host_huff_tree_tiny(f, n, limit, lens, C.byref(fb))
+    return rc, list(lens), fb.value

@@ -125,7 +125,7 @@ def test_compact_header_tree_matches_the_general_one():
     workspace pinned on the oracle: 19 symbols, limit 7, weights adding up to at most 322 — including shapes that
     need the depth limiter and shapes with fewer than two used symbols (dummy leaves)."""
     rnd = random.Random(5)
-    n_limited = 0
+    n_limited = n_fast = 0
     for it in range(6000):
         k = rnd.choice([0, 1, 2, 3, 5, 8, 12, 19])
         freq = [0] * 19
@@ -149,5 +149,8 @@ def test_compact_header_tree_matches_the_general_one():
         a = H.huff_tree(freq, 7)
         b = H.huff_tree_compact(freq, 7)
         assert a == b, (freq, a, b)
+        c = H.huff_tree_tiny(freq, 7)
+        assert c[:2] == a, (freq, a, c)
         n_limited += max(a[1]) == 7
-    assert n_limited > 50
+        n_fast += not c[2]
+    assert n_limited > 50 and n_fast > 50
