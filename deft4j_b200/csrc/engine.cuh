@@ -88,12 +88,14 @@ struct EngSmem {
     int leastSum[32], leastCnt[32];
     unsigned leastBlocked, leastSeen;
     int leastRem[2], leastSize[2];   // the length symbol each mode removes and its cost sum
+    uint32_t binStart[33];           // perm[binStart[b] .. binStart[b + 1]) = the matches with length symbol 257 + b
     unsigned long long red;
     unsigned long long hred[ENG_NW];
     long long recPay[ENG_NW];
     uint32_t wt[ENG_NW];
     int redAny, redAny2, tmpIdx, err;
     int sweepOk[4], segImproved, segmentedRound;
+    struct { long long bestSize, restMin; SC best; unsigned bestIndex, candIndex; int bestStored, bestArg; } carry;   // selection state carried into a sweep
     unsigned char tabDc[MAXT];   // tabid -> cost-array slot (0xFF: none)
     unsigned short dcOwner[DCN]; // slot -> tabid (0xFFFF: free)
     int dcNext;
@@ -130,6 +132,7 @@ struct EngScratch {
     size_t oTrialAll;     // MAXT * 56 int
     size_t oRecs;         // 2 Cand: B and the winner
     size_t oSlowWs;       // ENG_NW TreeWs<290, 584>
+    size_t oPerm;         // maxwords * 32 u32: the block's matches grouped by length symbol
     uint32_t maxwords, maxtiles;
 };
 // lays the slab out; returns the stride
@@ -146,6 +149,7 @@ inline size_t eng_scratch_layout(EngScratch& sc, uint32_t maxwords, uint64_t max
     sc.oTileFirst = take(4 * (size_t)sc.maxtiles);
     sc.oKind = take(maxn);
     sc.oMinfo = take(4 * maxn);
+    sc.oPerm = take(4 * maxn);
     sc.oDc = take(2 * maxn * DCN);
     sc.oMasks = take(4 * (size_t)(MAXM + 2) * maxwords);
     sc.oHists = take(4 * (size_t)(MAXM + 2) * 320);
@@ -173,6 +177,7 @@ struct Eng {
     int* trialAll;
     Cand* recs;
     TreeWs<290, 584>* slowWs;
+    uint32_t* perm;       // symbol indices of the block's matches, grouped by length symbol (ES->binStart)
     int tid;
     bool bigWeights;     // the histogram total may not fit the fast tree's 22-bit weights
 
@@ -314,6 +319,21 @@ struct Eng {
             const uint32_t ti = rel / DC_TILE;
             const int tprev = i ? (int)((v.symout[i - 1] - a0) / DC_TILE) : -1;   // a symbol is shorter than a tile: ti - tprev <= 1
             if ((int)ti != tprev) tileFirst[ti] = i;
+        }
+        // the matches grouped by length symbol (counting sort; the order inside a group does not matter)
+        if (tid < 32) ES->leastCnt[tid] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < v.n; i += ENG_NT) { const uint32_t s = v.sym[i]; if (sym_is_match(s)) atomicAdd(&ES->leastCnt[sym_lensym(s) - 257], 1); }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t acc = 0;
+            for (int b = 0; b < 32; b++) { ES->binStart[b] = acc; acc += (uint32_t)ES->leastCnt[b]; ES->leastCnt[b] = (int)ES->binStart[b]; }
+            ES->binStart[32] = acc;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < v.n; i += ENG_NT) {
+            const uint32_t s = v.sym[i];
+            if (sym_is_match(s)) perm[atomicAdd(&ES->leastCnt[sym_lensym(s) - 257], 1)] = i;
         }
         for (uint32_t i = v.n + tid; i < v.nwords * 32; i += ENG_NT) {
             kind[i] = 0; minfo[i] = 0;
@@ -764,7 +784,9 @@ struct Eng {
 
     // removeDistLitLeastExpensive (DeflateBlockHuffman.java:373-458) on (mid, tabid) for memo slot slot0 (mode 0: least
     // cost sum) and / or slot1 (mode 1: least count); a slot < 0 is not wanted.  The statistics are the same for both
-    // modes, so a state that asks for both pays one pass over the symbols.
+    // modes, so a state that asks for both pays for them once.  They are taken over the block's matches grouped by
+    // length symbol (perm / binStart): every thread walks a contiguous stretch of that list and adds its partial sums
+    // to the shared bins when the length symbol changes - a handful of atomics per thread, no warp-wide voting.
     __device__ __noinline__ void pass_least(int slot0, int slot1, int mid, int tabid) {
         if (ES->sym.nMasks + 2 > MAXM) { if (tid == 0) ES->sym.overflow = 1; __syncthreads(); return; }
         const short* d = ensure_dc(tabid);
@@ -773,54 +795,41 @@ struct Eng {
         if (tid == 0) { ES->leastBlocked = 0; ES->leastSeen = 0; }
         __syncthreads();
         const int lane = tid & 31;
-        // per length symbol: sum of (literal - match) cost, count, blocked (:386-420); lanes of a warp that hold the same
-        // length symbol are summed with one shared-memory atomic
         const uint8_t* mbytes = (const uint8_t*)maskp(mid);
-        const uint32_t end = v.nwords * 32;
-        {   // the warp-wide votes below need every lane of a warp in the loop: the bound is per warp, loads are guarded
-            uint32_t wb = (uint32_t)(tid >> 5) * 256;
-            uint2 kk = make_uint2(0, 0);
-            uint4 dq = make_uint4(0, 0, 0, 0);
-            uint32_t ob = 0;
-            { const uint32_t i0 = wb + (uint32_t)lane * 8; if (i0 < end) { kk = *(const uint2*)(kind + i0); dq = *(const uint4*)(d + i0); ob = mbytes[i0 >> 3]; } }
-            while (wb < end) {
-                const uint2 ckk = kk;
-                const uint4 cdq = dq;
-                const uint32_t cob = ob;
-                const uint32_t nwb = wb + ENG_NT * 8;
-                kk = make_uint2(0, 0); dq = make_uint4(0, 0, 0, 0); ob = 0;
-                { const uint32_t n0 = nwb + (uint32_t)lane * 8; if (n0 < end) { kk = *(const uint2*)(kind + n0); dq = *(const uint4*)(d + n0); ob = mbytes[n0 >> 3]; } }
-                const uint32_t dw[4] = {cdq.x, cdq.y, cdq.z, cdq.w};
-                // live matches of this lane, one bit per symbol
-                uint32_t liveBits = 0;
+        const uint32_t nM = ES->binStart[32];
+        {
+            const uint32_t per = (nM + ENG_NT - 1) / ENG_NT;
+            uint32_t j = (uint32_t)tid * per;
+            const uint32_t jend = min(nM, j + per);
+            int bin = 0;
+            if (j < jend) { while (ES->binStart[bin + 1] <= j) bin++; }
+            int sum = 0, cnt = 0;
+            bool blocked = false, seen = false;
+            auto flush = [&]() {
+                if (seen) atomicOr(&ES->leastSeen, 1u << bin);
+                if (blocked) atomicOr(&ES->leastBlocked, 1u << bin);
+                if (cnt) { atomicAdd(&ES->leastSum[bin], sum); atomicAdd(&ES->leastCnt[bin], cnt); }
+                sum = 0; cnt = 0; blocked = false; seen = false;
+            };
+            while (j < jend) {   // eight matches at a time: their indices, then their costs and mask bytes, in flight together
+                uint32_t idx[8];
+                int xv[8];
+                uint32_t mk[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) liveBits |= ((((u < 4 ? ckk.x : ckk.y) >> (8 * (u & 3))) & 0xff) ? 1u : 0u) << u;
-                liveBits &= ~cob;
-                unsigned pending = __ballot_sync(0xffffffffu, liveBits != 0);
-                if (pending) {
+                for (int u = 0; u < 8; u++) idx[u] = j + u < jend ? perm[j + u] : 0u;
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        if (!__any_sync(0xffffffffu, (liveBits >> u) & 1)) continue;
-                        const int k = (int)(((u < 4 ? ckk.x : ckk.y) >> (8 * (u & 3))) & 0xff);
-                        const bool live = (liveBits >> u) & 1;
-                        const int x = live ? (int)(short)((u & 1) ? (dw[u >> 1] >> 16) : (dw[u >> 1] & 0xffff)) : 0;
-                        const bool blocked = live && x == DC_BLOCKED;
-                        const int bin = live ? k - 1 : 31;
-                        const unsigned grp = __match_any_sync(0xffffffffu, bin);
-                        // one group reduction carries both the count (bits 24+) and the biased cost sum (x >= -64, 32 lanes)
-                        const unsigned packed = __reduce_add_sync(grp, (live && !blocked) ? (1u << 24) + (unsigned)(x + 64) : 0u);
-                        const int cn = (int)(packed >> 24);
-                        const int xs = (int)(packed & 0xFFFFFFu) - 64 * cn;
-                        const unsigned anyBlocked = __ballot_sync(0xffffffffu, blocked) & grp;
-                        if (live && lane == __ffs(grp) - 1) {
-                            atomicOr(&ES->leastSeen, 1u << bin);
-                            if (anyBlocked) atomicOr(&ES->leastBlocked, 1u << bin);
-                            if (cn) { atomicAdd(&ES->leastSum[bin], xs); atomicAdd(&ES->leastCnt[bin], cn); }
-                        }
-                    }
+                for (int u = 0; u < 8; u++) { xv[u] = d[idx[u]]; mk[u] = mbytes[idx[u] >> 3]; }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (j + u >= jend) break;
+                    while (ES->binStart[bin + 1] <= j + u) { flush(); bin++; }
+                    if ((mk[u] >> (idx[u] & 7)) & 1) continue;   // already replaced
+                    seen = true;
+                    if (xv[u] == DC_BLOCKED) blocked = true; else { sum += xv[u]; cnt++; }
                 }
-                wb = nwb;
+                j += 8;
             }
+            flush();
         }
         __syncthreads();
         if (tid == 0) {
@@ -848,34 +857,42 @@ struct Eng {
                 P0();
                 for (int k = tid; k < 320; k += ENG_NT) ES->hist[k] = 0;
                 if (tid == 0) { ES->u.hq.nS = 0; ES->u.hq.nL = 0; }
-                __syncthreads();
                 const int fresh = ES->sym.nMasks;
-                uint8_t* mdb = (uint8_t*)maskp(fresh);
-                unsigned long long hsh = 0;
-                const uint32_t pat = (uint32_t)(rem + 1) * 0x01010101u;
-                uint32_t i0 = (uint32_t)tid * 16;
-                uint4 kq = make_uint4(0, 0, 0, 0);
-                uint32_t ob = 0;
-                if (i0 < end) { kq = *(const uint4*)(kind + i0); ob = *(const uint16_t*)(mbytes + (i0 >> 3)); }
-                while (i0 - (uint32_t)lane * 16 < end) {
-                    const bool act = i0 < end;
-                    const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w};
-                    const uint32_t cob = ob;
-                    const uint32_t nx = i0 + ENG_NT * 16;
-                    if (nx < end) { kq = *(const uint4*)(kind + nx); ob = *(const uint16_t*)(mbytes + (nx >> 3)); }
-                    uint32_t nbits = 0;
-                    if (act) {
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {   // bytes equal to the length symbol -> one bit each
-                            const uint32_t x = kw[q] ^ pat;
-                            const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
-                            nbits |= (((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u)) << (4 * q);
-                        }
-                        nbits &= ~cob;
-                        hsh += store_mask16(mdb, i0, cob, nbits);
+                const uint32_t* mo = maskp(mid);
+                uint32_t* mn = maskp(fresh);
+                for (uint32_t k = tid; k < v.nwords; k += ENG_NT) mn[k] = mo[k];
+                __syncthreads();
+                // every match of the length symbol that is still a match: mask bit + histogram queue
+                const uint32_t j0 = ES->binStart[rem], j1 = ES->binStart[rem + 1];
+                for (uint32_t jb = j0 + (uint32_t)(tid & ~31); jb < j1; jb += ENG_NT) {   // warp-uniform trip count
+                    const uint32_t j = jb + (uint32_t)lane;
+                    uint32_t i = 0;
+                    bool fresh1 = false;
+                    if (j < j1) {
+                        i = perm[j];
+                        fresh1 = !((mbytes[i >> 3] >> (i & 7)) & 1);
+                        if (fresh1) atomicOr(&mn[i >> 5], 1u << (i & 31));
                     }
-                    if (__any_sync(0xffffffffu, nbits != 0)) hq_push_warp(nbits, i0, lane);
-                    i0 = nx;
+                    // queue the newly replaced matches of this warp with one shared atomic
+                    const unsigned bal = __ballot_sync(0xffffffffu, fresh1);
+                    if (bal) {
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(&ES->u.hq.nS, (uint32_t)__popc(bal));
+                        base = __shfl_sync(0xffffffffu, base, 0) + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                        if (fresh1) { if (base < HQS) ES->u.hq.qs[base] = i; else hist_delta_replace(i); }
+                    }
+                }
+                __syncthreads();
+                // the mask hash moves by the bytes that changed
+                unsigned long long hsh = 0;
+                for (uint32_t k = tid; k < v.nwords; k += ENG_NT) {
+                    const uint32_t a0 = mo[k], a1 = mn[k];
+                    if (a0 == a1) continue;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t b0 = (a0 >> (8 * q)) & 0xffu, b1 = (a1 >> (8 * q)) & 0xffu;
+                        if (b0 != b1) hsh += mask_byte_hash(b1, 4 * k + q) - mask_byte_hash(b0, 4 * k + q);
+                    }
                 }
                 const unsigned long long h = ES->maskHash[mid] + cta_sum64(hsh);
                 hq_apply();
@@ -1353,25 +1370,67 @@ struct Eng {
     __device__ __noinline__ bool run_segment(unsigned seg) {
         if (tid == 0) { ES->sym.doneMulti = 0; ES->sym.doneRun = 0; ES->sym.doneAor = 0; }
         __syncthreads();
-        constexpr int NSW = ENG_NW < 4 ? ENG_NW : 4;   // discovery sweepers: lane 0 of the first warps, one seed (or two) each
-        bool selecting = false;                        // the last turn of the loop is the selection sweep (thread 0 alone)
+        constexpr int NSW = ENG_NW < 4 ? ENG_NW : 4;   // sweepers: lane 0 of the first warps, one seed (or two) each
+        // The last turn of the loop is the selection sweep.  The candidates of a seed form one contiguous stretch of the
+        // enumeration, so the sweepers select inside their own stretch (indices from 0, best so far = the value carried
+        // in) and thread 0 joins the stretches in order: first strict minimum, indices shifted by what came before.
+        // With the trace armed the candidates must come out in order: thread 0 sweeps alone.
+        bool selecting = false;
+        const bool par = ES->en.trace == nullptr;
         for (int it = 0;; it++) {
             const int t = tid >> 5;
-            if ((tid & 31) == 0 && t < NSW && (!selecting || t == 0)) {   // the one call site of the (inlined) sweep
+            if (selecting && par && tid == 0) {
+                ES->carry.bestSize = ES->en.bestSize; ES->carry.restMin = ES->en.restMin; ES->carry.best = ES->en.best;
+                ES->carry.bestIndex = ES->en.bestIndex; ES->carry.candIndex = ES->en.candIndex; ES->carry.bestStored = ES->en.bestStored;
+                ES->carry.bestArg = ES->en.bestArg;
+            }
+            if (selecting) __syncthreads();
+            if ((tid & 31) == 0 && t < NSW && (!selecting || par || t == 0)) {   // the one call site of the (inlined) sweep
                 P0();
                 Enumer& en = t == 0 ? ES->en : ES->enx[t - 1];
                 if (t) { en.B = ES->en.B; en.blockType = ES->en.blockType; en.storedOK = ES->en.storedOK; en.storedSize = ES->en.storedSize; en.trace = nullptr; en.trialAll = nullptr; en.internalError = 0; }
+                const bool whole = selecting && !par;
+                unsigned sg = seg;
+                if (selecting && par) {
+                    en.bestSize = ES->carry.bestSize; en.restMin = 0x7fffffffffffffffll; en.candIndex = 0; en.bestIndex = 0xffffffffu;
+                    en.bestStored = 0; en.bestArg = -1;
+                    if (t) sg &= ~(unsigned)Enumer::SEG_HEAD;
+                }
                 const unsigned before = ES->en.bestIndex;
-                const bool ok = en.sweep(ES->sym, selecting, seg, selecting ? 0 : t * 4 / NSW, selecting ? 4 : (t + 1) * 4 / NSW);
+                const bool ok = en.sweep(ES->sym, selecting, sg, whole ? 0 : t * 4 / NSW, whole ? 4 : (t + 1) * 4 / NSW);
                 ES->sweepOk[t] = ok && !en.internalError ? 1 : 0;
                 if (selecting) {
-                    ES->segImproved = ES->en.bestIndex != before && !ES->en.bestStored;
-                    if (ES->en.internalError || ES->en.poisoned) ES->err = ERR_INTERNAL;
+                    if (!par) ES->segImproved = ES->en.bestIndex != before && !ES->en.bestStored;
+                    if (en.internalError || en.poisoned) ES->err = ERR_INTERNAL;
                     P1(PR_SELECT);
                 } else { P1(PR_SWEEP); }
             }
             __syncthreads();
-            if (selecting) return true;
+            if (selecting) {
+                if (par) {
+                    if (tid == 0) {
+                        long long bs = ES->carry.bestSize, rm = ES->carry.restMin;
+                        unsigned bi = ES->carry.bestIndex, base = ES->carry.candIndex;
+                        int st = ES->carry.bestStored, arg = ES->carry.bestArg;
+                        SC best = ES->carry.best;
+                        bool improved = false;
+                        for (int k = 0; k < NSW; k++) {
+                            const Enumer& e = k == 0 ? ES->en : ES->enx[k - 1];
+                            if (e.bestIndex != 0xffffffffu && e.bestSize < bs) {
+                                bs = e.bestSize; bi = base + e.bestIndex; st = e.bestStored; arg = e.bestArg; best = e.best;
+                                improved = !e.bestStored;
+                            }
+                            if (e.restMin < rm) rm = e.restMin;
+                            base += e.candIndex;
+                        }
+                        ES->en.bestSize = bs; ES->en.restMin = rm; ES->en.bestIndex = bi; ES->en.candIndex = base;
+                        ES->en.bestStored = st; ES->en.bestArg = arg; ES->en.best = best;
+                        ES->segImproved = improved ? 1 : 0;
+                    }
+                    __syncthreads();
+                }
+                return true;
+            }
             if (ES->sym.overflow) return false;
             collect_requests();
             bool done = true;
@@ -1490,6 +1549,7 @@ __device__ inline void eng_init(Eng& e, const EngScratch& sc, int cta) {
     e.trialAll = reinterpret_cast<int*>(base + sc.oTrialAll);
     e.recs = reinterpret_cast<Cand*>(base + sc.oRecs);
     e.slowWs = reinterpret_cast<TreeWs<290, 584>*>(base + sc.oSlowWs);
+    e.perm = reinterpret_cast<uint32_t*>(base + sc.oPerm);
     e.bigWeights = false;
     if (threadIdx.x == 0) ES->err = 0;
     __syncthreads();

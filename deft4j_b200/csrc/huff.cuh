@@ -608,6 +608,39 @@ D4_DEV int trim_ncl(const uint8_t* CL, int ncl) {
     return ncl;
 }
 
+// The pairs of one run as at most nine (symbol, run field, count) groups in closed form — what emit_run produces, without
+// its data-dependent loops: 28 threads of a warp evaluate 28 different strategies side by side, and a loop whose trip
+// count depends on the flags would serialise them.  The repeated value of every group is the run's value.
+struct RunGroups { int sym[9], run[9], cnt[9]; };
+D4_DEV void run_groups(int v, int n, int flags, RunGroups& g) {
+    const bool ohh = flags & 1, use8 = flags & 2, use7 = flags & 4, alt8 = flags & 8, noRep = flags & 16,
+               noZRep = flags & 32, noZRep2 = flags & 64, noRepZeros = flags & 128;
+    const bool z18 = v == 0 && !noZRep2, z17 = v == 0 && !noZRep;
+    int c = z18 ? n / 138 : 0;
+    g.sym[0] = 18; g.run[0] = 138; g.cnt[0] = c; n -= 138 * c;
+    c = (z18 && n >= 11) ? 1 : 0;
+    g.sym[1] = 18; g.run[1] = n; g.cnt[1] = c; if (c) n = 0;
+    c = z17 ? n / 10 : 0;
+    g.sym[2] = 17; g.run[2] = 10; g.cnt[2] = c; n -= 10 * c;
+    c = (z17 && n >= 3) ? 1 : 0;
+    g.sym[3] = 17; g.run[3] = n; g.cnt[3] = c; if (c) n = 0;
+    const bool rep = !noRep && n > 0 && (!noRepZeros || v != 0);
+    g.sym[4] = v; g.run[4] = 0; g.cnt[4] = rep ? 1 : 0;
+    int m = rep ? n - 1 : 0;                      // what the 16-runs may cover
+    const int rest = rep ? 0 : n;                 // no repeat codes: everything is spelled out
+    const int r6 = m % 6;
+    const bool sp8 = ohh && use8 && m >= 8 && r6 == 2;           // the walk m, m-6, ... stops at exactly 8
+    const bool sp7 = !sp8 && ohh && use7 && m >= 7 && r6 == 1;   // ... or at exactly 7
+    const int k6 = sp8 ? (m - 8) / 6 : sp7 ? (m - 7) / 6 : m / 6;
+    int rem = (sp8 || sp7) ? 0 : r6;
+    g.sym[5] = 16; g.run[5] = 6; g.cnt[5] = k6;
+    const bool tail16 = !(sp8 || sp7) && rem >= 3;
+    g.sym[6] = 16; g.run[6] = sp8 ? (alt8 ? 5 : 4) : sp7 ? 4 : rem; g.cnt[6] = (sp8 || sp7 || tail16) ? 1 : 0;
+    if (tail16) rem = 0;
+    g.sym[7] = 16; g.run[7] = sp8 ? (alt8 ? 3 : 4) : 3; g.cnt[7] = (sp8 || sp7) ? 1 : 0;
+    g.sym[8] = v; g.run[8] = 0; g.cnt[8] = rest + rem;
+}
+
 // sizes in bits of the trials (flags, prune = false) and (flags, prune = true); returns 1 when a tree cannot be
 // balanced (the reference throws)
 template <class WS>
@@ -615,44 +648,55 @@ D4_DEV int trial_sizes(const RunList& rl, int flags, int* bitsNoPrune, int* bits
     uint32_t f1[19], f2[19];
     uint8_t c1[19], c2[19];
     for (int i = 0; i < 19; i++) { f1[i] = 0; f2[i] = 0; }
-    for (int r = 0; r < rl.n; r++)
-        emit_run(rl.val[r], rl.len[r], flags, [&](int sym, int, int, int cnt) { f1[sym] += (uint32_t)cnt; });
+    RunGroups g;
+    for (int r = 0; r < rl.n; r++) {
+        run_groups(rl.val[r], rl.len[r], flags, g);
+#pragma unroll
+        for (int k = 0; k < 9; k++) f1[g.sym[k]] += (uint32_t)g.cnt[k];
+    }
     if (huff_tree_ws(f1, 19, 7, c1, ws)) return 1;
     const int ncl1 = trim_ncl(c1, 19);
     int sizeSum = 0, saved = 0;
-    for (int r = 0; r < rl.n; r++)
-        emit_run(rl.val[r], rl.len[r], flags, [&](int sym, int run, int val, int cnt) {
-            const int size = c1[sym] + (run > 0 ? pair_extra_bits(sym) : 0);
+    for (int r = 0; r < rl.n; r++) {
+        const int val = rl.val[r];
+        run_groups(val, rl.len[r], flags, g);
+        const int b = c1[val];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const int sym = g.sym[k], run = g.run[k], cnt = g.cnt[k];
+            const bool isRun = k != 4 && k != 8;   // groups 4 and 8 are plain lengths
+            const int size = c1[sym] + (isRun ? pair_extra_bits(sym) : 0);
             sizeSum += size * cnt;
-            bool expand = false;
-            if (run > 0) {
-                const int b = c1[val], tot = b * run;
-                if (b >= 1) {
-                    if (tot < size) saved += (size - tot) * cnt;
-                    expand = tot <= size;
-                }
-            }
-            if (expand) f2[val] += (uint32_t)(run * cnt); else f2[sym] += (uint32_t)cnt;
-        });
+            const int tot = b * run;
+            const bool can = isRun && b >= 1;
+            if (can && tot < size) saved += (size - tot) * cnt;
+            const bool expand = can && tot <= size;
+            f2[expand ? val : sym] += (uint32_t)(expand ? run * cnt : cnt);
+        }
+    }
     *bitsNoPrune = 5 + 5 + 4 + 3 * ncl1 + sizeSum - saved;
     if (huff_tree_ws(f2, 19, 7, c2, ws)) return 1;
     const int ncl2 = trim_ncl(c2, ncl1);
     int sum2 = 0;
-    for (int r = 0; r < rl.n; r++)
-        emit_run(rl.val[r], rl.len[r], flags, [&](int sym, int run, int val, int cnt) {
+    for (int r = 0; r < rl.n; r++) {
+        const int val = rl.val[r];
+        run_groups(val, rl.len[r], flags, g);
+        const int b1 = c1[val], b2 = c2[val];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const int sym = g.sym[k], run = g.run[k], cnt = g.cnt[k];
+            const bool isRun = k != 4 && k != 8;
+            const int ex = isRun ? pair_extra_bits(sym) : 0;
             int bits;
-            const int size1 = c1[sym] + (run > 0 ? pair_extra_bits(sym) : 0);
-            if (run > 0 && c1[val] >= 1 && c1[val] * run <= size1) {
-                bits = run * c2[val];                       // expanded by the prune step: `run` plain lengths
+            if (isRun && b1 >= 1 && b1 * run <= c1[sym] + ex) {
+                bits = run * b2;                                // expanded by the prune step: `run` plain lengths
             } else {
-                bits = c2[sym] + (run > 0 ? pair_extra_bits(sym) : 0);
-                if (run > 0) {
-                    const int b = c2[val], tot = b * run;
-                    if (b >= 1 && tot < bits) bits = tot;   // expanded by optimiseHeader
-                }
+                bits = c2[sym] + ex;
+                if (isRun && b2 >= 1 && b2 * run < bits) bits = b2 * run;   // expanded by optimiseHeader
             }
             sum2 += bits * cnt;
-        });
+        }
+    }
     *bitsPrune = 5 + 5 + 4 + 3 * ncl2 + sum2;
     return 0;
 }
