@@ -89,6 +89,7 @@ struct EngSmem {
     unsigned leastBlocked, leastSeen;
     int leastRem[2], leastSize[2];   // the length symbol each mode removes and its cost sum
     uint32_t binStart[33];           // perm[binStart[b] .. binStart[b + 1]) = the matches with length symbol 257 + b
+    uint32_t itemStart[33];          // items[itemStart[b] .. itemStart[b + 1]) cover bin b, 32 matches apiece
     unsigned long long red;
     unsigned long long hred[ENG_NW];
     long long recPay[ENG_NW];
@@ -104,7 +105,7 @@ struct EngSmem {
     union alignas(16) {
         unsigned char ws[ENG_NW][WS_BYTES];
         uint32_t P[ENG_NW][DC_TILE + 4 + 36]; // cost-array build: per warp, packed (cost | uncodable count << 16) prefixes of one tile + lane bases
-        struct { Hdr hdr; TreeWsCL ws; } mat;   // winner materialisation (thread 0)
+        struct { Tab tab; Hdr hdr; TreeWsCL ws; } mat;   // winner materialisation (thread 0)
         struct { uint32_t nS, nL; uint32_t qs[HQS]; uint32_t ql[HQL]; } hq;   // passes: matches that were just replaced
     } u;
 };
@@ -133,6 +134,8 @@ struct EngScratch {
     size_t oRecs;         // 2 Cand: B and the winner
     size_t oSlowWs;       // ENG_NW TreeWs<290, 584>
     size_t oPerm;         // maxwords * 32 u32: the block's matches grouped by length symbol
+    size_t oDcBits;       // DCN * 2 * maxwords u32: per cost array, the matches with a negative / a zero entry
+    size_t oItems;        // maxwords + 64 u32: stretches of <= 32 entries of perm with one length symbol
     uint32_t maxwords, maxtiles;
 };
 // lays the slab out; returns the stride
@@ -150,7 +153,9 @@ inline size_t eng_scratch_layout(EngScratch& sc, uint32_t maxwords, uint64_t max
     sc.oKind = take(maxn);
     sc.oMinfo = take(4 * maxn);
     sc.oPerm = take(4 * maxn);
+    sc.oItems = take(4 * ((size_t)maxwords + 64));
     sc.oDc = take(2 * maxn * DCN);
+    sc.oDcBits = take(4 * (size_t)maxwords * 2 * DCN);
     sc.oMasks = take(4 * (size_t)(MAXM + 2) * maxwords);
     sc.oHists = take(4 * (size_t)(MAXM + 2) * 320);
     sc.oHdrs = take(sizeof(Hdr) * MAXH);
@@ -178,6 +183,8 @@ struct Eng {
     Cand* recs;
     TreeWs<290, 584>* slowWs;
     uint32_t* perm;       // symbol indices of the block's matches, grouped by length symbol (ES->binStart)
+    uint32_t* dcBits;     // per cost array: maxwords words 'entry < 0', then maxwords words 'entry == 0'
+    uint32_t* items;      // work items of the least-expensive statistics: first perm index | length symbol bin << 27
     int tid;
     bool bigWeights;     // the histogram total may not fit the fast tree's 22-bit weights
 
@@ -186,26 +193,31 @@ struct Eng {
 
     __device__ __noinline__ unsigned long long hash_words(const uint32_t* p, int nwords32) {
         unsigned long long h = 0;
+#pragma unroll 1
         for (int k = tid; k < nwords32; k += ENG_NT) {
             unsigned long long x = (unsigned long long)p[k] + 0x9E3779B97F4A7C15ull * (unsigned long long)(k + 1);
             x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
             h += x;
         }
+#pragma unroll 1
         for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
         if ((tid & 31) == 0) ES->hred[tid >> 5] = h;
         __syncthreads();
         unsigned long long r = 0;
+#pragma unroll 1
         for (int k = 0; k < ENG_NW; k++) r += ES->hred[k];
         __syncthreads();
         return r | 1ull;
     }
     static __device__ __forceinline__ unsigned long long hash_words_warp(const uint32_t* p, int nwords32, int lane) {
         unsigned long long h = 0;
+#pragma unroll 1
         for (int k = lane; k < nwords32; k += 32) {
             unsigned long long x = (unsigned long long)p[k] + 0x9E3779B97F4A7C15ull * (unsigned long long)(k + 1);
             x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
             h += x;
         }
+#pragma unroll 1
         for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
         return h | 1ull;
     }
@@ -217,6 +229,7 @@ struct Eng {
         const unsigned long long h = hash_words_warp(q, (int)(sizeof(Tab) / 4), lane);
         const int nT = ES->sym.nTabs;
         int hit = -1;
+#pragma unroll 1
         for (int k0 = 0; k0 < nT && hit < 0; k0 += 32) {
             const int k = k0 + lane;
             unsigned m = __ballot_sync(0xffffffffu, k < nT && tabHash[k] == h);
@@ -225,6 +238,7 @@ struct Eng {
                 m &= m - 1;
                 const uint32_t* a = (const uint32_t*)&tabs[cand];
                 bool diff = false;
+#pragma unroll 1
                 for (int w = lane; w < (int)(sizeof(Tab) / 4); w += 32) diff |= a[w] != q[w];
                 if (!__any_sync(0xffffffffu, diff)) hit = cand;
             }
@@ -233,6 +247,7 @@ struct Eng {
             if (nT >= MAXT) { if (lane == 0) ES->sym.overflow = 1; return 0; }
             hit = nT;
             uint32_t* a = (uint32_t*)&tabs[hit];
+#pragma unroll 1
             for (int w = lane; w < (int)(sizeof(Tab) / 4); w += 32) a[w] = q[w];
             if (lane == 0) { tabHash[hit] = h; ES->sym.trialState[hit] = ST_EMPTY; ES->sym.nTabs = nT + 1; }
             __syncwarp();
@@ -249,16 +264,19 @@ struct Eng {
         return x;
     }
     __device__ __noinline__ unsigned long long cta_sum64(unsigned long long h) {
+#pragma unroll 1
         for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
         __syncthreads();
         if ((tid & 31) == 0) ES->hred[tid >> 5] = h;
         __syncthreads();
         unsigned long long r = 0;
+#pragma unroll 1
         for (int k = 0; k < ENG_NW; k++) r += ES->hred[k];
         return r;
     }
     __device__ __noinline__ unsigned long long mask_hash_cta(const uint32_t* m) {
         unsigned long long h = 0;
+#pragma unroll 1
         for (uint32_t k = tid; k < v.nwords; k += ENG_NT) {
             const uint32_t w = m[k];
             if (!w) continue;
@@ -277,6 +295,7 @@ struct Eng {
         __syncthreads();
         if (tid == 0) { ES->tmpIdx = -1; ES->redAny2 = 0; }
         __syncthreads();
+#pragma unroll 1
         for (int k = tid; k < fresh; k += ENG_NT)
             if (ES->maskHash[k] == h) atomicMax(&ES->tmpIdx, k);
         __syncthreads();
@@ -284,6 +303,7 @@ struct Eng {
         if (hit >= 0) {
             const uint32_t* a = maskp(hit);
             bool diff = false;
+#pragma unroll 1
             for (uint32_t k = tid; k < v.nwords; k += ENG_NT) diff |= a[k] != q[k];
             if (diff) ES->redAny2 = 1;
             __syncthreads();
@@ -307,8 +327,10 @@ struct Eng {
     __device__ __noinline__ void build_views() {
         const uint32_t a0 = (uint32_t)(v.out_off & ~15ull);
         const uint32_t ntiles = (uint32_t)(((v.out_off - a0) + v.ulen) / DC_TILE) + 2;
+#pragma unroll 1
         for (uint32_t t = tid; t < ntiles; t += ENG_NT) tileFirst[t] = v.n;
         __syncthreads();
+#pragma unroll 1
         for (uint32_t i = tid; i < v.n; i += ENG_NT) {
             const uint32_t s = v.sym[i];
             const uint32_t rel = v.symout[i] - a0;
@@ -323,21 +345,36 @@ struct Eng {
         // the matches grouped by length symbol (counting sort; the order inside a group does not matter)
         if (tid < 32) ES->leastCnt[tid] = 0;
         __syncthreads();
+#pragma unroll 1
         for (uint32_t i = tid; i < v.n; i += ENG_NT) { const uint32_t s = v.sym[i]; if (sym_is_match(s)) atomicAdd(&ES->leastCnt[sym_lensym(s) - 257], 1); }
         __syncthreads();
         if (tid == 0) {
             uint32_t acc = 0;
+#pragma unroll 1
             for (int b = 0; b < 32; b++) { ES->binStart[b] = acc; acc += (uint32_t)ES->leastCnt[b]; ES->leastCnt[b] = (int)ES->binStart[b]; }
             ES->binStart[32] = acc;
         }
         __syncthreads();
+        if (tid == 0) {
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int b = 0; b < 32; b++) { ES->itemStart[b] = acc; acc += (ES->binStart[b + 1] - ES->binStart[b] + 31) / 32; }
+            ES->itemStart[32] = acc;
+        }
+#pragma unroll 1
         for (uint32_t i = tid; i < v.n; i += ENG_NT) {
             const uint32_t s = v.sym[i];
             if (sym_is_match(s)) perm[atomicAdd(&ES->leastCnt[sym_lensym(s) - 257], 1)] = i;
         }
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t o = ES->itemStart[tid];
+#pragma unroll 1
+            for (uint32_t j = ES->binStart[tid]; j < ES->binStart[tid + 1]; j += 32) items[o++] = j | ((uint32_t)tid << 27);
+        }
+#pragma unroll 1
         for (uint32_t i = v.n + tid; i < v.nwords * 32; i += ENG_NT) {
             kind[i] = 0; minfo[i] = 0;
-            for (int sl = 0; sl < DCN; sl++) dc[(size_t)sl * maxn + i] = DC_NOT_MATCH;   // the rows' tails never change
         }
         __syncthreads();
     }
@@ -346,8 +383,10 @@ struct Eng {
     __device__ __noinline__ void pass_hist_full(int mid) {
         P0();
         const uint32_t* m = maskp(mid);
+#pragma unroll 1
         for (int k = tid; k < 320; k += ENG_NT) ES->hist[k] = 0;
         __syncthreads();
+#pragma unroll 1
         for (uint32_t i = tid; i < v.n; i += ENG_NT) {
             uint32_t s = v.sym[i];
             if (!sym_is_match(s)) {
@@ -358,6 +397,7 @@ struct Eng {
             } else {
                 const uint8_t* p = v.out + v.symout[i];
                 int len = sym_len(s);
+#pragma unroll 1
                 for (int k = 0; k < len; k++) atomicAdd(&ES->hist[p[k]], 1u);
             }
         }
@@ -369,6 +409,7 @@ struct Eng {
     // DeflateBlockHuffman.java:759-770); CTA-wide
     __device__ __noinline__ long long hist_payload(const uint32_t* h, const Tab& t) {
         long long acc = 0;
+#pragma unroll 1
         for (int k = tid; k < 318; k += ENG_NT) {
             const uint32_t f = h[k];
             if (!f) continue;
@@ -381,6 +422,7 @@ struct Eng {
         }
         if (tid == 0) ES->red = 0;
         __syncthreads();
+#pragma unroll 1
         for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
         if ((tid & 31) == 0 && acc) atomicAdd(&ES->red, (unsigned long long)acc);
         __syncthreads();
@@ -393,10 +435,12 @@ struct Eng {
     __device__ __noinline__ void reset_pools() {
         __syncthreads();
         sym_reset(ES->sym, tid, ENG_NT);
+#pragma unroll 1
         for (int k = tid; k < MAXT; k += ENG_NT) ES->tabDc[k] = 0xFF;
         if (tid < DCN) ES->dcOwner[tid] = 0xFFFF;
         if (tid == 0) ES->dcNext = 0;
         Tab& f = tabs[TAB_FIXED];
+#pragma unroll 1
         for (int k = tid; k < MAX_LL; k += ENG_NT) f.L[k] = (k < 286) ? ((k <= 143) ? 8 : (k <= 255) ? 9 : (k <= 279) ? 7 : 8) : 0;
         if (tid < MAX_D) f.D[tid] = tid < 30 ? 5 : 0;
         if (tid == 0) { f.nL = 286; f.nD = 30; f.type = 1; f.pad[0] = f.pad[1] = f.pad[2] = 0; }
@@ -412,9 +456,11 @@ struct Eng {
         reset_pools();
         const uint32_t* ms = maskp(SLOT_B);
         uint32_t* m0 = maskp(0);
+#pragma unroll 1
         for (uint32_t k = tid; k < v.nwords; k += ENG_NT) m0[k] = ms[k];
         const uint32_t* hs = histp(SLOT_B);
         uint32_t* h0 = histp(0);
+#pragma unroll 1
         for (int k = tid; k < 320; k += ENG_NT) h0[k] = hs[k];
         __syncthreads();
         const unsigned long long h = mask_hash_cta(m0);
@@ -427,9 +473,11 @@ struct Eng {
         else if (src.tab.type == 2) {
             uint32_t* st = (uint32_t*)&tabs[MAXT];
             const uint32_t* q = (const uint32_t*)&src.tab;
+#pragma unroll 1
             for (int k = tid; k < (int)(sizeof(Tab) / 4); k += ENG_NT) st[k] = q[k];
             uint32_t* hd = (uint32_t*)&hdrs[0];
             const uint32_t* hq = (const uint32_t*)&src.hdr;
+#pragma unroll 1
             for (int k = tid; k < (int)(sizeof(Hdr) / 4); k += ENG_NT) hd[k] = hq[k];
             __syncthreads();
             if (tid < 32) {
@@ -451,13 +499,16 @@ struct Eng {
         __syncthreads();
         bigWeights = v.ulen + (uint64_t)v.n + 4 >= (1ull << 22);
         uint32_t* mb = maskp(SLOT_B);
+#pragma unroll 1
         for (uint32_t k = tid; k < v.nwords; k += ENG_NT) mb[k] = maskSrc[k];
         uint32_t* d = (uint32_t*)&recs[0];
         const uint32_t* s = (const uint32_t*)&src;
+#pragma unroll 1
         for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
         build_views();
         pass_hist_full(SLOT_B);
         uint32_t* hb = histp(SLOT_B);
+#pragma unroll 1
         for (int k = tid; k < 320; k += ENG_NT) hb[k] = ES->hist[k];
         __syncthreads();
         adopt_B(toFixed);
@@ -494,6 +545,7 @@ struct Eng {
             ES->tmpIdx = slot;
         }
         const Tab& tb = tabs[t];
+#pragma unroll 1
         for (int k = tid; k < 256 + 32 + 32; k += ENG_NT) {
             if (k < 256) { const uint32_t c = tb.L[k]; ES->ctab[k] = c ? c : 0x10000u; }
             else if (k < 288) ES->refL[k - 256] = (uint8_t)(tb.L[k] + (k > 256 && k < 286 ? len_ebits_of(k) : 0));
@@ -502,6 +554,11 @@ struct Eng {
         __syncthreads();
         slot = ES->tmpIdx;
         short* d = dc + (size_t)slot * maxn;
+        uint32_t* negW = dcBits + (size_t)slot * 2 * maxwords;   // bit i: entry i < 0;  + maxwords: entry i == 0
+        uint32_t* zerW = negW + maxwords;
+#pragma unroll 1
+        for (uint32_t k = tid; k < v.nwords; k += ENG_NT) { negW[k] = 0; zerW[k] = 0; }
+        __syncthreads();
         const uint32_t a0 = (uint32_t)(v.out_off & ~15ull);
         const uint32_t head = (uint32_t)(v.out_off - a0);
         const uint32_t endRel = head + (uint32_t)v.ulen;
@@ -533,22 +590,35 @@ struct Eng {
         }
         if (lane == 0) P[DC_TILE] = 0;
 #define D4_PFX(k) (LB[(k) >> 4] + P[(k)])
-        // one symbol record: a match inside the tile gets its cost, the one that crosses the tile's end is remembered
-#define D4_DC_ONE(i_, m_, in_)                                                                                   \
+        // one symbol record: a match inside the tile gets its cost (val_), the one that crosses the tile's end is remembered
+#define D4_DC_ONE(i_, m_, val_)                                                                                  \
         do {                                                                                                     \
             const uint32_t mm = (m_);                                                                            \
             const int kq = (int)((mm >> 14) & 31);                                                               \
-            if (!kq) { if (in_) d[(i_)] = DC_NOT_MATCH; }                                                        \
-            else {                                                                                               \
+            val_ = DC_NOT_MATCH;                                                                                 \
+            if (kq) {                                                                                            \
                 const uint32_t s0 = (mm >> 19) & (DC_TILE - 1), e = s0 + (mm & 0x1FF) + 3;                       \
                 const int ref = ES->refL[kq] + ES->refD[(mm >> 9) & 31];                                         \
                 if (e <= DC_TILE) {                                                                              \
                     const uint32_t y = D4_PFX(e) - D4_PFX(s0);                                                   \
-                    d[(i_)] = (y >> 16) ? DC_BLOCKED : (short)((int)(y & 0xffffu) - ref);                        \
+                    val_ = (y >> 16) ? DC_BLOCKED : (short)((int)(y & 0xffffu) - ref);                           \
+                    d[(i_)] = val_;                                                                              \
                 } else { nIdx = (int)(i_); nRef = ref; nPart = LB[32] - D4_PFX(s0); nEnd = e - DC_TILE; }        \
             }                                                                                                    \
         } while (0)
+        // the 32 lanes hold the entries of symbols first .. first + 31: their sign / zero bits go out with two atomics
+#define D4_DC_BITS(first_, val_)                                                                                 \
+        do {                                                                                                     \
+            const unsigned bn = __ballot_sync(0xffffffffu, (val_) < 0), bz = __ballot_sync(0xffffffffu, (val_) == 0); \
+            if (lane == 0 && (bn | bz)) {                                                                        \
+                const uint32_t w0 = (first_) >> 5;                                                               \
+                const int sh = (int)((first_) & 31);                                                             \
+                if (bn) { atomicOr(&negW[w0], bn << sh); if (sh && (bn >> (32 - sh))) atomicOr(&negW[w0 + 1], bn >> (32 - sh)); } \
+                if (bz) { atomicOr(&zerW[w0], bz << sh); if (sh && (bz >> (32 - sh))) atomicOr(&zerW[w0 + 1], bz >> (32 - sh)); } \
+            }                                                                                                    \
+        } while (0)
         // one tile past the warp's run finishes its last crossing match
+#pragma unroll 1
         for (uint32_t T = T0; T <= T1 && T <= ntiles; T++) {
             const bool extra = T >= T1;
             if (extra && __shfl_sync(0xffffffffu, carryIdx, 0) < 0) break;
@@ -599,18 +669,29 @@ struct Eng {
             __syncwarp();
             if (lane == 0 && carryIdx >= 0) {
                 const uint32_t y = carryPart + D4_PFX(carryEnd);
-                d[carryIdx] = (y >> 16) ? DC_BLOCKED : (short)((int)(y & 0xffffu) - carryRef);
+                const short cv = (y >> 16) ? DC_BLOCKED : (short)((int)(y & 0xffffu) - carryRef);
+                d[carryIdx] = cv;
+                if (cv < 0) atomicOr(&negW[carryIdx >> 5], 1u << (carryIdx & 31));
+                if (cv == 0) atomicOr(&zerW[carryIdx >> 5], 1u << (carryIdx & 31));
                 carryIdx = -1;
             }
             if (!extra) {
                 int nIdx = -1, nRef = 0;
                 uint32_t nPart = 0, nEnd = 0;
                 const uint32_t ib = ci0 + (uint32_t)lane;
-                D4_DC_ONE(ib, c0, ib < ci1);
-                D4_DC_ONE(ib + 32, c1, ib + 32 < ci1);
-                D4_DC_ONE(ib + 64, c2, ib + 64 < ci1);
-                D4_DC_ONE(ib + 96, c3, ib + 96 < ci1);
-                for (uint32_t i = ib + 32u * DC_PRE; i < ci1; i += 32) { const uint32_t mx = minfo[i]; D4_DC_ONE(i, mx, true); }   // many short symbols
+                short v0, v1, v2, v3;
+                D4_DC_ONE(ib, c0, v0);      D4_DC_BITS(ci0, v0);
+                D4_DC_ONE(ib + 32, c1, v1); D4_DC_BITS(ci0 + 32, v1);
+                D4_DC_ONE(ib + 64, c2, v2); D4_DC_BITS(ci0 + 64, v2);
+                D4_DC_ONE(ib + 96, c3, v3); D4_DC_BITS(ci0 + 96, v3);
+#pragma unroll 1
+                for (uint32_t fb = ci0 + 32u * DC_PRE; fb < ci1; fb += 32) {   // many short symbols: the rest of the tile
+                    const uint32_t i = fb + (uint32_t)lane;
+                    const uint32_t mx = i < ci1 ? minfo[i] : 0u;
+                    short vx;
+                    D4_DC_ONE(i, mx, vx);
+                    D4_DC_BITS(fb, vx);
+                }
                 // hand the crossing match (if any) to lane 0
                 const unsigned who = __ballot_sync(0xffffffffu, nIdx >= 0);
                 if (who) {
@@ -623,6 +704,7 @@ struct Eng {
             }
             __syncwarp();
         }
+#undef D4_DC_BITS
 #undef D4_DC_ONE
 #undef D4_PFX
         __syncthreads();
@@ -631,19 +713,20 @@ struct Eng {
     }
 
     // match i leaves the symbol list and its bytes enter it as literals: histogram delta in ES->hist
-    __device__ __forceinline__ void hist_delta_replace(uint32_t i) {
+    __device__ __noinline__ void hist_delta_replace(uint32_t i) {
         const uint32_t s = v.sym[i];
         atomicSub(&ES->hist[sym_lensym(s)], 1u);
         atomicSub(&ES->hist[288 + dist_sym(sym_dist(s))], 1u);
         const uint8_t* p = v.out + v.symout[i];
         const int len = sym_len(s);
+#pragma unroll 1
         for (int k = 0; k < len; k++) atomicAdd(&ES->hist[p[k]], 1u);
     }
     // The same for every match a pass has just replaced, with the whole CTA: the pass queues the matches, then a thread
     // per short match (its bytes loaded eight at a time) and a warp per long one apply the delta.
     // all 32 lanes call this together with the matches (bits of `nbits`, symbols i0 ..) each of them replaced in this step:
     // one shared-memory atomic per warp and step instead of one per match
-    __device__ __forceinline__ void hq_push_warp(uint32_t nbits, uint32_t i0, int lane) {
+    __device__ __noinline__ void hq_push_warp(uint32_t nbits, uint32_t i0, int lane) {
         const uint32_t cnt = (uint32_t)__popc(nbits);
         uint32_t incl = cnt;
 #pragma unroll
@@ -653,6 +736,7 @@ struct Eng {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&ES->u.hq.nS, total);
         base = __shfl_sync(0xffffffffu, base, 0) + incl - cnt;
+#pragma unroll 1
         for (uint32_t b = nbits; b; b &= b - 1, base++) {
             const uint32_t i = i0 + (uint32_t)__ffs((int)b) - 1;
             if (base < HQS) ES->u.hq.qs[base] = i; else hist_delta_replace(i);
@@ -661,6 +745,7 @@ struct Eng {
     __device__ __noinline__ void hq_apply() {
         __syncthreads();
         const uint32_t nS = min(ES->u.hq.nS, (uint32_t)HQS);
+#pragma unroll 1
         for (uint32_t j = tid; j < nS; j += ENG_NT) {
             const uint32_t i = ES->u.hq.qs[j];
             const uint32_t mi = minfo[i];
@@ -673,6 +758,7 @@ struct Eng {
                 if (k < HQL) { ES->u.hq.ql[k] = i; continue; }
             }
             const uint8_t* p = v.out + so;
+#pragma unroll 1
             for (int k = 0; k < len; k += 8) {
                 uint32_t b[8];
 #pragma unroll
@@ -684,10 +770,12 @@ struct Eng {
         __syncthreads();
         const uint32_t nL = min(ES->u.hq.nL, (uint32_t)HQL);
         const int lane = tid & 31;
+#pragma unroll 1
         for (uint32_t j = (uint32_t)(tid >> 5); j < nL; j += ENG_NW) {
             const uint32_t i = ES->u.hq.ql[j];
             const int len = (int)(minfo[i] & 0x1FF) + 3;
             const uint8_t* p = v.out + v.symout[i];
+#pragma unroll 1
             for (int k = lane; k < len; k += 32) atomicAdd(&ES->hist[p[k]], 1u);
         }
         __syncthreads();
@@ -696,74 +784,53 @@ struct Eng {
     __device__ __forceinline__ void hist_store_delta(int dst, int src) {
         const uint32_t* hs = histp(src);
         uint32_t* hd = histp(dst);
+#pragma unroll 1
         for (int k = tid; k < 320; k += ENG_NT) hd[k] = hs[k] + ES->hist[k];
     }
 
-    // 16 cost-array entries (eight words) -> bit u set when entry u is negative (or, with `le`, not positive)
-    static __device__ __forceinline__ uint32_t neg_bits16(const uint32_t w[8], bool le) {
-        uint32_t r = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            uint32_t sgn = w[q] & 0x80008000u;
-            if (le) sgn |= ~(((w[q] & 0x7FFF7FFFu) + 0x7FFF7FFFu) | w[q]) & 0x80008000u;   // halfwords equal to zero
-            r |= (((sgn >> 15) & 1u) | ((sgn >> 30) & 2u)) << (2 * q);
-        }
-        return r;
-    }
-    // new mask bytes (two per step) -> stored, and the mask hash moves by the bytes that changed
-    __device__ __forceinline__ unsigned long long store_mask16(uint8_t* mdb, uint32_t i0, uint32_t oldb, uint32_t nbits) {
-        const uint32_t nb = oldb | nbits;
-        *(uint16_t*)(mdb + (i0 >> 3)) = (uint16_t)nb;
-        unsigned long long h = 0;
-        if (nbits & 0xffu) h += mask_byte_hash(nb & 0xffu, i0 >> 3) - mask_byte_hash(oldb & 0xffu, i0 >> 3);
-        if (nbits >> 8) h += mask_byte_hash(nb >> 8, (i0 >> 3) + 1) - mask_byte_hash(oldb >> 8, (i0 >> 3) + 1);
-        return h;
-    }
-
-    // replaceBackrefsWithLiteralsIfSmaller(prune) for memo slot `slot` = (mid, tabid).  16 symbols per thread and step:
-    // candidates are the negative (prune: non-positive) cost-array entries that the mask does not cover yet - read off
-    // the sign bits of eight words; a symbol that is not a match or has an uncodable byte holds a large positive value.
+    // replaceBackrefsWithLiteralsIfSmaller(prune) for memo slot `slot` = (mid, tabid): the candidates are the matches
+    // whose cost-array entry is negative (prune: not positive) and that the mask does not cover yet - one AND of the
+    // cost array's sign words with the mask words, a word (32 symbols) per thread and step; the entries themselves are
+    // only read for the (few) matches that are replaced.
     __device__ __noinline__ void pass_replace(int slot, int mid, int tabid, bool prune) {
         if (ES->sym.nMasks >= MAXM) { if (tid == 0) ES->sym.overflow = 1; __syncthreads(); return; }
         const short* d = ensure_dc(tabid);
         P0();
+        const uint32_t* negW = dcBits + (size_t)ES->tabDc[tabid] * 2 * maxwords;
+        const uint32_t* zerW = negW + maxwords;
+#pragma unroll 1
         for (int k = tid; k < 320; k += ENG_NT) ES->hist[k] = 0;
         if (tid == 0) { ES->red = 0; ES->redAny = 0; ES->u.hq.nS = 0; ES->u.hq.nL = 0; }
         __syncthreads();
         const int fresh = ES->sym.nMasks;
-        const uint8_t* mb = (const uint8_t*)maskp(mid);
-        uint8_t* mdb = (uint8_t*)maskp(fresh);
+        const uint32_t* mo = maskp(mid);
+        uint32_t* mn = maskp(fresh);
         long long saved = 0;
         unsigned long long hsh = 0;
         const int lane = tid & 31;
-        {
-            const uint32_t end = v.nwords * 32;
-            uint32_t i0 = (uint32_t)tid * 16;
-            uint4 da = make_uint4(0, 0, 0, 0), db = da;
-            uint32_t ob = 0;
-            if (i0 < end) { da = *(const uint4*)(d + i0); db = *(const uint4*)(d + i0 + 8); ob = *(const uint16_t*)(mb + (i0 >> 3)); }
-            bool any = false;
-            while (i0 - (uint32_t)lane * 16 < end) {   // per warp: every lane stays in the loop for the warp-wide queue push
-                const bool act = i0 < end;
-                const uint32_t w[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-                const uint32_t cob = ob;
-                const uint32_t nx = i0 + ENG_NT * 16;
-                if (nx < end) { da = *(const uint4*)(d + nx); db = *(const uint4*)(d + nx + 8); ob = *(const uint16_t*)(mb + (nx >> 3)); }
-                uint32_t nbits = 0;
-                if (act) {
-                    nbits = neg_bits16(w, prune) & ~cob;
-                    if (nbits) {
+        bool any = false;
+#pragma unroll 1
+        for (uint32_t kb = (uint32_t)(tid & ~31); kb < v.nwords; kb += ENG_NT) {   // per warp: every lane stays for the queue push
+            const uint32_t k = kb + (uint32_t)lane;
+            uint32_t cand = 0;
+            if (k < v.nwords) {
+                const uint32_t m = mo[k];
+                cand = (negW[k] | (prune ? zerW[k] : 0u)) & ~m;
+                mn[k] = m | cand;
+                if (cand) {
 #pragma unroll
-                        for (int u = 0; u < 16; u++)
-                            if ((nbits >> u) & 1) saved -= (int)(short)((u & 1) ? (w[u >> 1] >> 16) : (w[u >> 1] & 0xffff));
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t b0 = (m >> (8 * q)) & 0xffu, b1 = ((m | cand) >> (8 * q)) & 0xffu;
+                        if (b0 != b1) hsh += mask_byte_hash(b1, 4 * k + q) - mask_byte_hash(b0, 4 * k + q);
                     }
-                    hsh += store_mask16(mdb, i0, cob, nbits);
+#pragma unroll 1
+                    for (uint32_t b = cand; b; b &= b - 1) saved -= d[32 * k + (uint32_t)__ffs((int)b) - 1];
                 }
-                if (__any_sync(0xffffffffu, nbits != 0)) { hq_push_warp(nbits, i0, lane); any |= nbits != 0; }
-                i0 = nx;
             }
-            if (any) ES->redAny = 1;
+            if (__any_sync(0xffffffffu, cand != 0)) { hq_push_warp(cand, 32 * k, lane); any |= cand != 0; }
         }
+        if (any) ES->redAny = 1;
+#pragma unroll 1
         for (int dd = 16; dd > 0; dd >>= 1) saved += __shfl_xor_sync(0xffffffffu, saved, dd);
         if (lane == 0 && saved) atomicAdd(&ES->red, (unsigned long long)saved);
         const unsigned long long h = ES->maskHash[mid] + cta_sum64(hsh);   // (also the barrier after the loop)
@@ -778,6 +845,9 @@ struct Eng {
         if (tid == 0) {
             PSlot& p = ES->sym.pm[slot];
             p.mid = (unsigned short)newmid; p.delta = (long long)ES->red; p.state = ST_DONE;
+            // recodeHuffmanLessMatches (DeflateBlockHuffman.java:655-658) is the only user of the pruning pass and recodes
+            // its result right away: ask for that now, so it runs in this very step
+            if (prune && ES->sym.rc[newmid].state == ST_EMPTY) ES->sym.rc[newmid].state = ST_PENDING;
         }
         __syncthreads();
     }
@@ -796,45 +866,45 @@ struct Eng {
         __syncthreads();
         const int lane = tid & 31;
         const uint8_t* mbytes = (const uint8_t*)maskp(mid);
-        const uint32_t nM = ES->binStart[32];
         {
-            const uint32_t per = (nM + ENG_NT - 1) / ENG_NT;
-            uint32_t j = (uint32_t)tid * per;
-            const uint32_t jend = min(nM, j + per);
-            int bin = 0;
-            if (j < jend) { while (ES->binStart[bin + 1] <= j) bin++; }
-            int sum = 0, cnt = 0;
-            bool blocked = false, seen = false;
-            auto flush = [&]() {
+            const uint32_t nItems = ES->itemStart[32];
+#pragma unroll 1
+            for (uint32_t it = tid; it < nItems; it += ENG_NT) {   // <= 32 matches of one length symbol per item
+                const uint32_t w = items[it];
+                const int bin = (int)(w >> 27);
+                uint32_t j = w & 0x7FFFFFFu;
+                const uint32_t jend = min(ES->binStart[bin + 1], j + 32);
+                int sum = 0, cnt = 0;
+                bool blocked = false, seen = false;
+#pragma unroll 1
+                for (; j < jend; j += 8) {   // eight matches at a time: indices, then costs and mask bytes, in flight together
+                    uint32_t idx[8];
+                    int xv[8];
+                    uint32_t mk[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) idx[u] = j + u < jend ? perm[j + u] : 0u;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { xv[u] = d[idx[u]]; mk[u] = mbytes[idx[u] >> 3]; }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const bool live = j + u < jend && !((mk[u] >> (idx[u] & 7)) & 1);   // still a match
+                        seen |= live;
+                        const bool blk = live && xv[u] == DC_BLOCKED;
+                        blocked |= blk;
+                        if (live && !blk) { sum += xv[u]; cnt++; }
+                    }
+                }
                 if (seen) atomicOr(&ES->leastSeen, 1u << bin);
                 if (blocked) atomicOr(&ES->leastBlocked, 1u << bin);
                 if (cnt) { atomicAdd(&ES->leastSum[bin], sum); atomicAdd(&ES->leastCnt[bin], cnt); }
-                sum = 0; cnt = 0; blocked = false; seen = false;
-            };
-            while (j < jend) {   // eight matches at a time: their indices, then their costs and mask bytes, in flight together
-                uint32_t idx[8];
-                int xv[8];
-                uint32_t mk[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) idx[u] = j + u < jend ? perm[j + u] : 0u;
-#pragma unroll
-                for (int u = 0; u < 8; u++) { xv[u] = d[idx[u]]; mk[u] = mbytes[idx[u] >> 3]; }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    if (j + u >= jend) break;
-                    while (ES->binStart[bin + 1] <= j + u) { flush(); bin++; }
-                    if ((mk[u] >> (idx[u] & 7)) & 1) continue;   // already replaced
-                    seen = true;
-                    if (xv[u] == DC_BLOCKED) blocked = true; else { sum += xv[u]; cnt++; }
-                }
-                j += 8;
             }
-            flush();
         }
         __syncthreads();
         if (tid == 0) {
+#pragma unroll 1
             for (int mode = 0; mode < 2; mode++) {
                 int rem = -1, remSize = 0, remFreq = 0;
+#pragma unroll 1
                 for (int i = 0; i < 32; i++) {
                     if (!((ES->leastBlocked >> i) & 1) && ((ES->leastSeen >> i) & 1)) {
                         bool doRem = mode == 1 ? ES->leastCnt[i] < remFreq : ES->leastSum[i] < remSize;
@@ -847,6 +917,7 @@ struct Eng {
         __syncthreads();
         P1(PR_PASS_LEAST);
         int doneMid = -1, doneRem = -2;
+#pragma unroll 1
         for (int mode = 0; mode < 2; mode++) {
             const int slot = mode ? slot1 : slot0;
             if (slot < 0) continue;
@@ -855,15 +926,18 @@ struct Eng {
             if (rem >= 0 && rem == doneRem) newmid = doneMid;   // both modes remove the same length symbol
             else if (rem >= 0) {
                 P0();
+#pragma unroll 1
                 for (int k = tid; k < 320; k += ENG_NT) ES->hist[k] = 0;
                 if (tid == 0) { ES->u.hq.nS = 0; ES->u.hq.nL = 0; }
                 const int fresh = ES->sym.nMasks;
                 const uint32_t* mo = maskp(mid);
                 uint32_t* mn = maskp(fresh);
+#pragma unroll 1
                 for (uint32_t k = tid; k < v.nwords; k += ENG_NT) mn[k] = mo[k];
                 __syncthreads();
                 // every match of the length symbol that is still a match: mask bit + histogram queue
                 const uint32_t j0 = ES->binStart[rem], j1 = ES->binStart[rem + 1];
+#pragma unroll 1
                 for (uint32_t jb = j0 + (uint32_t)(tid & ~31); jb < j1; jb += ENG_NT) {   // warp-uniform trip count
                     const uint32_t j = jb + (uint32_t)lane;
                     uint32_t i = 0;
@@ -885,6 +959,7 @@ struct Eng {
                 __syncthreads();
                 // the mask hash moves by the bytes that changed
                 unsigned long long hsh = 0;
+#pragma unroll 1
                 for (uint32_t k = tid; k < v.nwords; k += ENG_NT) {
                     const uint32_t a0 = mo[k], a1 = mn[k];
                     if (a0 == a1) continue;
@@ -913,6 +988,7 @@ struct Eng {
         const int nq = ES->sym.nqPass;
         if (!nq) return;
         P0();
+#pragma unroll 1
         for (int q = 0; q < nq; q++) {
             const int slot = ES->sym.qPass[q];
             const unsigned key = ES->sym.pm[slot].key;
@@ -927,6 +1003,7 @@ struct Eng {
                 // the other mode on the same state, when it is waiting too
                 const unsigned sib = pm_key(mid, tabid, op == OP_LEAST0 ? OP_LEAST1 : OP_LEAST0);
                 int other = -1;
+#pragma unroll 1
                 for (int r = q + 1; r < nq; r++)
                     if (ES->sym.pm[ES->sym.qPass[r]].key == sib && ES->sym.pm[ES->sym.qPass[r]].state != ST_DONE) { other = ES->sym.qPass[r]; break; }
                 pass_least(op == OP_LEAST0 ? slot : other, op == OP_LEAST0 ? other : slot, mid, tabid);
@@ -942,6 +1019,7 @@ struct Eng {
     static __device__ __forceinline__ void runlist_warp(const Tab& t, RunList& rl, uint16_t* start, int lane) {
         const int nL = t.nL, n = t.nL + t.nD;
         int cnt = 0;
+#pragma unroll 1
         for (int i0 = 0; i0 < n; i0 += 32) {
             const int i = i0 + lane;
             const int vv = i < n ? (i < nL ? t.L[i] : t.D[i - nL]) : -1;
@@ -956,6 +1034,7 @@ struct Eng {
             cnt += __popc(bal);
         }
         __syncwarp();
+#pragma unroll 1
         for (int k = lane; k < cnt; k += 32) rl.len[k] = (uint16_t)((k + 1 < cnt ? start[k + 1] : n) - start[k]);
         if (lane == 0) rl.n = (uint16_t)cnt;
         __syncwarp();
@@ -969,6 +1048,7 @@ struct Eng {
         if (huff_tree_ws(f, 19, 7, CL, ws)) ES->err = ERR_TREE;
         ncl = trim_ncl(CL, ncl);
         int bits = 5 + 5 + 4 + 3 * ncl + 2 * (int)f[16] + 3 * (int)f[17] + 7 * (int)f[18];
+#pragma unroll 1
         for (int k = 0; k < 19; k++) bits += (int)f[k] * CL[k];
         *nclOut = ncl;
         *bitsOut = bits;
@@ -987,6 +1067,7 @@ struct Eng {
         if (lane < 19) f19[lane] = 0;
         runlist_warp(t, rl, start, lane);
         const int R = rl.n;
+#pragma unroll 1
         for (int r = lane; r < R; r += 32) {
             int cnt = 0;
             emit_run(rl.val[r], rl.len[r], FLAGS_DEFAULT, [&](int, int, int, int k) { cnt += k; });
@@ -994,6 +1075,7 @@ struct Eng {
         }
         __syncwarp();
         int carry = 0;
+#pragma unroll 1
         for (int i0 = 0; i0 < R; i0 += 32) {
             const int i = i0 + lane;
             const int x = i < R ? off[i] : 0;
@@ -1004,10 +1086,12 @@ struct Eng {
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
         __syncwarp();
+#pragma unroll 1
         for (int r = lane; r < R; r += 32) {
             int o = off[r];
             emit_run(rl.val[r], rl.len[r], FLAGS_DEFAULT, [&](int sym, int run, int val, int k) {
                 const uint16_t p = pair_pack(sym, run, val);
+#pragma unroll 1
                 for (int q = 0; q < k; q++) h.pairs[o++] = p;
                 atomicAdd(&f19[sym], (uint32_t)k);
             });
@@ -1017,6 +1101,7 @@ struct Eng {
             int ncl, bits;
             hdr_code_from_freq(f19, cl, 19, &ncl, &bits, tw);
             h.np = (uint16_t)carry; h.ncl = (uint8_t)ncl; h.bits = bits;
+#pragma unroll 1
             for (int k = 0; k < 19; k++) h.CL[k] = cl[k];
         }
         __syncwarp();
@@ -1029,8 +1114,10 @@ struct Eng {
         uint16_t* value = reinterpret_cast<uint16_t*>(wsb + 2464);         // 292
         static_assert(sizeof(TreeWs<32, 68>) <= 1184 && 2464 + 292 * 2 <= WS_BYTES, "warp workspace layout");
         const uint32_t* hs = histp(mid);
+#pragma unroll 1
         for (int k = lane; k < 320; k += 32) freq[k] = hs[k];
         Tab& T = tabs[MAXT + w];
+#pragma unroll 1
         for (int k = lane; k < MAX_LL; k += 32) T.L[k] = 0;
         T.D[lane] = 0;
         __syncwarp();
@@ -1043,6 +1130,7 @@ struct Eng {
             int nd = 30;
             while (nd > 0 && df[nd - 1] == 0) nd--;
             int nz = 0;
+#pragma unroll 1
             for (int k = 0; k < nd; k++) nz += df[k] != 0;
             if (nd == 0) { T.nD = 1; }                                          // handleZero: one entry, length 0
             else if (nz <= 1) { T.nD = (uint16_t)nd; T.D[nd - 1] = 1; }         // handleOne
@@ -1055,6 +1143,7 @@ struct Eng {
                     deepD = huff_tree_fast_depths(reinterpret_cast<const uint16_t*>(freq + 288), valD, nd, nrD, T.D, 0, 1);
                 }
                 if (deepD > 15) {
+#pragma unroll 1
                     for (int k = 0; k < MAX_D; k++) T.D[k] = 0;
                     if (huff_tree<32, 68>(hs + 288, nd, 15, T.D, *reinterpret_cast<TreeWs<32, 68>*>(wsb))) ES->err = ERR_TREE;
                 }
@@ -1069,10 +1158,12 @@ struct Eng {
         int deep = 16;
         if (!bigWeights) {   // code lengths: every lane walks some leaves up to the root
             deep = huff_tree_fast_depths(reinterpret_cast<const uint16_t*>(freq), value, nl, nr, T.L, lane, 32);
+#pragma unroll 1
             for (int dd = 16; dd > 0; dd >>= 1) deep = max(deep, __shfl_xor_sync(0xffffffffu, deep, dd));
         }
         if (deep > 15) {   // deeper than 15 (or weights too large for the fast keys): the full algorithm with its limiter
             __syncwarp();
+#pragma unroll 1
             for (int k = lane; k < MAX_LL; k += 32) T.L[k] = 0;
             __syncwarp();
             if (lane == 0) {
@@ -1084,6 +1175,7 @@ struct Eng {
         P1(PR_TREES);
         // payload = histogram . (code length + extra bits) (recodeToHuffmanInternal, :759-770)
         long long acc = 0;
+#pragma unroll 1
         for (int k = lane; k < 318; k += 32) {
             const uint32_t f = hs[k];
             if (!f) continue;
@@ -1094,6 +1186,7 @@ struct Eng {
             else bits = 0;
             acc += (long long)f * bits;
         }
+#pragma unroll 1
         for (int dd = 16; dd > 0; dd >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, dd);
         if (lane == 0) ES->recPay[w] = acc;
         const long long p1_ = clock64();
@@ -1110,12 +1203,14 @@ struct Eng {
         const int w = tid >> 5, lane = tid & 31;
         const int h0 = ES->sym.nHdrs;
         __syncthreads();
+#pragma unroll 1
         for (int base = 0; base < nq; base += ENG_NW) {
             const int r = base + w;
             const bool mine = r < nq && h0 + r < MAXH;
             if (mine) recode_one(ES->sym.qRec[r], w, lane, h0 + r);
             __syncthreads();
             if (w == 0) {   // intern the staged tables one after the other (two requests may produce the same table)
+#pragma unroll 1
                 for (int k = 0; k < ENG_NW && base + k < nq; k++) {
                     if (h0 + base + k >= MAXH) { if (lane == 0) ES->sym.overflow = 1; continue; }
                     const int t = intern_tab_warp(k, lane);
@@ -1140,6 +1235,7 @@ struct Eng {
     static __device__ __forceinline__ int replace_runs_warp(const uint16_t* in, int np, const uint8_t* CL, bool prune, uint16_t* out,
                                                            int* saved, int lane) {
         int base = 0, sv = 0;
+#pragma unroll 1
         for (int c0 = 0; c0 < np; c0 += 32) {
             const int i = c0 + lane;
             const uint16_t p = i < np ? in[i] : 0;
@@ -1161,6 +1257,7 @@ struct Eng {
             else if (cnt) out[o] = p;
             base += __shfl_sync(0xffffffffu, incl, 31);
         }
+#pragma unroll 1
         for (int dd = 16; dd > 0; dd >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, dd);
         *saved = sv;
         __syncwarp();
@@ -1178,6 +1275,7 @@ struct Eng {
         const Hdr& hs = hdrs[src];
         Hdr& hd = hdrs[dst];
         const int np = hs.np;
+#pragma unroll 1
         for (int k = lane; k < np; k += 32) in[k] = hs.pairs[k];
         if (lane < 19) { cl[lane] = hs.CL[lane]; f19[lane] = 0; }
         int ncl = hs.ncl, bits = hs.bits;
@@ -1199,6 +1297,7 @@ struct Eng {
                 npo = replace_runs_warp(in, np, cl, true, out, &saved, lane);
                 pairs = out;
             }
+#pragma unroll 1
             for (int k = lane; k < npo; k += 32) atomicAdd(&f19[pair_sym(pairs[k])], 1u);
             __syncwarp();
             if (lane == 0) hdr_code_from_freq(f19, cl2, ncl, &ncl, &bits, tw);   // numCodelenLens is NOT reset (H8)
@@ -1206,6 +1305,7 @@ struct Eng {
             bits = __shfl_sync(0xffffffffu, bits, 0);
         }
         __syncwarp();
+#pragma unroll 1
         for (int k = lane; k < npo; k += 32) hd.pairs[k] = pairs[k];
         if (lane < 19) hd.CL[lane] = cl2[lane];
         if (lane == 0) { hd.np = (uint16_t)npo; hd.ncl = (uint8_t)ncl; hd.bits = bits; ES->sym.hbits[dst] = (unsigned short)bits; }
@@ -1219,6 +1319,7 @@ struct Eng {
         const int w = tid >> 5, lane = tid & 31;
         const int h0 = ES->sym.nHdrs;
         __syncthreads();
+#pragma unroll 1
         for (int r = w; r < nq; r += ENG_NW) {
             const int src = ES->sym.qHdr[r] >> 2, op = ES->sym.qHdr[r] & 3;
             if (h0 + r >= MAXH) { if (lane == 0) ES->sym.overflow = 1; continue; }
@@ -1246,6 +1347,7 @@ struct Eng {
         P0();
         const int w = tid >> 5, lane = tid & 31;
         unsigned char* ub = &ES->u.ws[0][0];
+#pragma unroll 1
         for (int base = 0; base < nq; base += TRIAL_GROUP) {
             const int cnt = nq - base < TRIAL_GROUP ? nq - base : TRIAL_GROUP;
             if (w < cnt)
@@ -1269,6 +1371,7 @@ struct Eng {
             if (tid < cnt) {
                 const int t = ES->sym.qTrial[base + tid];
                 int best = 0x7fffffff, arg = 0;
+#pragma unroll 1
                 for (int k = 0; k < 56; k++) { const int bts = trialAll[t * 56 + k]; if (bts < best) { best = bts; arg = k; } }
                 ES->sym.trialBits[t] = (unsigned short)best; ES->sym.trialArg[t] = (unsigned char)arg; ES->sym.trialState[t] = ST_DONE;
             }
@@ -1278,26 +1381,39 @@ struct Eng {
         P1(PR_TRIALS);
     }
 
-    // the PENDING entries of the memo tables -> this step's request lists
-    __device__ __noinline__ void collect_requests() {
+    __device__ __noinline__ void collect_recodes() {
         __syncthreads();
-        if (tid == 0) { ES->sym.nqPass = ES->sym.nqRec = ES->sym.nqHdr = ES->sym.nqTrial = 0; }
+        if (tid == 0) ES->sym.nqRec = 0;
         __syncthreads();
-        for (int k = tid; k < PMEMO; k += ENG_NT)
-            if (ES->sym.pm[k].key != 0 && ES->sym.pm[k].state != ST_DONE) {
-                const int i = atomicAdd(&ES->sym.nqPass, 1);
-                if (i < QPASS) ES->sym.qPass[i] = (unsigned short)k;
-            }
+#pragma unroll 1
         for (int k = tid; k < ES->sym.nMasks; k += ENG_NT)
             if (ES->sym.rc[k].state == ST_PENDING) {
                 const int i = atomicAdd(&ES->sym.nqRec, 1);
                 if (i < QREC) ES->sym.qRec[i] = (unsigned short)k;
             }
+        __syncthreads();
+        if (tid == 0) ES->sym.nqRec = min(ES->sym.nqRec, QREC);
+        __syncthreads();
+    }
+
+    // the PENDING entries of the memo tables -> this step's request lists
+    __device__ __noinline__ void collect_requests() {
+        __syncthreads();
+        if (tid == 0) { ES->sym.nqPass = ES->sym.nqRec = ES->sym.nqHdr = ES->sym.nqTrial = 0; }
+        __syncthreads();
+#pragma unroll 1
+        for (int k = tid; k < PMEMO; k += ENG_NT)
+            if (ES->sym.pm[k].key != 0 && ES->sym.pm[k].state != ST_DONE) {
+                const int i = atomicAdd(&ES->sym.nqPass, 1);
+                if (i < QPASS) ES->sym.qPass[i] = (unsigned short)k;
+            }
+#pragma unroll 1
         for (int k = tid; k < ES->sym.nHdrs * 3; k += ENG_NT)
             if (ES->sym.hop[k / 3][k % 3] == 0xFFFF) {
                 const int i = atomicAdd(&ES->sym.nqHdr, 1);
                 if (i < QHDR) ES->sym.qHdr[i] = (unsigned short)(((k / 3) << 2) | (k % 3));
             }
+#pragma unroll 1
         for (int k = tid; k < ES->sym.nTabs; k += ENG_NT)
             if (ES->sym.trialState[k] == ST_PENDING) {
                 const int i = atomicAdd(&ES->sym.nqTrial, 1);
@@ -1305,10 +1421,10 @@ struct Eng {
             }
         __syncthreads();
         if (tid == 0) {   // what did not fit stays PENDING and is picked up by the next step
-            ES->sym.nqPass = min(ES->sym.nqPass, QPASS); ES->sym.nqRec = min(ES->sym.nqRec, QREC);
+            ES->sym.nqPass = min(ES->sym.nqPass, QPASS);
             ES->sym.nqHdr = min(ES->sym.nqHdr, QHDR); ES->sym.nqTrial = min(ES->sym.nqTrial, QTRIAL);
         }
-        __syncthreads();
+        collect_recodes();
     }
 
     // everything the last sweeps asked for.  Header trials feed nothing but the selection, so they wait until a batch
@@ -1316,6 +1432,7 @@ struct Eng {
     __device__ __noinline__ void execute() {
         __syncthreads();
         exec_passes();
+        collect_recodes();   // includes what the pruning passes of this step have just asked for
         exec_recodes();
         exec_hdrops();
         const bool others = ES->sym.nqPass + ES->sym.nqRec + ES->sym.nqHdr > 0;
@@ -1335,27 +1452,33 @@ struct Eng {
         if (c.mid != slot) {
             const uint32_t* ms = maskp(c.mid);
             uint32_t* md = maskp(slot);
+#pragma unroll 1
             for (uint32_t k = tid; k < v.nwords; k += ENG_NT) md[k] = ms[k];
             const uint32_t* hs = histp(c.mid);
             uint32_t* hd = histp(slot);
+#pragma unroll 1
             for (int k = tid; k < 320; k += ENG_NT) hd[k] = hs[k];
         }
         const uint32_t* ts = (const uint32_t*)&tabs[c.tabid];
         uint32_t* td = (uint32_t*)&dst.tab;
-        for (int k = tid; k < (int)(sizeof(Tab) / 4); k += ENG_NT) td[k] = ts[k];
+        uint32_t* tm = (uint32_t*)&ES->u.mat.tab;
+#pragma unroll 1
+        for (int k = tid; k < (int)(sizeof(Tab) / 4); k += ENG_NT) { const uint32_t x = ts[k]; td[k] = x; tm[k] = x; }
         __syncthreads();
         if (c.type == 2) {
             if (arg >= 0) {   // a header strategy trial won: optimiseBlockDynBlock (DeflateStream.java:184-198) for real
                 if (tid == 0) {
-                    if (hdr_trial(dst.tab, c_trial_flags[arg], ES->u.mat.hdr, ES->u.mat.ws)) ES->err = ERR_TREE;
+                    if (hdr_trial(ES->u.mat.tab, c_trial_flags[arg], ES->u.mat.hdr, ES->u.mat.ws)) ES->err = ERR_TREE;
                 }
                 __syncthreads();
                 const uint32_t* hs = (const uint32_t*)&ES->u.mat.hdr;
                 uint32_t* hd = (uint32_t*)&dst.hdr;
+#pragma unroll 1
                 for (int k = tid; k < (int)(sizeof(Hdr) / 4); k += ENG_NT) hd[k] = hs[k];
             } else {
                 const uint32_t* hs = (const uint32_t*)&hdrs[c.hid];
                 uint32_t* hd = (uint32_t*)&dst.hdr;
+#pragma unroll 1
                 for (int k = tid; k < (int)(sizeof(Hdr) / 4); k += ENG_NT) hd[k] = hs[k];
             }
         } else if (tid == 0) { dst.hdr.np = 0; dst.hdr.ncl = 0; dst.hdr.bits = 0; }
@@ -1377,6 +1500,7 @@ struct Eng {
         // With the trace armed the candidates must come out in order: thread 0 sweeps alone.
         bool selecting = false;
         const bool par = ES->en.trace == nullptr;
+#pragma unroll 1
         for (int it = 0;; it++) {
             const int t = tid >> 5;
             if (selecting && par && tid == 0) {
@@ -1414,6 +1538,7 @@ struct Eng {
                         int st = ES->carry.bestStored, arg = ES->carry.bestArg;
                         SC best = ES->carry.best;
                         bool improved = false;
+#pragma unroll 1
                         for (int k = 0; k < NSW; k++) {
                             const Enumer& e = k == 0 ? ES->en : ES->enx[k - 1];
                             if (e.bestIndex != 0xffffffffu && e.bestSize < bs) {
@@ -1434,6 +1559,7 @@ struct Eng {
             if (ES->sym.overflow) return false;
             collect_requests();
             bool done = true;
+#pragma unroll 1
             for (int k = 0; k < NSW; k++) done = done && ES->sweepOk[k];
             const bool nothing = ES->sym.nqPass + ES->sym.nqRec + ES->sym.nqHdr + ES->sym.nqTrial == 0;
             if (done && nothing) { selecting = true; continue; }
@@ -1465,6 +1591,7 @@ struct Eng {
             const unsigned segs[4] = {Enumer::SEG_HEAD | Enumer::SEG_MULTI_H, Enumer::SEG_MULTI_O, Enumer::SEG_FIXED | Enumer::SEG_LEAST0,
                                       Enumer::SEG_LEAST1};
             bool haveBest = false;
+#pragma unroll 1
             for (int k = 0; k < 4; k++) {
                 const long long bs = ES->en.bestSize;
                 const unsigned bi = ES->en.bestIndex, ci = ES->en.candIndex;
@@ -1498,12 +1625,15 @@ struct Eng {
         {
             const uint32_t* s = (const uint32_t*)&recs[1];
             uint32_t* d = (uint32_t*)&recs[0];
+#pragma unroll 1
             for (int k = tid; k < (int)(sizeof(Cand) / 4); k += ENG_NT) d[k] = s[k];
             const uint32_t* ms = maskp(SLOT_BEST);
             uint32_t* md = maskp(SLOT_B);
+#pragma unroll 1
             for (uint32_t k = tid; k < v.nwords; k += ENG_NT) md[k] = ms[k];
             const uint32_t* hs = histp(SLOT_BEST);
             uint32_t* hd = histp(SLOT_B);
+#pragma unroll 1
             for (int k = tid; k < 320; k += ENG_NT) hd[k] = hs[k];
         }
         __syncthreads();
@@ -1513,6 +1643,7 @@ struct Eng {
                 const int hid = ES->sym.nHdrs;
                 const uint32_t* hs = (const uint32_t*)&recs[0].hdr;
                 uint32_t* hd = (uint32_t*)&hdrs[hid];
+#pragma unroll 1
                 for (int k = tid; k < (int)(sizeof(Hdr) / 4); k += ENG_NT) hd[k] = hs[k];
                 __syncthreads();
                 if (tid == 0) {
@@ -1550,6 +1681,8 @@ __device__ inline void eng_init(Eng& e, const EngScratch& sc, int cta) {
     e.recs = reinterpret_cast<Cand*>(base + sc.oRecs);
     e.slowWs = reinterpret_cast<TreeWs<290, 584>*>(base + sc.oSlowWs);
     e.perm = reinterpret_cast<uint32_t*>(base + sc.oPerm);
+    e.dcBits = reinterpret_cast<uint32_t*>(base + sc.oDcBits);
+    e.items = reinterpret_cast<uint32_t*>(base + sc.oItems);
     e.bigWeights = false;
     if (threadIdx.x == 0) ES->err = 0;
     __syncthreads();

@@ -162,7 +162,7 @@ struct Enumer {
     D4_HD SC bad(SC c) { c.ok = 0; poisoned = true; return c; }
     D4_HD long long size(const SymState& st, const SC& c) const { return c.payload + (c.type == 2 ? (long long)st.hbits[c.hid] : 0); }
 
-    D4_HD SC op_pass(SymState& st, SC c, int op) {
+    D4_HD_BIG SC op_pass(SymState& st, SC c, int op) {
         if (!c.ok) return bad(c);
         if (op >= OP_LEAST0 && op <= OP_LEAST1 && c.type != 2) return c;   // removeDistLitLeastExpensive: DYNAMIC only
         const unsigned key = pm_key(c.mid, c.tabid, op);
@@ -179,7 +179,7 @@ struct Enumer {
         if (ins) st.requested = 1;
         return bad(c);
     }
-    D4_HD SC op_recode(SymState& st, SC c) {   // recodeHuffman (:670-743)
+    D4_HD_BIG SC op_recode(SymState& st, SC c) {   // recodeHuffman (:670-743)
         if (!c.ok) return bad(c);
         RSlot& r = st.rc[c.mid];
         if (r.state == ST_DONE) { c.tabid = (short)r.tabid; c.hid = (short)r.hid; c.payload = r.payload; c.type = 2; return c; }
@@ -190,8 +190,8 @@ struct Enumer {
         }
         return bad(c);
     }
-    D4_HD SC op_recode_less(SymState& st, SC c) { return op_recode(st, op_pass(st, c, OP_REPLACE_PRUNE)); }   // recodeHuffmanLessMatches (:655-658)
-    D4_HD SC op_to_fixed(SymState& st, SC c) {   // recodeToFixedHuffman (:637-653)
+    D4_HD_BIG SC op_recode_less(SymState& st, SC c) { return op_recode(st, op_pass(st, c, OP_REPLACE_PRUNE)); }   // recodeHuffmanLessMatches (:655-658)
+    D4_HD_BIG SC op_to_fixed(SymState& st, SC c) {   // recodeToFixedHuffman (:637-653)
         if (!c.ok) return bad(c);
         if (c.type == 1) return c;
         const unsigned key = pm_key(c.mid, 0xFFF, OP_FIXED);
@@ -207,7 +207,7 @@ struct Enumer {
         if (ins) st.requested = 1;
         return bad(c);
     }
-    D4_HD SC op_hdr(SymState& st, SC c, int hop) {
+    D4_HD_BIG SC op_hdr(SymState& st, SC c, int hop) {
         if (!c.ok) return bad(c);
         if (c.type != 2) return c;
         volatile unsigned short& h = st.hop[c.hid][hop];
@@ -220,7 +220,7 @@ struct Enumer {
         return bad(c);
     }
     // DeflateBlockHuffman.optimise (:460-469): replace pass, then the header half; *saved = bits saved
-    D4_HD SC op_optimise(SymState& st, SC c, long long* saved) {
+    D4_HD_BIG SC op_optimise(SymState& st, SC c, long long* saved) {
         if (!c.ok) return bad(c);
         const long long before = size(st, c);
         c = op_pass(st, c, OP_REPLACE);
@@ -235,7 +235,7 @@ struct Enumer {
         const unsigned k = (*trace->n)++;
         if (k < trace->cap) { trace->buf[2 * k] = idx; trace->buf[2 * k + 1] = sz; }
     }
-    D4_HD void cb(const SymState& st, const SC& c, bool isRest = true) {
+    D4_HD_BIG void cb(const SymState& st, const SC& c, bool isRest = true) {
         if (!c.ok) { poisoned = true; return; }
         if (!select) return;
         const long long sz = size(st, c);
@@ -251,7 +251,7 @@ struct Enumer {
 
     // one base of addOptimisedRecoded's 56 header strategy trials (DeflateStream.java:277-316): the first-minimum
     // strategy is the only one the strict `<` of the callback can accept
-    D4_HD void trial_base(SymState& st, const SC& c) {
+    D4_HD_BIG void trial_base(SymState& st, const SC& c) {
         if (!c.ok) { poisoned = true; return; }
         const int t = c.tabid;
         if (st.trialState[t] != ST_DONE) {
@@ -269,7 +269,7 @@ struct Enumer {
     }
 
     // recodedHuffmanFull (DeflateStream.java:212-229): x is replaced while a further recodeHuffmanLessMatches shrinks it
-    D4_HD SC recoded_full(SymState& st, SC x, bool* changed) {
+    D4_HD_BIG SC recoded_full(SymState& st, SC x, bool* changed) {
         *changed = false;
         if (!x.ok) return bad(x);
         while (true) {

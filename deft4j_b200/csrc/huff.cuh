@@ -278,7 +278,7 @@ D4_DEV int huff_tree_fast(uint32_t* freq, int n, int limit, uint8_t* lens, uint3
 // enough to give every thread of a CTA its own in shared memory.  The leaf -> symbol map is not stored: real leaves are the
 // symbols with freq > 0 in order, dummies follow at the first indices with freq == 0 (HuffmanTree.java:41-58).
 // Returns 0 and the code lengths, or 2 when the tree is deeper than `limit` (the caller runs huff_tree_ws instead).
-D4_DEV int huff_tree_tiny(const uint32_t* freq, int n, int limit, uint8_t* lens, uint16_t* heap, uint8_t* parent) {
+D4_DEV_BIG int huff_tree_tiny(const uint32_t* freq, int n, int limit, uint8_t* lens, uint16_t* heap, uint8_t* parent) {
     int hs = 0;
     auto add = [&](uint32_t x) {
         int k = hs++;
@@ -642,62 +642,78 @@ D4_DEV void run_groups(int v, int n, int flags, RunGroups& g) {
 }
 
 // sizes in bits of the trials (flags, prune = false) and (flags, prune = true); returns 1 when a tree cannot be
-// balanced (the reference throws)
+// balanced (the reference throws).  Three walks over the runs: (0) pair frequencies -> header code c1; (1) sizes under
+// c1, what optimiseHeader / the prune step expand, frequencies after the prune expansion -> c2; (2) sizes under c2.
+// The groups of a run use four symbols only - 18, 17, 16 and the run's own value - so the counters of the three run
+// codes live in registers and the frequency arrays are touched once per run.  One loop nest for all three walks: the
+// code is expanded once (the engine kernel is instruction-cache bound).
 template <class WS>
 D4_DEV int trial_sizes(const RunList& rl, int flags, int* bitsNoPrune, int* bitsPrune, WS& ws) {
-    uint32_t f1[19], f2[19];
+    uint32_t f[19];
     uint8_t c1[19], c2[19];
-    for (int i = 0; i < 19; i++) { f1[i] = 0; f2[i] = 0; }
+    int ncl1 = 19, sizeSum = 0, saved = 0, sum2 = 0;
+    int s16 = 0, s17 = 0, s18 = 0, t16 = 0, t17 = 0, t18 = 0;
     RunGroups g;
-    for (int r = 0; r < rl.n; r++) {
-        run_groups(rl.val[r], rl.len[r], flags, g);
-#pragma unroll
-        for (int k = 0; k < 9; k++) f1[g.sym[k]] += (uint32_t)g.cnt[k];
-    }
-    if (huff_tree_ws(f1, 19, 7, c1, ws)) return 1;
-    const int ncl1 = trim_ncl(c1, 19);
-    int sizeSum = 0, saved = 0;
-    for (int r = 0; r < rl.n; r++) {
-        const int val = rl.val[r];
-        run_groups(val, rl.len[r], flags, g);
-        const int b = c1[val];
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            const int sym = g.sym[k], run = g.run[k], cnt = g.cnt[k];
-            const bool isRun = k != 4 && k != 8;   // groups 4 and 8 are plain lengths
-            const int size = c1[sym] + (isRun ? pair_extra_bits(sym) : 0);
-            sizeSum += size * cnt;
-            const int tot = b * run;
-            const bool can = isRun && b >= 1;
-            if (can && tot < size) saved += (size - tot) * cnt;
-            const bool expand = can && tot <= size;
-            f2[expand ? val : sym] += (uint32_t)(expand ? run * cnt : cnt);
-        }
-    }
-    *bitsNoPrune = 5 + 5 + 4 + 3 * ncl1 + sizeSum - saved;
-    if (huff_tree_ws(f2, 19, 7, c2, ws)) return 1;
-    const int ncl2 = trim_ncl(c2, ncl1);
-    int sum2 = 0;
-    for (int r = 0; r < rl.n; r++) {
-        const int val = rl.val[r];
-        run_groups(val, rl.len[r], flags, g);
-        const int b1 = c1[val], b2 = c2[val];
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            const int sym = g.sym[k], run = g.run[k], cnt = g.cnt[k];
-            const bool isRun = k != 4 && k != 8;
-            const int ex = isRun ? pair_extra_bits(sym) : 0;
-            int bits;
-            if (isRun && b1 >= 1 && b1 * run <= c1[sym] + ex) {
-                bits = run * b2;                                // expanded by the prune step: `run` plain lengths
-            } else {
-                bits = c2[sym] + ex;
-                if (isRun && b2 >= 1 && b2 * run < bits) bits = b2 * run;   // expanded by optimiseHeader
+#pragma unroll 1
+    for (int walk = 0; walk < 3; walk++) {
+        for (int i = 0; i < 19; i++) f[i] = 0;
+        uint32_t a16 = 0, a17 = 0, a18 = 0;
+#pragma unroll 1
+        for (int r = 0; r < rl.n; r++) {
+            const int val = rl.val[r];
+            run_groups(val, rl.len[r], flags, g);
+            const int lit = g.cnt[4] + g.cnt[8];   // plain lengths of the run's value (groups 4 and 8)
+            if (walk == 0) {
+                a18 += (uint32_t)(g.cnt[0] + g.cnt[1]);
+                a17 += (uint32_t)(g.cnt[2] + g.cnt[3]);
+                a16 += (uint32_t)(g.cnt[5] + g.cnt[6] + g.cnt[7]);
+                f[val] += (uint32_t)lit;
+                continue;
             }
-            sum2 += bits * cnt;
+            const int b1 = c1[val], b2 = walk == 2 ? c2[val] : 0;
+            uint32_t toVal = (uint32_t)lit;
+            if (walk == 1) sizeSum += b1 * lit; else sum2 += b2 * lit;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (k == 4) continue;
+                const int size1 = k < 2 ? s18 : k < 4 ? s17 : s16;
+                const int run = g.run[k], cnt = g.cnt[k];
+                const int tot = b1 * run;
+                const bool can = b1 >= 1;
+                const bool expand = can && tot <= size1;      // the prune step turns the run into `run` plain lengths
+                if (walk == 1) {
+                    sizeSum += size1 * cnt;
+                    if (can && tot < size1) saved += (size1 - tot) * cnt;   // optimiseHeader does so only when strictly smaller
+                    toVal += expand ? (uint32_t)(run * cnt) : 0u;
+                    const uint32_t keep = expand ? 0u : (uint32_t)cnt;
+                    if (k < 2) a18 += keep; else if (k < 4) a17 += keep; else a16 += keep;
+                } else {
+                    int bits;
+                    if (expand) bits = run * b2;
+                    else {
+                        bits = k < 2 ? t18 : k < 4 ? t17 : t16;
+                        if (b2 >= 1 && b2 * run < bits) bits = b2 * run;    // expanded by optimiseHeader
+                    }
+                    sum2 += bits * cnt;
+                }
+            }
+            if (walk == 1) f[val] += toVal;
+        }
+        if (walk == 2) break;
+        f[16] += a16; f[17] += a17; f[18] += a18;
+        uint8_t* c = walk == 0 ? c1 : c2;
+        if (huff_tree_ws(f, 19, 7, c, ws)) return 1;
+        if (walk == 0) {
+            ncl1 = trim_ncl(c1, 19);
+            s16 = c1[16] + 2; s17 = c1[17] + 3; s18 = c1[18] + 7;
+        } else {
+            *bitsNoPrune = 5 + 5 + 4 + 3 * ncl1 + sizeSum - saved;
+            const int ncl2 = trim_ncl(c2, ncl1);
+            sum2 = 3 * ncl2;
+            t16 = c2[16] + 2; t17 = c2[17] + 3; t18 = c2[18] + 7;
         }
     }
-    *bitsPrune = 5 + 5 + 4 + 3 * ncl2 + sum2;
+    *bitsPrune = 5 + 5 + 4 + sum2;
     return 0;
 }
 
