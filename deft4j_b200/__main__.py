@@ -76,6 +76,86 @@ def optimise_file(inp, outp, fmt, raw, merge_blocks, stream_cls, out=None, err=N
     return True
 
 
+def _write_back(path, result, inp, err):
+    """the overwrite-through-a-temp-file protocol of CMDUtil.optimiseFile (:137-176)"""
+    if os.path.isfile(path):
+        ext = os.path.splitext(inp)[1] or None
+        fd, tmp = tempfile.mkstemp(prefix="deft-temp-", suffix=ext)
+        try:
+            with os.fdopen(fd, "wb") as f:
+                f.write(result)
+            shutil.copyfile(tmp, path)
+        finally:
+            try:
+                os.unlink(tmp)
+            except OSError:
+                print("Issue deleting temporary file " + tmp, file=err)
+    else:
+        with open(path, "wb") as f:
+            f.write(result)
+
+
+def optimise_files_batched(paths, merge_blocks, stream_cls, out, err, max_bytes=256 << 20):
+    """`optimise-folder` over many files: the deflate streams of a whole group of files (up to max_bytes of input) go to
+    the device as ONE list (DeflateFilesContainer.optimise's batch point, DeflateFilesContainer.java:18-43, widened
+    to the folder); every file then prints and is written back exactly as CMDUtil.optimiseFile would have done."""
+    import io
+    from .container.deflate_files_container import optimise_containers
+    ok = True
+    group, size = [], 0
+
+    def flush():
+        nonlocal ok
+        conts = [g for g in group if g[2] is not None]
+        sinks = [io.StringIO() for _ in conts]
+        try:
+            totals = optimise_containers([g[2] for g in conts], merge_blocks, sinks)
+        except Exception as e:  # noqa: BLE001
+            print("Error when optimising files %s ..: %r" % (conts[0][0] if conts else "", e), file=err)
+            totals, ok = None, False
+        k = 0
+        for path, data, cont in group:
+            print("Optimising file " + path, file=out)
+            if cont is None:
+                print("Invalid file container" if data is None else "Invalid file", file=err)
+                print("Failed to optimise input file", file=err)
+                print("Error when optimising file " + path, file=err)
+                ok = False
+                continue
+            print("File type recognised as " + cont.fileType(), file=out)
+            if totals is None:
+                k += 1
+                continue
+            out.write(sinks[k].getvalue())
+            if totals[k] != 0:
+                print("Saved %d bits with optimisation" % totals[k], file=out)
+            k += 1
+            try:
+                _write_back(path, cont.write(), path, err)
+            except IOError:
+                print("Failed to write output", file=err)
+                print("Error when optimising file " + path, file=err)
+                ok = False
+        group.clear()
+
+    for path in paths:
+        with open(path, "rb") as f:
+            data = f.read()
+        cont = getContainerForBytes(data, os.path.basename(path), stream_cls)
+        try:
+            good = cont is not None and cont.read(data)
+        except Exception:  # noqa: BLE001
+            good = False
+        group.append((path, data, cont if good else None))
+        size += len(data)
+        if size >= max_bytes or len(group) >= 4096:
+            flush()
+            size = 0
+    if group:
+        flush()
+    return ok
+
+
 def main(argv=None, out=None, err=None, stream_cls=None):
     """`stream_cls` lets a caller supply another implementation of the DeflateStream interface (the CPU-only tests
     pass their checker); the command line always uses the CUDA engine."""
@@ -119,6 +199,7 @@ def main(argv=None, out=None, err=None, stream_cls=None):
             paths += [os.path.join(root, f) for f in sorted(files)]
     else:
         paths = [a.inputFolder]
+    todo = []
     for path in paths:
         if not os.path.isfile(path):
             continue
@@ -127,14 +208,8 @@ def main(argv=None, out=None, err=None, stream_cls=None):
         cont = getContainerForBytes(head, os.path.basename(path), cls)
         if cont is None or isinstance(cont, RawDeflateFile):
             continue
-        print("Optimising file " + path, file=out)
-        try:
-            if not optimise_file(path, path, None, False, a.merge_blocks, cls, out, err):
-                print("Error when optimising file " + path, file=err)
-                ok = False
-        except Exception as e:  # noqa: BLE001 - the reference prints the stack trace and carries on
-            print("Error when optimising file %s: %r" % (path, e), file=err)
-            ok = False
+        todo.append(path)
+    ok = optimise_files_batched(todo, a.merge_blocks, cls, out, err)
     if not ok:
         print("Failed to optimise " + a.inputFolder, file=err)
     return 0 if ok else 1

@@ -65,6 +65,7 @@ SYMBOLS = {
     "deft4cu_debug_trace_begin": (C.c_int, [C.c_uint32]),
     "deft4cu_debug_trace_end": (C.c_int, [C.POINTER(C.c_int64), C.c_uint32, C.POINTER(C.c_uint32)]),
     "deft4cu_debug_prof": (C.c_int, [C.POINTER(C.c_uint64), C.c_uint32, C.c_int]),
+    "deft4cu_debug_engine_launches": (C.c_uint64, []),
 }
 
 _lib = None

@@ -36,6 +36,31 @@ def optimise_streams(streams, merge_blocks=True, out=sys.stdout):
     return saved_total
 
 
+def optimise_containers(containers, merge_blocks=True, outs=None):
+    """Several containers (the files of `optimise-folder`, OptimiseFolder.java:33-67) as ONE stream list on the
+    device; every container then reports exactly what its own `optimise` would have printed.  `outs`: one text sink
+    per container (None: silent).  Returns the saved bits per container."""
+    lists = [c.getDeflateStreams() for c in containers]
+    flat = [s for l in lists for s in l]
+    if flat and hasattr(type(flat[0]), "optimise_batch"):
+        saved_flat = type(flat[0]).optimise_batch(flat, merge_blocks)
+    else:
+        saved_flat = [s.optimise(merge_blocks) for s in flat]
+    totals, k = [], 0
+    for ci, l in enumerate(lists):
+        out = outs[ci] if outs is not None else None
+        total = 0
+        for i, stream in enumerate(l):
+            saved = saved_flat[k]; k += 1
+            if PRINT_OPT and saved > 0 and out is not None:
+                print("%d bits saved in stream %d (%s)" % (saved, i, stream.getName()), file=out)
+            total += saved
+        if PRINT_OPT and total > 0 and out is not None:
+            print("Total bits saved %d" % total, file=out)
+        totals.append(total)
+    return totals
+
+
 class DeflateFilesContainer:
     def __init__(self, stream_cls=None):
         self.stream_cls = stream_cls or _default_stream_cls()

@@ -25,6 +25,7 @@ namespace d4 {
 static int g_device = -1;
 static int g_sms = 148;
 static bool g_sync_debug = getenv("D4_SYNC") != nullptr;
+static uint64_t g_opt_launches = 0;   // launches of the candidate engine (k_opt_blocks) since start: tests count them
 static std::mutex g_mu;
 
 static int ensure_init() {
@@ -35,6 +36,21 @@ static int ensure_init() {
 #define LAUNCH(kern, grid, block, stream, ...)                                   \
     do {                                                                         \
         kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                     \
+        launches++;                                                              \
+        D4_CUDA_CHECK(cudaGetLastError());                                       \
+        if (g_sync_debug) {                                                      \
+            cudaError_t se_ = cudaStreamSynchronize(stream);                     \
+            if (se_ != cudaSuccess) {                                            \
+                set_error(std::string(#kern) + " faulted: " + cudaGetErrorString(se_)); \
+                return DEFT4CU_ERR_CUDA;                                         \
+            }                                                                    \
+        }                                                                        \
+    } while (0)
+
+// the same with dynamic shared memory (opt-in above 48 KiB is set once in deft4cu_init)
+#define LAUNCH_SM(kern, grid, block, smem, stream, ...)                          \
+    do {                                                                         \
+        kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                \
         launches++;                                                              \
         D4_CUDA_CHECK(cudaGetLastError());                                       \
         if (g_sync_debug) {                                                      \
@@ -167,6 +183,7 @@ class Batch {
     bool have_sums = false;
     bool parsed = false;
     bool optimised = false;
+    bool too_big = false;   // parse() refused: the decoded size of the batch does not fit the 32-bit pools (split it)
 
     ~Batch() { release_all(); if (own_cs) cudaStreamDestroy(own_cs); }
 
@@ -198,6 +215,24 @@ class Batch {
         return DEFT4CU_OK;
     }
 
+    // the same from streams that already sit in other batches' input buffers (device to device)
+    int upload_from(const std::vector<std::pair<Batch*, uint32_t>>& src) {
+        n = (uint32_t)src.size();
+        if (!own_cs) { D4_CUDA_CHECK(cudaStreamCreateWithFlags(&own_cs, cudaStreamNonBlocking)); cs = own_cs; }
+        in_len.resize(n); in_off.resize(n);
+        uint64_t off = 0;
+        for (uint32_t i = 0; i < n; i++) { in_len[i] = src[i].first->in_len[src[i].second]; in_off[i] = off; off += (in_len[i] + 32 + 15) & ~15ull; }
+        total_in = off + 512;
+        D4_CUDA_CHECK(dalloc(&d_in, total_in, cs));
+        D4_CUDA_CHECK(cudaMemsetAsync(d_in, 0, total_in, cs));
+        for (uint32_t i = 0; i < n; i++) {
+            Batch* b = src[i].first;
+            D4_CUDA_CHECK(cudaStreamSynchronize(b->cs));   // its upload has finished
+            if (in_len[i]) D4_CUDA_CHECK(cudaMemcpyAsync(d_in + in_off[i], b->d_in + b->in_off[src[i].second], in_len[i], cudaMemcpyDeviceToDevice, cs));
+        }
+        return DEFT4CU_OK;
+    }
+
     // ---- parse: find block boundaries, count (walkers), emit, LZ77 resolve, model init ---------------------
     std::vector<StreamDesc> wdescs;     // per walker (device copy: d_descs)
     std::vector<StreamInfo> winfos;     // per walker
@@ -207,6 +242,7 @@ class Batch {
 
     int parse() {
         release_model();
+        too_big = false;
         cudaEvent_t ev[4];
         for (auto& e : ev) cudaEventCreate(&e);
         descs.assign(n + 1, StreamDesc{});
@@ -270,7 +306,7 @@ class Batch {
             D4_CUDA_CHECK(dalloc(&d_chunks, ct, cs));
             D4_CUDA_CHECK(cudaMemcpyAsync(d_descs, wdescs.data(), sizeof(StreamDesc) * W, cudaMemcpyHostToDevice, cs));
             D4_CUDA_CHECK(cudaMemcpyAsync(d_list, all_list.data(), 4 * (size_t)W, cudaMemcpyHostToDevice, cs));
-            if (W) LAUNCH(k_count, W, PARSE_NT, cs, d_in, d_descs, d_infos, d_blocks, d_chunks, d_list, seg_bits, spec_max_bits);
+            if (W) LAUNCH_SM(k_count, W, PARSE_NT, WIN_BYTES + WIN_SLACK + 16, cs, d_in, d_descs, d_infos, d_blocks, d_chunks, d_list, seg_bits, spec_max_bits);
             D4_CUDA_CHECK(cudaMemcpyAsync(winfos.data(), d_infos, sizeof(StreamInfo) * W, cudaMemcpyDeviceToHost, cs));
             D4_CUDA_CHECK(cudaStreamSynchronize(cs));
             // ---- follow every stream's chain from walker 0; re-walk what was guessed wrong ---------------------
@@ -310,7 +346,7 @@ class Batch {
                 for (uint32_t w : pending)
                     D4_CUDA_CHECK(cudaMemcpyAsync(d_descs + w, &wdescs[w], sizeof(StreamDesc), cudaMemcpyHostToDevice, cs));
                 D4_CUDA_CHECK(cudaMemcpyAsync(d_list, pending.data(), 4 * pending.size(), cudaMemcpyHostToDevice, cs));
-                LAUNCH(k_count, (unsigned)pending.size(), PARSE_NT, cs, d_in, d_descs, d_infos, d_blocks, d_chunks, d_list, seg_bits, spec_max_bits);
+                LAUNCH_SM(k_count, (unsigned)pending.size(), PARSE_NT, WIN_BYTES + WIN_SLACK + 16, cs, d_in, d_descs, d_infos, d_blocks, d_chunks, d_list, seg_bits, spec_max_bits);
                 for (uint32_t w : pending)
                     D4_CUDA_CHECK(cudaMemcpyAsync(&winfos[w], d_infos + w, sizeof(StreamInfo), cudaMemcpyDeviceToHost, cs));
                 D4_CUDA_CHECK(cudaStreamSynchronize(cs));
@@ -359,7 +395,10 @@ class Batch {
         }
         descs[n].sym_base = sb; descs[n].out_base = ob;
         nsym_total = sb; nout_total = ob;
-        if (ob >= 0xF8000000ull) {
+        uint64_t ob_max = 0xF8000000ull;   // decoded offsets are 32-bit
+        if (const char* e = getenv("D4_MAX_DECODED")) ob_max = std::min<uint64_t>(ob_max, strtoull(e, nullptr, 10));   // tests force the split
+        if (ob >= ob_max) {
+            too_big = true;
             for (uint32_t i = 0; i < n; i++) if (infos[i].status == ST_OK) infos[i].status = ST_UNSUPPORTED;
             set_error("decoded size of the batch exceeds 4 GiB; split the batch");
             return DEFT4CU_ERR_UNSUPPORTED;
@@ -543,6 +582,7 @@ class Batch {
             if (tracing) grid = 1;
             EngScratch sc{};
             D4_CUDA_CHECK(alloc_scratch(sc, grid, (maxsym + 31) / 32 + 1, maxout));
+            g_opt_launches++;
             LAUNCH(k_opt_blocks, grid, ENG_NT, cs, d_jobs, (uint32_t)jobs.size(), d_bs, d_logs, d_sym, d_symout, d_out, d_maskpool, sc, d_counter, d_gerr);
             free_scratch(sc);
             dfree(d_jobs, cs); dfree(d_counter, cs);
@@ -706,6 +746,7 @@ int deft4cu_init(int device) {
     cudaDeviceProp p;
     D4_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
     g_sms = p.multiProcessorCount;
+    D4_CUDA_CHECK(cudaFuncSetAttribute(k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_BYTES + WIN_SLACK + 16));
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = ~0ull;
@@ -753,6 +794,9 @@ int deft4cu_debug_trace_end(int64_t* dst, uint32_t cap, uint32_t* n) {
     g_trace_dev = nullptr;
     return DEFT4CU_OK;
 }
+
+// how many times the candidate engine kernel has been launched (a list of streams should cost ONE launch)
+uint64_t deft4cu_debug_engine_launches(void) { return g_opt_launches; }
 
 // cycle counters of a -DD4_PROF build (engine.cuh g_prof); returns DEFT4CU_ERR_ARG in ordinary builds
 int deft4cu_debug_prof(uint64_t* dst, uint32_t n, int reset) {
@@ -806,6 +850,30 @@ int deft4cu_stream_optimise_batch(deft4cu_stream* const* s, uint32_t n, uint32_t
     for (uint32_t i = 0; i < n; i++) {
         if (!s[i]) return DEFT4CU_ERR_ARG;
         if (std::find(batches.begin(), batches.end(), s[i]->batch.get()) == batches.end()) batches.push_back(s[i]->batch.get());
+    }
+    // The reference's batch point is the stream LIST (DeflateFilesContainer.optimise, DeflateFilesContainer.java:18-43),
+    // but containers parse their streams one at a time (each parse must report where the stream ended), so the list
+    // usually arrives as one batch per stream.  Streams that have not been optimised yet are regrouped into ONE batch
+    // (device-to-device copy of their input, parsed again together): one launch of every kernel for the whole list.
+    if (batches.size() > 1) {
+        bool fresh = true;
+        for (Batch* b : batches) fresh = fresh && !b->optimised && b->parsed;
+        for (uint32_t i = 0; i < n && fresh; i++)
+            for (uint32_t k = 0; k < i; k++) if (s[k] == s[i]) fresh = false;   // a handle listed twice
+        if (fresh) {
+            std::vector<std::pair<Batch*, uint32_t>> src(n);
+            for (uint32_t i = 0; i < n; i++) src[i] = {s[i]->batch.get(), s[i]->idx};
+            auto nb = std::make_shared<Batch>();
+            int rc = nb->upload_from(src);
+            if (rc == DEFT4CU_OK) rc = nb->parse();
+            bool same = rc == DEFT4CU_OK;
+            for (uint32_t i = 0; i < n && same; i++) same = nb->infos[i].status == ST_OK;
+            if (same) {
+                for (uint32_t i = 0; i < n; i++) { s[i]->batch = nb; s[i]->idx = i; }
+                batches.assign(1, nb.get());
+            } else if (rc != DEFT4CU_OK && rc != DEFT4CU_ERR_UNSUPPORTED) return rc;
+            // (too large for one batch, or a stream that no longer parses: keep the batches as they are)
+        }
     }
     int worst = DEFT4CU_OK;
     for (Batch* b : batches) {
@@ -985,6 +1053,15 @@ int deft4cu_optimise_batch(const uint8_t* const* in, const uint64_t* in_len, uin
     rc = b.upload(in, in_len, n);
     if (rc) return rc;
     rc = b.parse();
+    if (rc == DEFT4CU_ERR_UNSUPPORTED && b.too_big && n > 1) {
+        // more than 4 GiB of decoded data: the list is optimised in two halves (streams never interact)
+        b.release_all();
+        const uint32_t h = n / 2;
+        const int r1 = deft4cu_optimise_batch(in, in_len, h, flags, results);
+        if (r1 && r1 != DEFT4CU_ERR_UNSUPPORTED) return r1;
+        const int r2 = deft4cu_optimise_batch(in + h, in_len + h, n - h, flags, results + h);
+        return r2 ? r2 : r1;
+    }
     if (rc) {
         if (rc == DEFT4CU_ERR_UNSUPPORTED && b.infos.size() == n) {
             for (uint32_t i = 0; i < n; i++) { memset(&results[i], 0, sizeof results[i]); results[i].status = b.infos[i].status; }

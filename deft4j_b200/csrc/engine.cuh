@@ -56,7 +56,7 @@ struct BlkView {
 };
 
 constexpr int DC_TILE = 512;      // decoded bytes per cost-array tile: one 16-byte load per lane of a warp
-constexpr int DCN = 8;            // cost arrays kept per block (round-robin eviction)
+constexpr int DCN = 16;           // cost arrays kept per block (round-robin eviction)
 constexpr int WS_BYTES = 3072;    // per-warp workspace for trees / header work
 constexpr int HQS = 4608, HQL = 1024;   // queue of freshly replaced matches (all / long ones) for the histogram update
 constexpr int SLOT_B = MAXM, SLOT_BEST = MAXM + 1;   // extra mask / histogram slots: the records of B and of the winner
@@ -127,7 +127,6 @@ struct EngScratch {
     size_t oHists;        // (MAXM + 2) * 320 u32
     size_t oTabHash;      // MAXT u64
     size_t oDc;           // DCN * maxwords * 32 short
-    size_t oKind;         // maxwords * 32 u8
     size_t oMinfo;        // maxwords * 32 u32
     size_t oTileFirst;    // maxtiles u32
     size_t oTrialAll;     // MAXT * 56 int
@@ -150,7 +149,6 @@ inline size_t eng_scratch_layout(EngScratch& sc, uint32_t maxwords, uint64_t max
     sc.oTabHash = take(sizeof(unsigned long long) * MAXT);
     sc.oTabs = take(sizeof(Tab) * (MAXT + ENG_NW));
     sc.oTileFirst = take(4 * (size_t)sc.maxtiles);
-    sc.oKind = take(maxn);
     sc.oMinfo = take(4 * maxn);
     sc.oPerm = take(4 * maxn);
     sc.oItems = take(4 * ((size_t)maxwords + 64));
@@ -176,7 +174,6 @@ struct Eng {
     uint32_t* hists;
     unsigned long long* tabHash;
     short* dc;
-    uint8_t* kind;
     uint32_t* minfo;
     uint32_t* tileFirst;
     int* trialAll;
@@ -336,7 +333,6 @@ struct Eng {
             const uint32_t rel = v.symout[i] - a0;
             const bool mt = sym_is_match(s);
             const uint32_t kq = mt ? (uint32_t)(sym_lensym(s) - 256) : 0u;
-            kind[i] = (uint8_t)kq;
             minfo[i] = mt ? ((s & 0x1FF) | ((uint32_t)dist_sym(sym_dist(s)) << 9) | (kq << 14) | ((rel & (DC_TILE - 1)) << 19)) : 0u;
             const uint32_t ti = rel / DC_TILE;
             const int tprev = i ? (int)((v.symout[i - 1] - a0) / DC_TILE) : -1;   // a symbol is shorter than a tile: ti - tprev <= 1
@@ -374,7 +370,7 @@ struct Eng {
         }
 #pragma unroll 1
         for (uint32_t i = v.n + tid; i < v.nwords * 32; i += ENG_NT) {
-            kind[i] = 0; minfo[i] = 0;
+            minfo[i] = 0;
         }
         __syncthreads();
     }
@@ -1674,7 +1670,6 @@ __device__ inline void eng_init(Eng& e, const EngScratch& sc, int cta) {
     e.hists = reinterpret_cast<uint32_t*>(base + sc.oHists);
     e.tabHash = reinterpret_cast<unsigned long long*>(base + sc.oTabHash);
     e.dc = reinterpret_cast<short*>(base + sc.oDc);
-    e.kind = base + sc.oKind;
     e.minfo = reinterpret_cast<uint32_t*>(base + sc.oMinfo);
     e.tileFirst = reinterpret_cast<uint32_t*>(base + sc.oTileFirst);
     e.trialAll = reinterpret_cast<int*>(base + sc.oTrialAll);

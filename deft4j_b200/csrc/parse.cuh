@@ -65,6 +65,56 @@ __device__ __forceinline__ int decode_sym(const DecTab& t, uint64_t w, int* len)
     return -1;
 }
 
+// Multi-bit lookup in front of the by-length decoder: slot i of the table holds what decode_sym finds in the bit pattern i
+// when a code of at most LUT bits matches ((len << 9) | symbol; 0: no such code).  Every slot is filled by running the
+// reference's first-match-by-length rule on its own index, so incomplete and over-subscribed length sets decode exactly
+// as Huffman.readSymbol does (Huffman.java:170-197); codes longer than the table fall through to decode_sym.
+constexpr int LUT_L_BITS = 10, LUT_D_BITS = 9;
+struct DecLut {
+    uint16_t lit[1 << LUT_L_BITS];
+    uint16_t dst[1 << LUT_D_BITS];
+};
+__device__ __forceinline__ void build_lut(const DecTab& t, uint16_t* lut, int bits, int tid, int nthreads) {
+    for (int i = tid; i < (1 << bits); i += nthreads) {
+        uint32_t code = 0, w = (uint32_t)i;
+        uint16_t e = 0;
+#pragma unroll 1
+        for (int l = 1; l <= bits; l++) {
+            code = (code << 1) | (w & 1u);
+            w >>= 1;
+            const uint32_t idx = code - t.first[l];
+            if (idx < t.count[l]) { e = (uint16_t)((l << 9) | t.symtab[t.offs[l] + idx]); break; }
+        }
+        lut[i] = e;
+    }
+}
+__device__ __forceinline__ int decode_sym_lut(const DecTab& t, const uint16_t* lut, int bits, uint64_t w, int* len) {
+    const uint32_t e = lut[(uint32_t)w & ((1u << bits) - 1u)];
+    if (e) { *len = (int)(e >> 9); return (int)(e & 511u); }
+    return decode_sym(t, w, len);
+}
+
+// ---- staging of the bitstream window in shared memory --------------------------------------------------------------
+// k_count decodes a window of PARSE_NT chunks at a time, speculatively and then again in the fix-up rounds: the
+// window's bytes are copied into shared memory once with cp.async (LDGSTS: global -> shared without passing through
+// registers) and every peek reads shared memory.  `avail` bytes of the source are valid; the rest is zero-filled.
+constexpr int WIN_BYTES = PARSE_NT * CHUNK_BITS / 8;      // 32 KiB
+constexpr int WIN_SLACK = 64;                              // a unit is <= 48 bits and a peek reads 16 bytes
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+// >= 57 valid bits starting at bit `rel` of the staged window
+__device__ __forceinline__ uint64_t peek_bits_smem(const uint8_t* win, uint32_t rel) {
+    const uint32_t byte = rel >> 3;
+    const uint64_t* q = (const uint64_t*)(win + (byte & ~7u));
+    const int sh = (int)(byte & 7u) * 8;
+    const uint64_t lo = q[0], hi = q[1];
+    const uint64_t w = sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+    return w >> (rel & 7u);
+}
+
 struct Unit {
     int nbits;       // bits consumed, 0 = decode error
     int outlen;      // decoded bytes produced
@@ -73,12 +123,16 @@ struct Unit {
 };
 
 // One literal / EOB / match unit (DeflateBlockHuffman.decodeStream, :778-890).
-__device__ __forceinline__ Unit decode_unit(const DecTab& lit, const DecTab& dst, const uint8_t* in, uint64_t pos) {
+__device__ __forceinline__ Unit decode_unit_w(const DecTab& lit, const DecTab& dst, const DecLut& lut, uint64_t w);
+__device__ __forceinline__ Unit decode_unit(const DecTab& lit, const DecTab& dst, const DecLut& lut, const uint8_t* in, uint64_t pos) {
+    return decode_unit_w(lit, dst, lut, peek_bits(in, pos));
+}
+// the same from the (>= 57) bits at the unit's position
+__device__ __forceinline__ Unit decode_unit_w(const DecTab& lit, const DecTab& dst, const DecLut& lut, uint64_t w) {
     Unit u;
     u.nbits = 0; u.outlen = 0; u.packed = 0; u.eob = 0;
-    uint64_t w = peek_bits(in, pos);
     int l;
-    int s = decode_sym(lit, w, &l);
+    int s = decode_sym_lut(lit, lut.lit, LUT_L_BITS, w, &l);
     if (s < 0 || s > 285) return u;
     if (s < 256) { u.nbits = l; u.outlen = 1; u.packed = (uint32_t)s; return u; }
     if (s == 256) { u.nbits = l; u.eob = 1; u.packed = 256; return u; }
@@ -89,7 +143,7 @@ __device__ __forceinline__ Unit decode_unit(const DecTab& lit, const DecTab& dst
     w >>= eb; nb += eb;
     int edge = (len == 258 && s == 284) ? 1 : 0;
     int dl;
-    int ds = decode_sym(dst, w, &dl);
+    int ds = decode_sym_lut(dst, lut.dst, LUT_D_BITS, w, &dl);
     if (ds < 0 || ds > 29) return u;
     w >>= dl; nb += dl;
     int deb = c_dist_ebits[ds];
@@ -322,12 +376,14 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
     }
 
     __shared__ DecTab s_lit, s_dst, s_fixlit, s_fixdst;
+    __shared__ DecLut s_lut, s_fixlut;
     __shared__ BlockRec s_blk;
     __shared__ uint32_t s_start[PARSE_NT], s_end[PARSE_NT], s_cnt[PARSE_NT], s_outb[PARSE_NT];
     __shared__ uint8_t s_flag[PARSE_NT];
     __shared__ uint32_t s_scan_cnt[PARSE_NT / 32], s_scan_out[PARSE_NT / 32];
     __shared__ int s_status, s_type, s_final, s_stop;
     __shared__ uint64_t s_pos;
+    extern __shared__ __align__(16) uint8_t s_win[];   // WIN_BYTES + WIN_SLACK + 16: the window being decoded
 
     if (t == 0) {
         // the fixed litlen CODES are those of the 288-entry RFC table (HuffmanTable.java:183-186 skips two
@@ -340,6 +396,9 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
         s_status = ST_OK;
         s_pos = sd.start_bit;
     }
+    __syncthreads();
+    build_lut(s_fixlit, s_fixlut.lit, LUT_L_BITS, t, PARSE_NT);
+    build_lut(s_fixdst, s_fixlut.dst, LUT_D_BITS, t, PARSE_NT);
     __syncthreads();
 
     uint64_t n_syms = 0, out_total = 0, n_chunks = 0;
@@ -412,11 +471,30 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
         if (type != 0) {
             const DecTab& lit = (type == 1) ? s_fixlit : s_lit;
             const DecTab& dst = (type == 1) ? s_fixdst : s_dst;
+            if (type == 2) {   // the block's own lookup tables
+                build_lut(s_lit, s_lut.lit, LUT_L_BITS, t, PARSE_NT);
+                build_lut(s_dst, s_lut.dst, LUT_D_BITS, t, PARSE_NT);
+                __syncthreads();
+            }
+            const DecLut& lut = (type == 1) ? s_fixlut : s_lut;
             const uint64_t data_bit = s_blk.data_bit;
             uint64_t win = data_bit;  // true symbol boundary
             int64_t payload = 0;
             bool eob_seen = false;
             while (!eob_seen) {
+                // ---- the window's bytes -> shared memory (cp.async), 16-byte aligned source --------------
+                const uint64_t wbyte = (win >> 3) & ~15ull;
+                {
+                    const int64_t valid = (int64_t)(sd.in_len + 32) - (int64_t)wbyte;   // bytes of the stream (+ its zero padding) from here
+                    for (int o = t * 16; o < WIN_BYTES + WIN_SLACK + 16; o += PARSE_NT * 16) {
+                        const int64_t left = valid - o;
+                        const int nb = left >= 16 ? 16 : left > 0 ? (int)left : 0;
+                        cp_async16(s_win + o, in + wbyte + (nb ? o : 0), nb);
+                    }
+                    cp_async_wait_all();
+                    __syncthreads();
+                }
+                const uint32_t wrel = (uint32_t)(win - wbyte * 8);   // bit offset of the window start inside the staged bytes
                 // ---- speculative decode of one window ----------------------------------------------
                 uint32_t start = (uint32_t)t * CHUNK_BITS;
                 const uint32_t limit = (uint32_t)(t + 1) * CHUNK_BITS;
@@ -430,7 +508,7 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
                         while (p < limit) {
                             uint64_t abs = win + p;
                             if (abs >= total_bits) { flag = 2; break; }
-                            Unit u = decode_unit(lit, dst, in, abs);
+                            Unit u = decode_unit_w(lit, dst, lut, peek_bits_smem(s_win, wrel + p));
                             if (u.nbits == 0 || abs + u.nbits > total_bits) { flag = 2; break; }
                             p += u.nbits; cnt++; outb += u.outlen;
                             if (u.eob) { flag = 1; break; }
@@ -588,6 +666,7 @@ k_emit(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, c
         return;
     }
     __shared__ DecTab s_lit, s_dst;
+    __shared__ DecLut s_lut;
     if (t == 0) {
         if (b.type == 1) {
             uint8_t L[MAX_LL], D[MAX_D];
@@ -600,6 +679,9 @@ k_emit(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, c
     }
     if (t == 32) build_dectab(b.tab.D, b.tab.nD, s_dst);
     __syncthreads();
+    build_lut(s_lit, s_lut.lit, LUT_L_BITS, t, (int)blockDim.x);
+    build_lut(s_dst, s_lut.dst, LUT_D_BITS, t, (int)blockDim.x);
+    __syncthreads();
     const uint64_t symb = sd.sym_base + b.sym_base, outb = sd.out_base + b.out_base;
     for (uint32_t c = t; c < b.n_chunks; c += blockDim.x) {
         const ChunkRec r = chunks[sd.chunk_base + b.chunk_base + c];
@@ -607,7 +689,7 @@ k_emit(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, c
         uint64_t si = symb + r.sym_idx;
         uint32_t oo = (uint32_t)(outb + r.out_off);
         for (uint32_t k = 0; k < r.n; k++) {
-            Unit u = decode_unit(s_lit, s_dst, in, pos);
+            Unit u = decode_unit(s_lit, s_dst, s_lut, in, pos);
             pos += u.nbits;
             sym[si + k] = u.packed;
             symout[si + k] = oo;

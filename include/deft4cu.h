@@ -137,6 +137,9 @@ void deft4cu_device_batch_free(deft4cu_device_batch* b);
  * ---------------------------------------------------------------------------------------------- */
 int  deft4cu_debug_trace_begin(uint32_t cap_pairs);
 int  deft4cu_debug_trace_end(int64_t* dst_pairs, uint32_t cap_pairs, uint32_t* n_pairs);
+/* Launches of the candidate engine kernel since the library was loaded: DeflateFilesContainer.optimise's stream list
+ * (DeflateFilesContainer.java:18-43) is meant to cost one. */
+uint64_t deft4cu_debug_engine_launches(void);
 /* Engine phase cycle counters (only in a -DD4_PROF build of the library; DEFT4CU_ERR_ARG otherwise):
  * dst[c] = cycles, dst[32 + c] = calls for phase category c (engine.cuh PR_*). */
 int  deft4cu_debug_prof(uint64_t* dst, uint32_t n, int reset);

@@ -519,3 +519,48 @@ def test_zip_container_and_cli_on_the_gpu(gpu, oracle, tmp_path, capsys):
     assert main(["optimise", os.path.join(os.path.dirname(__file__), "golden", "asyoulik", "asyoulik-gzip.txt.gz"), str(dst)]) == 0
     assert dst.read_bytes() == read_golden("asyoulik/asyoulik-gzip-opt.txt.gz")
     assert "167 bits saved in stream 0" in capsys.readouterr().out
+
+
+# ---- the stream LIST is the batch: one launch of the candidate engine per container / folder / list -------------------
+def test_container_list_is_one_device_batch(gpu, tmp_path, capsys):
+    """DeflateFilesContainer.optimise hands a list of streams over (DeflateFilesContainer.java:18-43): ball.png's 20
+    zlib streams, parsed one by one by the PNG reader, must reach the candidate engine as ONE launch; the same for the
+    files of `optimise-folder`; output identical to the reference's goldens either way."""
+    import shutil
+    from deft4j_b200 import _native
+    from deft4j_b200.container import getContainerForBytes
+    from deft4j_b200.__main__ import main
+    L = _native.lib()
+    data = read_golden("apng/ball.png")
+    cont = getContainerForBytes(data, "ball.png", gpu.DeflateStream)
+    assert cont.read(data) and len(cont.getDeflateStreams()) >= 20
+    n0 = L.deft4cu_debug_engine_launches()
+    cont.optimise(True, None)
+    assert L.deft4cu_debug_engine_launches() - n0 == 1
+    assert cont.write() == read_golden("apng/ball-opt.png")
+    # a folder with several kinds of files: one launch for all of them, every file as the reference writes it
+    pairs = [("apng/ball.png", "apng/ball-opt.png"), ("text.png", "text-opt.png"), ("lz-twice-twice.txt.gz", "lz-twice-twice-opt.txt.gz"),
+             ("asyoulik/asyoulik-gzip.txt.gz", "asyoulik/asyoulik-gzip-opt.txt.gz"), ("284-edge-case/284.png", "284-edge-case/284-opt.png")]
+    for inp, _ in pairs:
+        shutil.copyfile(os.path.join(os.path.dirname(__file__), "golden", inp), tmp_path / os.path.basename(inp))
+    n0 = L.deft4cu_debug_engine_launches()
+    assert main(["optimise-folder", str(tmp_path)]) == 0
+    assert L.deft4cu_debug_engine_launches() - n0 == 1
+    for inp, gold in pairs:
+        assert (tmp_path / os.path.basename(inp)).read_bytes() == read_golden(gold), inp
+    out = capsys.readouterr().out
+    assert "167 bits saved in stream 0" in out and out.count("Optimising file") == len(pairs)
+
+
+def test_batches_beyond_the_decoded_limit_are_split(gpu, oracle, monkeypatch):
+    """Decoded offsets are 32-bit, so one device batch holds less than 4 GiB of decoded data; a larger list is split
+    (streams never interact).  The limit is lowered to force the split on a small list."""
+    streams = W.c4_streams(9, seed=21)
+    ref = gpu.optimise_batch(streams, True)
+    monkeypatch.setenv("D4_MAX_DECODED", "150000")
+    res = gpu.optimise_batch(streams, True)
+    hs = gpu.DeflateStream.parse_batch(streams[:4])
+    monkeypatch.delenv("D4_MAX_DECODED")
+    for a, b in zip(res, ref):
+        assert (a["status"], a["saved_bits"], a["out"], a["crc32"]) == (b["status"], b["saved_bits"], b["out"], b["crc32"])
+    assert any(r["status"] == 0 for r in res)
