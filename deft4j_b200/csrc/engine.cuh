@@ -56,7 +56,9 @@ struct BlkView {
 };
 
 constexpr int DC_TILE = 512;      // decoded bytes per cost-array tile: one 16-byte load per lane of a warp
-constexpr int DCN = 16;           // cost arrays kept per block (round-robin eviction)
+constexpr int DCN = 16;           // per-table sign masks kept per block (round-robin eviction)
+constexpr int LCN = 12;           // literal-cost arrays kept per block (round-robin eviction)
+constexpr int MAXLIT = 64;        // distinct sets of literal code lengths tracked per block
 constexpr int WS_BYTES = 3072;    // per-warp workspace for trees / header work
 constexpr int HQS = 4608, HQL = 1024;   // queue of freshly replaced matches (all / long ones) for the histogram update
 constexpr int SLOT_B = MAXM, SLOT_BEST = MAXM + 1;   // extra mask / histogram slots: the records of B and of the winner
@@ -76,7 +78,7 @@ __device__ unsigned long long g_prof[64];
 #endif
 enum { PR_BLOCK = 0, PR_ROUND, PR_SWEEP, PR_SELECT, PR_PASS, PR_DC, PR_RECODE, PR_TREES, PR_HDR_DEFAULT, PR_HDROP, PR_TRIALS,
        PR_LOAD, PR_MATERIAL, PR_REBASE, PR_INTERN_MASK, PR_INTERN_TAB, PR_FIXED, PR_SLOWTREE, PR_SEGMENTED, PR_HIST,
-       PR_PASS_MAIN, PR_PASS_HQ, PR_LEAST_APPLY, PR_PASS_LEAST };
+       PR_PASS_MAIN, PR_PASS_HQ, PR_LEAST_APPLY, PR_PASS_LEAST, PR_MASKS };
 
 struct EngSmem {
     SymState sym;
@@ -97,9 +99,16 @@ struct EngSmem {
     int redAny, redAny2, tmpIdx, err;
     int sweepOk[4], segImproved, segmentedRound;
     struct { long long bestSize, restMin; SC best; unsigned bestIndex, candIndex; int bestStored, bestArg; } carry;   // selection state carried into a sweep
-    unsigned char tabDc[MAXT];   // tabid -> cost-array slot (0xFF: none)
+    unsigned char tabDc[MAXT];   // tabid -> sign-mask slot (0xFF: none)
     unsigned short dcOwner[DCN]; // slot -> tabid (0xFFFF: free)
     int dcNext;
+    // literal-cost arrays are shared by all tables with the same literal code lengths
+    unsigned char tabLit[MAXT];          // tabid -> literal set (0xFF: not looked up yet)
+    unsigned long long litHash[MAXLIT];  // literal set -> hash of its 256 code lengths
+    unsigned short litRep[MAXLIT];       // ... a table that has it
+    unsigned char litSlot[MAXLIT];       // ... its cost-array slot (0xFF: none)
+    unsigned char slotLit[LCN];          // slot -> literal set (0xFF: free)
+    int nLit, litNext;
     uint32_t ctab[256];          // cost-array build: literal code lengths (0x10000 = no code: counted apart)
     uint8_t refL[32], refD[32];  // cost of a match's length symbol / distance symbol incl. extra bits
     union alignas(16) {
@@ -126,7 +135,8 @@ struct EngScratch {
     size_t oHdrs;         // MAXH Hdr
     size_t oHists;        // (MAXM + 2) * 320 u32
     size_t oTabHash;      // MAXT u64
-    size_t oDc;           // DCN * maxwords * 32 short
+    size_t oDc;           // LCN * maxwords * 32 short: literal-cost arrays
+    size_t oKd;           // maxwords * 32 u16: per symbol, (length symbol - 256) | distance symbol << 5 (0: not a match)
     size_t oMinfo;        // maxwords * 32 u32
     size_t oTileFirst;    // maxtiles u32
     size_t oTrialAll;     // MAXT * 56 int
@@ -152,7 +162,8 @@ inline size_t eng_scratch_layout(EngScratch& sc, uint32_t maxwords, uint64_t max
     sc.oMinfo = take(4 * maxn);
     sc.oPerm = take(4 * maxn);
     sc.oItems = take(4 * ((size_t)maxwords + 64));
-    sc.oDc = take(2 * maxn * DCN);
+    sc.oDc = take(2 * maxn * LCN);
+    sc.oKd = take(2 * maxn);
     sc.oDcBits = take(4 * (size_t)maxwords * 2 * DCN);
     sc.oMasks = take(4 * (size_t)(MAXM + 2) * maxwords);
     sc.oHists = take(4 * (size_t)(MAXM + 2) * 320);
@@ -173,7 +184,8 @@ struct Eng {
     Hdr* hdrs;
     uint32_t* hists;
     unsigned long long* tabHash;
-    short* dc;
+    short* dc;            // literal-cost arrays (LCN slots of maxn)
+    uint16_t* kd;         // per symbol: (length symbol - 256) | distance symbol << 5; 0 = not a match
     uint32_t* minfo;
     uint32_t* tileFirst;
     int* trialAll;
@@ -333,7 +345,9 @@ struct Eng {
             const uint32_t rel = v.symout[i] - a0;
             const bool mt = sym_is_match(s);
             const uint32_t kq = mt ? (uint32_t)(sym_lensym(s) - 256) : 0u;
-            minfo[i] = mt ? ((s & 0x1FF) | ((uint32_t)dist_sym(sym_dist(s)) << 9) | (kq << 14) | ((rel & (DC_TILE - 1)) << 19)) : 0u;
+            const uint32_t dsy = mt ? (uint32_t)dist_sym(sym_dist(s)) : 0u;
+            minfo[i] = mt ? ((s & 0x1FF) | (dsy << 9) | (kq << 14) | ((rel & (DC_TILE - 1)) << 19)) : 0u;
+            kd[i] = (uint16_t)(kq | (dsy << 5));
             const uint32_t ti = rel / DC_TILE;
             const int tprev = i ? (int)((v.symout[i - 1] - a0) / DC_TILE) : -1;   // a symbol is shorter than a tile: ti - tprev <= 1
             if ((int)ti != tprev) tileFirst[ti] = i;
@@ -370,7 +384,7 @@ struct Eng {
         }
 #pragma unroll 1
         for (uint32_t i = v.n + tid; i < v.nwords * 32; i += ENG_NT) {
-            minfo[i] = 0;
+            minfo[i] = 0; kd[i] = 0;
         }
         __syncthreads();
     }
@@ -432,9 +446,10 @@ struct Eng {
         __syncthreads();
         sym_reset(ES->sym, tid, ENG_NT);
 #pragma unroll 1
-        for (int k = tid; k < MAXT; k += ENG_NT) ES->tabDc[k] = 0xFF;
+        for (int k = tid; k < MAXT; k += ENG_NT) { ES->tabDc[k] = 0xFF; ES->tabLit[k] = 0xFF; }
         if (tid < DCN) ES->dcOwner[tid] = 0xFFFF;
-        if (tid == 0) ES->dcNext = 0;
+        if (tid < LCN) ES->slotLit[tid] = 0xFF;
+        if (tid == 0) { ES->dcNext = 0; ES->nLit = 0; ES->litNext = 0; }
         Tab& f = tabs[TAB_FIXED];
 #pragma unroll 1
         for (int k = tid; k < MAX_LL; k += ENG_NT) f.L[k] = (k < 286) ? ((k <= 143) ? 8 : (k <= 255) ? 9 : (k <= 279) ? 7 : 8) : 0;
@@ -520,41 +535,90 @@ struct Eng {
 
     // ---- cost arrays ------------------------------------------------------------------------------------------------
 
-    // dc[i] = (literal cost of match i's bytes) - (cost of the match) under table `t`, DC_BLOCKED when a byte has no code
-    // (DeflateBlockHuffman.java:238-246).  It does not depend on the mask, so every replace / least pass under the same
-    // tables reads it.  ONE coalesced pass over the block's decoded bytes: every warp streams its own run of 512-byte
-    // tiles (a 128-bit load per lane, code lengths looked up in shared memory, a warp-wide prefix sum into its slice of
-    // shared memory) and every match that starts in a tile takes P[end] - P[start]; the one match that crosses the
-    // tile's end is finished from the next tile.  No CTA barrier inside.
-    __device__ __noinline__ const short* ensure_dc(int t) {
-        int slot = ES->tabDc[t];
+    // The cost of a match under table T splits into  lit[i] - refL[length symbol] - refD[distance symbol]:
+    //   lit[i]  = sum of the literal code lengths of the match's bytes, DC_BLOCKED when a byte has no code
+    //             (DeflateBlockHuffman.java:238-246) - a function of the 256 literal lengths alone.  Most of the tables a
+    //             block meets differ in a few length / distance symbols only (measured: 22 of 30 new tables share their
+    //             literal lengths with an earlier one), so the arrays are cached per SET OF LITERAL LENGTHS.
+    //   refL/D  = code length + extra bits of the two symbols a match is written with: two 32-entry tables per T.
+    // Per table only the sign masks (entry < 0, entry == 0) are materialised, by a short streaming pass.
+
+    // refL / refD of table t -> shared memory
+    __device__ __forceinline__ void load_ref(int t) {
+        const Tab& tb = tabs[t];
+        if (tid < 32) ES->refL[tid] = (uint8_t)(tb.L[256 + tid] + (tid > 0 && tid < 30 ? len_ebits_of(256 + tid) : 0));
+        else if (tid < 64) ES->refD[tid - 32] = (uint8_t)(tb.D[tid - 32] + (tid - 32 < 30 ? dist_ebits_of(tid - 32) : 0));
+    }
+    // cost-array entry of symbol i under the table whose refL / refD are loaded
+    __device__ __forceinline__ int dc_val(const short* lit, uint32_t i) const {
+        const int x = lit[i];
+        if (x == DC_BLOCKED) return DC_BLOCKED;
+        const uint32_t k = kd[i];
+        return x - ES->refL[k & 31] - ES->refD[k >> 5];
+    }
+
+    // the literal-cost array of table t's literal lengths.  ONE coalesced pass over the block's decoded bytes when it is
+    // not cached: every warp streams its own run of 512-byte tiles (a 128-bit load per lane, code lengths looked up in
+    // shared memory, a warp-wide prefix sum into its slice of shared memory) and every match that starts in a tile takes
+    // P[end] - P[start]; the one match that crosses the tile's end is finished from the next tile.
+    __device__ __noinline__ const short* ensure_lit(int t) {
+        int ls = ES->tabLit[t];
+        if (ls == 0xFF) {   // which set of literal lengths is this?
+            __syncthreads();
+            const uint32_t* q = (const uint32_t*)tabs[t].L;
+            unsigned long long hh = 0;
+            if (tid < 64) {
+                unsigned long long x = (unsigned long long)q[tid] + 0x9E3779B97F4A7C15ull * (unsigned long long)(tid + 1);
+                x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+                hh = x;
+            }
+            const unsigned long long h = cta_sum64(hh);
+            if (tid == 0) ES->tmpIdx = -1;
+            __syncthreads();
+            const int nl = ES->nLit;
+#pragma unroll 1
+            for (int k = 0; k < nl; k++) {   // few sets: one after the other, confirmed by a full comparison
+                if (ES->litHash[k] != h) continue;
+                const uint32_t* r = (const uint32_t*)tabs[ES->litRep[k]].L;
+                const int diff = __syncthreads_or(tid < 64 && r[tid] != q[tid]);
+                if (!diff) { if (tid == 0) ES->tmpIdx = k; break; }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int k = ES->tmpIdx;
+                if (k < 0) {
+                    if (ES->nLit == MAXLIT) {   // table of sets full: forget all of them (and their arrays)
+                        ES->nLit = 0;
+                        for (int j = 0; j < MAXT; j++) ES->tabLit[j] = 0xFF;
+                        for (int j = 0; j < LCN; j++) ES->slotLit[j] = 0xFF;
+                    }
+                    k = ES->nLit++;
+                    ES->litHash[k] = h; ES->litRep[k] = (unsigned short)t; ES->litSlot[k] = 0xFF;
+                }
+                ES->tabLit[t] = (unsigned char)k;
+            }
+            __syncthreads();
+            ls = ES->tabLit[t];
+        }
+        int slot = ES->litSlot[ls];
         if (slot != 0xFF) return dc + (size_t)slot * maxn;
         P0();
         __syncthreads();  // every thread has seen the miss before thread 0 records the new slot
         if (tid == 0) {
-            slot = ES->dcNext;
-            ES->dcNext = (slot + 1) % DCN;
-            const int owner = ES->dcOwner[slot];
-            if (owner != 0xFFFF) ES->tabDc[owner] = 0xFF;
-            ES->dcOwner[slot] = (unsigned short)t;
-            ES->tabDc[t] = (unsigned char)slot;
+            slot = ES->litNext;
+            ES->litNext = (slot + 1) % LCN;
+            const int owner = ES->slotLit[slot];
+            if (owner != 0xFF) ES->litSlot[owner] = 0xFF;
+            ES->slotLit[slot] = (unsigned char)ls;
+            ES->litSlot[ls] = (unsigned char)slot;
             ES->tmpIdx = slot;
         }
         const Tab& tb = tabs[t];
 #pragma unroll 1
-        for (int k = tid; k < 256 + 32 + 32; k += ENG_NT) {
-            if (k < 256) { const uint32_t c = tb.L[k]; ES->ctab[k] = c ? c : 0x10000u; }
-            else if (k < 288) ES->refL[k - 256] = (uint8_t)(tb.L[k] + (k > 256 && k < 286 ? len_ebits_of(k) : 0));
-            else ES->refD[k - 288] = (uint8_t)(tb.D[k - 288] + (k - 288 < 30 ? dist_ebits_of(k - 288) : 0));
-        }
+        for (int k = tid; k < 256; k += ENG_NT) { const uint32_t c = tb.L[k]; ES->ctab[k] = c ? c : 0x10000u; }
         __syncthreads();
         slot = ES->tmpIdx;
         short* d = dc + (size_t)slot * maxn;
-        uint32_t* negW = dcBits + (size_t)slot * 2 * maxwords;   // bit i: entry i < 0;  + maxwords: entry i == 0
-        uint32_t* zerW = negW + maxwords;
-#pragma unroll 1
-        for (uint32_t k = tid; k < v.nwords; k += ENG_NT) { negW[k] = 0; zerW[k] = 0; }
-        __syncthreads();
         const uint32_t a0 = (uint32_t)(v.out_off & ~15ull);
         const uint32_t head = (uint32_t)(v.out_off - a0);
         const uint32_t endRel = head + (uint32_t)v.ulen;
@@ -570,7 +634,7 @@ struct Eng {
         // l's first byte: the prefix at byte k is LB[k / 16] + P[k] (P[DC_TILE] = 0, LB[32] = tile total).
         constexpr int DC_PRE = 4;
         uint32_t* LB = P + DC_TILE + 4;
-        int carryIdx = -1, carryRef = 0;
+        int carryIdx = -1;
         uint32_t carryPart = 0, carryEnd = 0;
         uint4 q = make_uint4(0, 0, 0, 0);
         uint32_t i0 = 0, i1 = 0, i2 = 0;       // symbols of the current tile: [i0, i1); of the next one: [i1, i2)
@@ -586,31 +650,16 @@ struct Eng {
         }
         if (lane == 0) P[DC_TILE] = 0;
 #define D4_PFX(k) (LB[(k) >> 4] + P[(k)])
-        // one symbol record: a match inside the tile gets its cost (val_), the one that crosses the tile's end is remembered
-#define D4_DC_ONE(i_, m_, val_)                                                                                  \
+        // one symbol record: a match inside the tile gets its literal cost, the one that crosses the tile's end is remembered
+#define D4_DC_ONE(i_, m_)                                                                                        \
         do {                                                                                                     \
             const uint32_t mm = (m_);                                                                            \
-            const int kq = (int)((mm >> 14) & 31);                                                               \
-            val_ = DC_NOT_MATCH;                                                                                 \
-            if (kq) {                                                                                            \
+            if ((mm >> 14) & 31) {                                                                               \
                 const uint32_t s0 = (mm >> 19) & (DC_TILE - 1), e = s0 + (mm & 0x1FF) + 3;                       \
-                const int ref = ES->refL[kq] + ES->refD[(mm >> 9) & 31];                                         \
                 if (e <= DC_TILE) {                                                                              \
                     const uint32_t y = D4_PFX(e) - D4_PFX(s0);                                                   \
-                    val_ = (y >> 16) ? DC_BLOCKED : (short)((int)(y & 0xffffu) - ref);                           \
-                    d[(i_)] = val_;                                                                              \
-                } else { nIdx = (int)(i_); nRef = ref; nPart = LB[32] - D4_PFX(s0); nEnd = e - DC_TILE; }        \
-            }                                                                                                    \
-        } while (0)
-        // the 32 lanes hold the entries of symbols first .. first + 31: their sign / zero bits go out with two atomics
-#define D4_DC_BITS(first_, val_)                                                                                 \
-        do {                                                                                                     \
-            const unsigned bn = __ballot_sync(0xffffffffu, (val_) < 0), bz = __ballot_sync(0xffffffffu, (val_) == 0); \
-            if (lane == 0 && (bn | bz)) {                                                                        \
-                const uint32_t w0 = (first_) >> 5;                                                               \
-                const int sh = (int)((first_) & 31);                                                             \
-                if (bn) { atomicOr(&negW[w0], bn << sh); if (sh && (bn >> (32 - sh))) atomicOr(&negW[w0 + 1], bn >> (32 - sh)); } \
-                if (bz) { atomicOr(&zerW[w0], bz << sh); if (sh && (bz >> (32 - sh))) atomicOr(&zerW[w0 + 1], bz >> (32 - sh)); } \
+                    d[(i_)] = (y >> 16) ? DC_BLOCKED : (short)(y & 0xffffu);                                     \
+                } else { nIdx = (int)(i_); nPart = LB[32] - D4_PFX(s0); nEnd = e - DC_TILE; }                    \
             }                                                                                                    \
         } while (0)
         // one tile past the warp's run finishes its last crossing match
@@ -665,47 +714,90 @@ struct Eng {
             __syncwarp();
             if (lane == 0 && carryIdx >= 0) {
                 const uint32_t y = carryPart + D4_PFX(carryEnd);
-                const short cv = (y >> 16) ? DC_BLOCKED : (short)((int)(y & 0xffffu) - carryRef);
-                d[carryIdx] = cv;
-                if (cv < 0) atomicOr(&negW[carryIdx >> 5], 1u << (carryIdx & 31));
-                if (cv == 0) atomicOr(&zerW[carryIdx >> 5], 1u << (carryIdx & 31));
+                d[carryIdx] = (y >> 16) ? DC_BLOCKED : (short)(y & 0xffffu);
                 carryIdx = -1;
             }
             if (!extra) {
-                int nIdx = -1, nRef = 0;
+                int nIdx = -1;
                 uint32_t nPart = 0, nEnd = 0;
                 const uint32_t ib = ci0 + (uint32_t)lane;
-                short v0, v1, v2, v3;
-                D4_DC_ONE(ib, c0, v0);      D4_DC_BITS(ci0, v0);
-                D4_DC_ONE(ib + 32, c1, v1); D4_DC_BITS(ci0 + 32, v1);
-                D4_DC_ONE(ib + 64, c2, v2); D4_DC_BITS(ci0 + 64, v2);
-                D4_DC_ONE(ib + 96, c3, v3); D4_DC_BITS(ci0 + 96, v3);
+                D4_DC_ONE(ib, c0);
+                D4_DC_ONE(ib + 32, c1);
+                D4_DC_ONE(ib + 64, c2);
+                D4_DC_ONE(ib + 96, c3);
 #pragma unroll 1
-                for (uint32_t fb = ci0 + 32u * DC_PRE; fb < ci1; fb += 32) {   // many short symbols: the rest of the tile
-                    const uint32_t i = fb + (uint32_t)lane;
-                    const uint32_t mx = i < ci1 ? minfo[i] : 0u;
-                    short vx;
-                    D4_DC_ONE(i, mx, vx);
-                    D4_DC_BITS(fb, vx);
-                }
+                for (uint32_t i = ib + 32u * DC_PRE; i < ci1; i += 32) { const uint32_t mx = minfo[i]; D4_DC_ONE(i, mx); }   // many short symbols
                 // hand the crossing match (if any) to lane 0
                 const unsigned who = __ballot_sync(0xffffffffu, nIdx >= 0);
                 if (who) {
                     const int src = __ffs((int)who) - 1;
                     carryIdx = __shfl_sync(0xffffffffu, nIdx, src);
-                    carryRef = __shfl_sync(0xffffffffu, nRef, src);
                     carryPart = __shfl_sync(0xffffffffu, nPart, src);
                     carryEnd = __shfl_sync(0xffffffffu, nEnd, src);
                 }
             }
             __syncwarp();
         }
-#undef D4_DC_BITS
 #undef D4_DC_ONE
 #undef D4_PFX
         __syncthreads();
         P1(PR_DC);
         return d;
+    }
+
+    // the sign masks of table t's cost array: bit i of negW / zerW = entry i is negative / zero.  One streaming pass over
+    // the literal costs and the symbols' (length symbol, distance symbol) pairs, eight symbols (one mask byte) per thread
+    // and step.  Leaves refL / refD of t in shared memory.
+    __device__ __noinline__ const uint32_t* ensure_masks(int t, const short* lit) {
+        load_ref(t);
+        int slot = ES->tabDc[t];
+        __syncthreads();
+        if (slot != 0xFF) return dcBits + (size_t)slot * 2 * maxwords;
+        P0();
+        if (tid == 0) {
+            slot = ES->dcNext;
+            ES->dcNext = (slot + 1) % DCN;
+            const int owner = ES->dcOwner[slot];
+            if (owner != 0xFFFF) ES->tabDc[owner] = 0xFF;
+            ES->dcOwner[slot] = (unsigned short)t;
+            ES->tabDc[t] = (unsigned char)slot;
+            ES->tmpIdx = slot;
+        }
+        __syncthreads();
+        slot = ES->tmpIdx;
+        uint32_t* negW = dcBits + (size_t)slot * 2 * maxwords;
+        uint8_t* negB = (uint8_t*)negW;
+        uint8_t* zerB = (uint8_t*)(negW + maxwords);
+        const uint32_t end = v.nwords * 32;
+        uint32_t i0 = (uint32_t)tid * 8;
+        uint4 lq = make_uint4(0, 0, 0, 0), kq = lq;
+        if (i0 < end) { kq = *(const uint4*)(kd + i0); lq = *(const uint4*)(lit + i0); }
+#pragma unroll 1
+        while (i0 < end) {
+            const uint4 cl = lq, ck = kq;
+            const uint32_t nx = i0 + ENG_NT * 8;
+            if (nx < end) { kq = *(const uint4*)(kd + nx); lq = *(const uint4*)(lit + nx); }
+            uint32_t nb = 0, zb = 0;
+            if (ck.x | ck.y | ck.z | ck.w) {
+                const uint32_t lw[4] = {cl.x, cl.y, cl.z, cl.w}, kw[4] = {ck.x, ck.y, ck.z, ck.w};
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t k = (u & 1) ? (kw[u >> 1] >> 16) : (kw[u >> 1] & 0xffffu);
+                    const int x = (int)(short)((u & 1) ? (lw[u >> 1] >> 16) : (lw[u >> 1] & 0xffffu));
+                    if (k && x != DC_BLOCKED) {
+                        const int val = x - ES->refL[k & 31] - ES->refD[k >> 5];
+                        nb |= (val < 0 ? 1u : 0u) << u;
+                        zb |= (val == 0 ? 1u : 0u) << u;
+                    }
+                }
+            }
+            negB[i0 >> 3] = (uint8_t)nb;
+            zerB[i0 >> 3] = (uint8_t)zb;
+            i0 = nx;
+        }
+        __syncthreads();
+        P1(PR_MASKS);
+        return negW;
     }
 
     // match i leaves the symbol list and its bytes enter it as literals: histogram delta in ES->hist
@@ -790,10 +882,10 @@ struct Eng {
     // only read for the (few) matches that are replaced.
     __device__ __noinline__ void pass_replace(int slot, int mid, int tabid, bool prune) {
         if (ES->sym.nMasks >= MAXM) { if (tid == 0) ES->sym.overflow = 1; __syncthreads(); return; }
-        const short* d = ensure_dc(tabid);
-        P0();
-        const uint32_t* negW = dcBits + (size_t)ES->tabDc[tabid] * 2 * maxwords;
+        const short* d = ensure_lit(tabid);
+        const uint32_t* negW = ensure_masks(tabid, d);   // (also loads the table's refL / refD)
         const uint32_t* zerW = negW + maxwords;
+        P0();
 #pragma unroll 1
         for (int k = tid; k < 320; k += ENG_NT) ES->hist[k] = 0;
         if (tid == 0) { ES->red = 0; ES->redAny = 0; ES->u.hq.nS = 0; ES->u.hq.nL = 0; }
@@ -820,7 +912,7 @@ struct Eng {
                         if (b0 != b1) hsh += mask_byte_hash(b1, 4 * k + q) - mask_byte_hash(b0, 4 * k + q);
                     }
 #pragma unroll 1
-                    for (uint32_t b = cand; b; b &= b - 1) saved -= d[32 * k + (uint32_t)__ffs((int)b) - 1];
+                    for (uint32_t b = cand; b; b &= b - 1) saved -= dc_val(d, 32 * k + (uint32_t)__ffs((int)b) - 1);
                 }
             }
             if (__any_sync(0xffffffffu, cand != 0)) { hq_push_warp(cand, 32 * k, lane); any |= cand != 0; }
@@ -855,7 +947,8 @@ struct Eng {
     // to the shared bins when the length symbol changes - a handful of atomics per thread, no warp-wide voting.
     __device__ __noinline__ void pass_least(int slot0, int slot1, int mid, int tabid) {
         if (ES->sym.nMasks + 2 > MAXM) { if (tid == 0) ES->sym.overflow = 1; __syncthreads(); return; }
-        const short* d = ensure_dc(tabid);
+        const short* d = ensure_lit(tabid);
+        load_ref(tabid);
         P0();
         if (tid < 32) { ES->leastSum[tid] = 0; ES->leastCnt[tid] = 0; }
         if (tid == 0) { ES->leastBlocked = 0; ES->leastSeen = 0; }
@@ -880,14 +973,14 @@ struct Eng {
 #pragma unroll
                     for (int u = 0; u < 8; u++) idx[u] = j + u < jend ? perm[j + u] : 0u;
 #pragma unroll
-                    for (int u = 0; u < 8; u++) { xv[u] = d[idx[u]]; mk[u] = mbytes[idx[u] >> 3]; }
+                    for (int u = 0; u < 8; u++) { xv[u] = d[idx[u]]; mk[u] = mbytes[idx[u] >> 3] | ((uint32_t)kd[idx[u]] << 8); }
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         const bool live = j + u < jend && !((mk[u] >> (idx[u] & 7)) & 1);   // still a match
                         seen |= live;
                         const bool blk = live && xv[u] == DC_BLOCKED;
                         blocked |= blk;
-                        if (live && !blk) { sum += xv[u]; cnt++; }
+                        if (live && !blk) { sum += xv[u] - ES->refL[bin + 1] - ES->refD[mk[u] >> 13]; cnt++; }
                     }
                 }
                 if (seen) atomicOr(&ES->leastSeen, 1u << bin);
@@ -1670,6 +1763,7 @@ __device__ inline void eng_init(Eng& e, const EngScratch& sc, int cta) {
     e.hists = reinterpret_cast<uint32_t*>(base + sc.oHists);
     e.tabHash = reinterpret_cast<unsigned long long*>(base + sc.oTabHash);
     e.dc = reinterpret_cast<short*>(base + sc.oDc);
+    e.kd = reinterpret_cast<uint16_t*>(base + sc.oKd);
     e.minfo = reinterpret_cast<uint32_t*>(base + sc.oMinfo);
     e.tileFirst = reinterpret_cast<uint32_t*>(base + sc.oTileFirst);
     e.trialAll = reinterpret_cast<int*>(base + sc.oTrialAll);

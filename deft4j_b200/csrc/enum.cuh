@@ -48,7 +48,7 @@ namespace d4 {
 #ifdef D4_SMALL_POOLS           // stress build: ordinary inputs overflow the pools, which forces the segmented rounds
 constexpr int MAXM = 96, MAXT = 96, MAXH = 192, PMEMO = 256;
 #else
-constexpr int MAXM = 256;     // distinct symbol-list masks kept per block
+constexpr int MAXM = 192;     // distinct symbol-list masks kept per block (a C2 block meets ~65 in its two rounds)
 constexpr int MAXT = 256;     // distinct code tables kept per block
 constexpr int MAXH = 512;     // dynamic headers kept per block
 constexpr int PMEMO = 512;    // pass memo slots (open addressing)

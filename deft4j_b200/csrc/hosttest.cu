@@ -82,6 +82,8 @@ int host_trial_sizes(const uint8_t* lit, int nlit, const uint8_t* dist, int ndis
 // GPU (tests/test_gpu_parity.py).
 // =====================================================================================================================
 #include <array>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "enum.cuh"
@@ -183,9 +185,38 @@ struct HostEngine {
         else if (recTab[0].type == 2) { b.tabid = (short)intern_tab(recTab[0]); b.hid = (short)new_hdr(recHdr[0]); b.type = 2; }
         en.B = b; en.blockType = b.type;
     }
+    // instrumentation: how close is a table that needs a cost array to one that already has one?
+    std::vector<int> dcSeen;
+    long long statBuilds = 0, statChanged = 0, statTouched = 0, statMatches = 0, statFlip = 0, statBytesTouched = 0;
+    void note_dc(int tabid) {
+        for (int t : dcSeen) if (t == tabid) return;
+        if (!dcSeen.empty()) {
+            int best = -1, bestD = 1 << 30;
+            for (int t : dcSeen) {
+                int dd = 0;
+                for (int b = 0; b < 256; b++) dd += tabs[t].L[b] != tabs[tabid].L[b];
+                if (dd < bestD) { bestD = dd; best = t; }
+            }
+            bool ch[256]; bool flip = false;
+            for (int b = 0; b < 256; b++) { ch[b] = tabs[best].L[b] != tabs[tabid].L[b]; if (ch[b] && (tabs[best].L[b] == 0 || tabs[tabid].L[b] == 0)) flip = true; }
+            long long touched = 0, nm = 0, bt = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                if (!sym_is_match(sym[i])) continue;
+                nm++;
+                int c = 0;
+                for (int k = 0; k < sym_len(sym[i]); k++) c += ch[out[symout[i] + k]];
+                touched += c > 0; bt += c;
+            }
+            { int cl = 0, cd = 0; for (int k = 257; k < 286; k++) cl += tabs[best].L[k] != tabs[tabid].L[k]; for (int k = 0; k < 30; k++) cd += tabs[best].D[k] != tabs[tabid].D[k];
+              fprintf(stderr, "  dc tab %d vs %d: lit %d lensym %d dist %d touched %lld/%lld bytes %lld flip %d\n", tabid, best, bestD, cl, cd, touched, nm, bt, (int)flip); }
+            statBuilds++; statChanged += bestD; statTouched += touched; statMatches += nm; statFlip += flip; statBytesTouched += bt;
+        }
+        dcSeen.push_back(tabid);
+    }
     void exec_pass(int slot) {
         PSlot& p = S.pm[slot];
         const int mid = pm_key_mid(p.key), tabid = pm_key_tab(p.key), op = pm_key_op(p.key);
+        if (op != OP_FIXED) note_dc(tabid);
         if (op == OP_FIXED) { p.delta = payload_of(hists[mid], tabs[TAB_FIXED]); p.mid = (unsigned short)mid; p.state = ST_DONE; return; }
         if ((int)masks.size() >= MAXM) { S.overflow = 1; return; }
         const Tab& t = tabs[tabid];
@@ -426,6 +457,7 @@ int host_engine_round(void* p, long long storedSize, int forceSegmented, long lo
     res[5] = e->en.restMin; res[6] = e->en.candIndex; res[7] = e->err; res[8] = e->nSweeps; res[9] = e->nSegmented;
     res[10] = e->S.nMasks; res[11] = e->S.nTabs; res[12] = e->S.nHdrs; res[13] = e->S.nP; res[14] = e->nSlowTrees;
     res[15] = e->recPay[1] + (e->recTab[1].type == 2 ? e->recHdr[1].bits : 0);
+    if (getenv("D4_HOST_DCSTATS")) fprintf(stderr, "dcstats builds %lld avg_changed_bytes %.2f touched_frac %.3f flips %lld byte_updates_per_build %.0f matches %lld\n", e->statBuilds, e->statBuilds ? (double)e->statChanged / e->statBuilds : 0.0, e->statMatches ? (double)e->statTouched / e->statMatches : 0.0, e->statFlip, e->statBuilds ? (double)e->statBytesTouched / e->statBuilds : 0.0, e->statBuilds ? e->statMatches / e->statBuilds : 0);
     if (traceN) *traceN = e->traceN;
     return e->err;
 }

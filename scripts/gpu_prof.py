@@ -8,7 +8,7 @@ import workloads as W
 from deft4j_b200 import optimise_batch, _native as N
 NAMES = ["block", "round", "sweep", "select", "pass", "dc_build", "recode", "trees(warp0)", "hdr_default(warp0)", "hdr_ops", "trials",
          "load", "materialise", "advance", "intern_mask", "intern_tab", "fixed", "slow_tree", "segmented", "hist_full",
-         "replace_main", "replace_hq", "least_apply", "least_stats"]
+         "replace_main", "replace_hq", "least_apply", "least_stats", "sign_masks"]
 mib = float(sys.argv[1]) if len(sys.argv) > 1 else 4
 merge = len(sys.argv) > 2 and sys.argv[2] == "merge"
 raw = W.c2_stream(int(mib * (1 << 20)))
