@@ -90,6 +90,7 @@ struct EngSmem {
     int leastSum[32], leastCnt[32];
     unsigned leastBlocked, leastSeen;
     int leastRem[2], leastSize[2];   // the length symbol each mode removes and its cost sum
+    const short* hqLit;              // replace pass in progress: its literal-cost array (nullptr otherwise)
     uint32_t binStart[33];           // perm[binStart[b] .. binStart[b + 1]) = the matches with length symbol 257 + b
     uint32_t itemStart[33];          // items[itemStart[b] .. itemStart[b + 1]) cover bin b, 32 matches apiece
     unsigned long long red;
@@ -827,17 +828,25 @@ struct Eng {
 #pragma unroll 1
         for (uint32_t b = nbits; b; b &= b - 1, base++) {
             const uint32_t i = i0 + (uint32_t)__ffs((int)b) - 1;
-            if (base < HQS) ES->u.hq.qs[base] = i; else hist_delta_replace(i);
+            if (base < HQS) ES->u.hq.qs[base] = i;
+            else {   // queue full: this one is applied on the spot
+                hist_delta_replace(i);
+                if (ES->hqLit) atomicAdd(&ES->red, (unsigned long long)(long long)(-dc_val(ES->hqLit, i)));
+            }
         }
     }
-    __device__ __noinline__ void hq_apply() {
+    // `lit` (replace passes): the cost-array entries of the queued matches are summed into ES->red on the way (what the
+    // replacements save); nullptr: not wanted
+    __device__ __noinline__ void hq_apply(const short* lit) {
         __syncthreads();
         const uint32_t nS = min(ES->u.hq.nS, (uint32_t)HQS);
+        long long sv = 0;
 #pragma unroll 1
         for (uint32_t j = tid; j < nS; j += ENG_NT) {
             const uint32_t i = ES->u.hq.qs[j];
             const uint32_t mi = minfo[i];
             const uint32_t so = v.symout[i];
+            if (lit) sv -= dc_val(lit, i);
             const int len = (int)(mi & 0x1FF) + 3;
             atomicSub(&ES->hist[256 + ((mi >> 14) & 31)], 1u);
             atomicSub(&ES->hist[288 + ((mi >> 9) & 31)], 1u);
@@ -854,6 +863,11 @@ struct Eng {
 #pragma unroll
                 for (int q = 0; q < 8; q++) if (b[q] < 256u) atomicAdd(&ES->hist[b[q]], 1u);
             }
+        }
+        if (lit) {
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, dd);
+            if ((tid & 31) == 0 && sv) atomicAdd(&ES->red, (unsigned long long)sv);
         }
         __syncthreads();
         const uint32_t nL = min(ES->u.hq.nL, (uint32_t)HQL);
@@ -888,12 +902,11 @@ struct Eng {
         P0();
 #pragma unroll 1
         for (int k = tid; k < 320; k += ENG_NT) ES->hist[k] = 0;
-        if (tid == 0) { ES->red = 0; ES->redAny = 0; ES->u.hq.nS = 0; ES->u.hq.nL = 0; }
+        if (tid == 0) { ES->red = 0; ES->redAny = 0; ES->u.hq.nS = 0; ES->u.hq.nL = 0; ES->hqLit = d; }
         __syncthreads();
         const int fresh = ES->sym.nMasks;
         const uint32_t* mo = maskp(mid);
         uint32_t* mn = maskp(fresh);
-        long long saved = 0;
         unsigned long long hsh = 0;
         const int lane = tid & 31;
         bool any = false;
@@ -911,22 +924,17 @@ struct Eng {
                         const uint32_t b0 = (m >> (8 * q)) & 0xffu, b1 = ((m | cand) >> (8 * q)) & 0xffu;
                         if (b0 != b1) hsh += mask_byte_hash(b1, 4 * k + q) - mask_byte_hash(b0, 4 * k + q);
                     }
-#pragma unroll 1
-                    for (uint32_t b = cand; b; b &= b - 1) saved -= dc_val(d, 32 * k + (uint32_t)__ffs((int)b) - 1);
                 }
             }
             if (__any_sync(0xffffffffu, cand != 0)) { hq_push_warp(cand, 32 * k, lane); any |= cand != 0; }
         }
         if (any) ES->redAny = 1;
-#pragma unroll 1
-        for (int dd = 16; dd > 0; dd >>= 1) saved += __shfl_xor_sync(0xffffffffu, saved, dd);
-        if (lane == 0 && saved) atomicAdd(&ES->red, (unsigned long long)saved);
         const unsigned long long h = ES->maskHash[mid] + cta_sum64(hsh);   // (also the barrier after the loop)
         __syncthreads();
         P1(PR_PASS_MAIN);
         int newmid = mid;
         if (ES->redAny) {
-            { P0(); hq_apply(); P1(PR_PASS_HQ); }
+            { P0(); hq_apply(d); P1(PR_PASS_HQ); }
             newmid = intern_mask(h);
             if (newmid == fresh) hist_store_delta(newmid, mid);
         }
@@ -1017,7 +1025,7 @@ struct Eng {
                 P0();
 #pragma unroll 1
                 for (int k = tid; k < 320; k += ENG_NT) ES->hist[k] = 0;
-                if (tid == 0) { ES->u.hq.nS = 0; ES->u.hq.nL = 0; }
+                if (tid == 0) { ES->u.hq.nS = 0; ES->u.hq.nL = 0; ES->hqLit = nullptr; }
                 const int fresh = ES->sym.nMasks;
                 const uint32_t* mo = maskp(mid);
                 uint32_t* mn = maskp(fresh);
@@ -1059,7 +1067,7 @@ struct Eng {
                     }
                 }
                 const unsigned long long h = ES->maskHash[mid] + cta_sum64(hsh);
-                hq_apply();
+                hq_apply(nullptr);
                 newmid = intern_mask(h);
                 if (newmid == fresh) hist_store_delta(newmid, mid);
                 doneMid = newmid; doneRem = rem;

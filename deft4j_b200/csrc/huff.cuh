@@ -660,8 +660,18 @@ D4_DEV int trial_sizes(const RunList& rl, int flags, int* bitsNoPrune, int* bits
         uint32_t a16 = 0, a17 = 0, a18 = 0;
 #pragma unroll 1
         for (int r = 0; r < rl.n; r++) {
-            const int val = rl.val[r];
-            run_groups(val, rl.len[r], flags, g);
+            const int val = rl.val[r], n = rl.len[r];
+            // A run too short for any run code (zeros: 17 needs 3; other values: a length plus a 16 of 3) is spelled out
+            // whatever the strategy: most runs of a code-length array are like that, and the test does not depend on the
+            // flags, so the 28 strategies of a warp take this shortcut together.
+            const bool plain = n < 3 || (val != 0 && n < 4);
+            if (plain) {
+                if (walk == 0) f[val] += (uint32_t)n;
+                else if (walk == 1) { sizeSum += c1[val] * n; f[val] += (uint32_t)n; }
+                else sum2 += c2[val] * n;
+                continue;
+            }
+            run_groups(val, n, flags, g);
             const int lit = g.cnt[4] + g.cnt[8];   // plain lengths of the run's value (groups 4 and 8)
             if (walk == 0) {
                 a18 += (uint32_t)(g.cnt[0] + g.cnt[1]);
