@@ -416,8 +416,8 @@ def run_shapes(ctx, L, N, a, peak, peak_src):
         streams = gen()
         shards = shard_streams([len(s) for s in streams], ctx.world)
         mine = [streams[i] for i in shards[ctx.rank]]
-        m = measure(ctx, L, N, mine, merge, steps=2, warmup=1, verify=not a.no_verify, e2e_steps=2)
-        dev_ms = ctx.max(m["dev_ms"]) / 2
+        m = measure(ctx, L, N, mine, merge, steps=3, warmup=2, verify=not a.no_verify, e2e_steps=2)
+        dev_ms = ctx.max(m["dev_ms"]) / 3
         e2e_s = ctx.max(m["e2e_s"])
         total_in = sum(len(s) for s in streams)
         fams = ctx.gather(m["fam"])
@@ -429,7 +429,71 @@ def run_shapes(ctx, L, N, a, peak, peak_src):
                         "family_ms_per_step": rf["family_ms_per_step"], "saved_bits": ctx.sum(m["saved_bits"]),
                         "uncompressed_bytes": ctx.sum(m["unc_bytes"]),
                         "output_verified": None if a.no_verify else bool(m["verified"]), "seconds": round(time.time() - t0, 1)}
+    shapes["c3_png_files"] = run_png_files(ctx, a)
     return shapes
+
+
+def run_png_files(ctx, a, count=768):
+    """C3 through the container layer (SURVEY.md 8 'next' row: PNGFile): PNG files in host memory ->
+    deft4cu_png_optimise_batch (native chunk model on host threads, all IDAT streams one device batch) -> rewritten
+    files in host memory; wall clock around the call, host bytes in and out.  Compare with c3_png_idat.e2e (the same
+    images as bare streams).  `python_mirror_e2e` is the same work through the Python mirror of PNGFile
+    (read_containers -> optimise_containers -> write), which the CLI uses for mixed folders."""
+    import io
+    import workloads as W
+    from deft4j_b200.container import read_containers, optimise_containers, optimise_png_files
+    t0 = time.time()
+    files = W.c3_png_files(count, first=10_000)
+    mine = files[ctx.rank::ctx.world]
+    names = ["img%d.png" % i for i in range(len(mine))]
+
+    def native():
+        return optimise_png_files(mine, True)
+
+    def mirror():
+        conts = read_containers(mine, names)
+        assert all(c is not None for c in conts)
+        saved = optimise_containers(conts, True)
+        return [{"status": 0, "out": c.write(), "saved_bits": s} for c, s in zip(conts, saved)]
+
+    def timed(fn, passes, warm):
+        best, res = None, None
+        for it in range(warm + passes):
+            ctx.barrier()
+            t = time.perf_counter()
+            res = fn()
+            dt = ctx.max(time.perf_counter() - t)
+            if it >= warm:
+                best = dt if best is None else min(best, dt)
+        return best, res
+
+    from deft4j_b200.container.png_file import _png_call
+
+    def abi_call():     # the C-ABI call alone, as the raw-stream e2e is timed: host buffers in, library-owned host buffers out
+        L_, r_, n_ = _png_call(mine, True, None)
+        L_.deft4cu_free_file_results(r_, n_)
+
+    best_abi, _ = timed(abi_call, 4, 3)
+    best, res = timed(native, 3, 1)
+    best_py, res_py = timed(mirror, 2, 2)
+    assert all(r["status"] == 0 for r in res)
+    ok = None
+    if not a.no_verify:
+        from PIL import Image
+        assert [r["out"] for r in res] == [r["out"] for r in res_py], "native front-end and Python mirror disagree"
+        for k in range(0, len(mine), max(1, len(mine) // 16)):
+            assert Image.open(io.BytesIO(res[k]["out"])).tobytes() == Image.open(io.BytesIO(mine[k])).tobytes(), "pixels differ"
+            assert len(res[k]["out"]) <= len(mine[k])
+        ok = True
+    total_in = sum(len(f) for f in files)
+    return {"workload": "%d Pillow-written 256x256 RGBA PNG files (compress_level=6) through the native PNG front-end "
+                        "(deft4cu_png_optimise_batch): read, optimise (merge blocks), write; wall clock around the C-ABI call "
+                        "(e2e), around deft4j_b200.container.optimise_png_files which also copies the files into Python bytes "
+                        "(e2e_python_api), and around the Python mirror of PNGFile (python_mirror_e2e)" % count,
+            "files": count, "input_bytes": total_in, "merge_blocks": True, "e2e": total_in / best_abi / 1e6, "unit": "MB/s",
+            "seconds_per_pass": best_abi, "e2e_python_api": total_in / best / 1e6, "python_mirror_e2e": total_in / best_py / 1e6,
+            "saved_bits": ctx.sum(sum(r["saved_bits"] for r in res)), "output_bytes": ctx.sum(sum(len(r["out"]) for r in res)),
+            "scaling": "strong", "output_verified": ok, "seconds": round(time.time() - t0, 1)}
 
 
 def run_ours(a):

@@ -103,6 +103,7 @@ def optimise_files_batched(paths, merge_blocks, stream_cls, out, err, max_bytes=
     from .container.deflate_files_container import optimise_containers
     ok = True
     group, size = [], 0
+    native_png = stream_cls is None or getattr(stream_cls, "__module__", "") == "deft4j_b200.deflate_stream"
 
     def flush():
         nonlocal ok
@@ -138,19 +139,66 @@ def optimise_files_batched(paths, merge_blocks, stream_cls, out, err, max_bytes=
                 ok = False
         group.clear()
 
+    pending = []   # (path, data) of the group being collected
+
+    def native_png_group():
+        """A group made of PNG files only goes through the native front-end (deft4cu_png_optimise_batch): same lines, same
+        files, the chunk work on host threads instead of in this interpreter."""
+        nonlocal ok
+        from .container.png_file import optimise_png_files
+        res = optimise_png_files([d for _, d in pending], merge_blocks)
+        for (path, _), r in zip(pending, res):
+            print("Optimising file " + path, file=out)
+            if r["status"] == 1:
+                print("Invalid file", file=err)
+                print("Failed to optimise input file", file=err)
+                print("Error when optimising file " + path, file=err)
+                ok = False
+                continue
+            print("File type recognised as PNG", file=out)
+            if r["status"] == 3:
+                print("Error when optimising file " + path, file=err)
+                ok = False
+                continue
+            for i, (name, saved) in enumerate(r["streams"]):
+                if saved > 0:
+                    print("%d bits saved in stream %d (%s)" % (saved, i, name), file=out)
+            if r["saved_bits"] > 0:
+                print("Total bits saved %d" % r["saved_bits"], file=out)
+            if r["saved_bits"] != 0:
+                print("Saved %d bits with optimisation" % r["saved_bits"], file=out)
+            if r["status"] == 2:
+                print("Failed to write output", file=err)
+                print("Error when optimising file " + path, file=err)
+                ok = False
+                continue
+            _write_back(path, r["out"], path, err)
+        pending.clear()
+
+    def read_group():
+        from .container.deflate_files_container import read_containers
+        from .container.container_util import detectFormat
+        if native_png and pending and all(detectFormat(d) == "png" for _, d in pending):
+            if group:
+                flush()
+            native_png_group()
+            return
+        conts = read_containers([d for _, d in pending], [os.path.basename(p) for p, _ in pending], stream_cls)
+        for (path, data), cont in zip(pending, conts):
+            group.append((path, data, cont))
+        pending.clear()
+
     for path in paths:
         with open(path, "rb") as f:
             data = f.read()
-        cont = getContainerForBytes(data, os.path.basename(path), stream_cls)
-        try:
-            good = cont is not None and cont.read(data)
-        except Exception:  # noqa: BLE001
-            good = False
-        group.append((path, data, cont if good else None))
+        pending.append((path, data))
         size += len(data)
-        if size >= max_bytes or len(group) >= 4096:
+        if size >= max_bytes or len(pending) >= 4096:
+            read_group()
             flush()
             size = 0
+    if pending:
+        read_group()
     if group:
         flush()
     return ok

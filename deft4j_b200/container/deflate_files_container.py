@@ -36,6 +36,86 @@ def optimise_streams(streams, merge_blocks=True, out=sys.stdout):
     return saved_total
 
 
+def read_containers(datas, names, stream_cls=None):
+    """Read many files so that ALL their deflate streams are parsed in one device batch.
+
+    A container parses its streams one at a time, because each parse tells it where the stream ended (the trailer
+    follows).  Here every file is read twice on the host: a first pass with a recording stub collects the byte ranges
+    the containers hand to `DeflateStream.parse`, those are parsed together (`DeflateStream.parse_batch`, one launch of
+    every parse kernel), and the second pass hands the parsed streams back in order.  Returns one container per file,
+    None where the file cannot be read.  Falls back to plain per-file reads for stream classes without `parse_batch`."""
+    from .container_util import getContainerForBytes
+    from ._io import ByteReader
+    cls = stream_cls or _default_stream_cls()
+    if not hasattr(cls, "parse_batch"):
+        out = []
+        for data, name in zip(datas, names):
+            cont = getContainerForBytes(data, name, cls)
+            out.append(cont if cont is not None and cont.read(data) else None)
+        return out
+    recorded = []
+
+    class _Recorder:
+        def __init__(self, name=None):
+            self.name = name
+
+        def parse(self, src):
+            recorded[-1].append((self.name, src.remaining() if isinstance(src, ByteReader) else bytes(src)))
+            return True
+
+    for data, name in zip(datas, names):
+        recorded.append([])
+        try:
+            cont = getContainerForBytes(data, name, _Recorder)
+            if cont is None or not cont.read(data):
+                recorded[-1] = None
+        except Exception:  # noqa: BLE001 - a stub parse leaves the reader in front of the stream: later fields are garbage
+            pass
+    flat = [b for r in recorded if r for _, b in r]
+    parsed = cls.parse_batch(flat, [n for r in recorded if r for n, _ in r]) if flat else []
+    it = iter(parsed)
+    out = []
+    for data, name, rec in zip(datas, names, recorded):
+        if rec is None:
+            out.append(None)
+            continue
+        mine = [next(it) for _ in rec]
+        queue = list(mine)
+
+        def factory(nm=None, _q=queue):
+            s = _q.pop(0) if _q else None
+            return _Preparsed(s, nm, cls)
+
+        cont = getContainerForBytes(data, name, factory)
+        ok = cont is not None and cont.read(data)
+        out.append(cont if ok else None)
+    return out
+
+
+class _Preparsed:
+    """Stands in for a stream class while a container is read the second time: `parse` hands over the stream the
+    batch parse produced (and advances the reader by what it consumed)."""
+
+    def __new__(cls, stream, name, real_cls):
+        from ._io import ByteReader
+        if stream is None:
+            stream = real_cls(name) if name is not None else real_cls()
+            stream._preparse_failed = True
+        elif name is not None:
+            stream.setName(name)
+        real_parse = stream.parse
+
+        def parse(src, _s=stream):
+            if getattr(_s, "_preparse_failed", False):
+                return real_parse(src)   # (fails again, with the reference's behaviour)
+            if isinstance(src, ByteReader):
+                src.pos += _s.consumed
+            return True
+
+        stream.parse = parse
+        return stream
+
+
 def optimise_containers(containers, merge_blocks=True, outs=None):
     """Several containers (the files of `optimise-folder`, OptimiseFolder.java:33-67) as ONE stream list on the
     device; every container then reports exactly what its own `optimise` would have printed.  `outs`: one text sink

@@ -6,8 +6,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <chrono>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/deft4cu.h"
@@ -27,6 +29,24 @@ static int g_sms = 148;
 static bool g_sync_debug = getenv("D4_SYNC") != nullptr;
 static uint64_t g_opt_launches = 0;   // launches of the candidate engine (k_opt_blocks) since start: tests count them
 static std::mutex g_mu;
+
+// D4_HOST_TIMING=1: wall time of the host-side phases on stderr (diagnostics for the container path)
+struct HostTimer {
+    const char* what; std::chrono::steady_clock::time_point t0; bool on;
+    explicit HostTimer(const char* w) : what(w), t0(std::chrono::steady_clock::now()) { static bool e = getenv("D4_HOST_TIMING") != nullptr; on = e; }
+    ~HostTimer() {
+        if (on && g_device >= 0) {
+            cudaMemPool_t pool;
+            uint64_t res = 0, used = 0;
+            if (cudaDeviceGetDefaultMemPool(&pool, g_device) == cudaSuccess) {
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &res);
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+            }
+            fprintf(stderr, "[deft4cu] pool reserved %7.1f MiB used %7.1f MiB  ", res / 1048576.0, used / 1048576.0);
+        }
+        if (on) fprintf(stderr, "[deft4cu] %-14s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
 
 static int ensure_init() {
     if (g_device >= 0) return DEFT4CU_OK;
@@ -176,6 +196,7 @@ class Batch {
     std::vector<int64_t> size_bits_in;
 
     uint8_t* d_dst = nullptr;
+    std::vector<uint8_t> h_dst;   // host copy of d_dst, filled by the first per-stream write of a multi-stream batch
     std::vector<uint64_t> dst_off, dst_len;
     uint64_t dst_total = 0;
     uint64_t* d_dst_off = nullptr;
@@ -195,12 +216,15 @@ class Batch {
         parsed = false; have_sums = false; optimised = false;
     }
     void release_all() {
+        HostTimer ht("release");
+        drop_stage();
         release_model();
         dfree(d_in, cs);
         if (cs) cudaStreamSynchronize(cs);
     }
 
     int upload(const uint8_t* const* in, const uint64_t* len, uint32_t count) {
+        HostTimer ht("upload");
         n = count;
         if (!own_cs) { D4_CUDA_CHECK(cudaStreamCreateWithFlags(&own_cs, cudaStreamNonBlocking)); cs = own_cs; }
         in_len.assign(len, len + n);
@@ -209,10 +233,45 @@ class Batch {
         for (uint32_t i = 0; i < n; i++) { in_off[i] = off; off += (in_len[i] + 32 + 15) & ~15ull; }
         total_in = off + 512;   // k_find loads three 8-byte words per thread of its last tile (FIND_TILE / 8 + 24 bytes)
         D4_CUDA_CHECK(dalloc(&d_in, total_in, cs));
+        // Many small streams (a folder of PNGs, the entries of a ZIP): a copy per stream from pageable memory costs ~10 us
+        // each, so they are gathered by a few host threads into one pinned block and go over in a single DMA.
+        if (n >= 16 && total_in <= (1ull << 30) && !getenv("D4_NO_STAGING")) {
+            stage = host_block_acquire(total_in, 1);
+            if (stage) {
+                auto fill = [&](uint32_t lo, uint32_t hi) {
+                    for (uint32_t i = lo; i < hi; i++) {
+                        if (in_len[i]) memcpy(stage + in_off[i], in[i], in_len[i]);
+                        const uint64_t end = in_off[i] + in_len[i], nxt = i + 1 < n ? in_off[i + 1] : total_in;
+                        memset(stage + end, 0, nxt - end);
+                    }
+                };
+                const uint32_t nt = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, total_in >> 22));
+                if (nt <= 1) fill(0, n);
+                else {
+                    // equal shares of BYTES, cut at stream boundaries
+                    std::vector<uint32_t> cut(nt + 1, n);
+                    cut[0] = 0;
+                    for (uint32_t t = 1, i = 0; t < nt; t++) {
+                        while (i < n && in_off[i] < total_in / nt * t) i++;
+                        cut[t] = i;
+                    }
+                    std::vector<std::thread> th;
+                    for (uint32_t t = 1; t < nt; t++) th.emplace_back(fill, cut[t], cut[t + 1]);
+                    fill(cut[0], cut[1]);
+                    for (auto& x : th) x.join();
+                }
+                D4_CUDA_CHECK(cudaMemcpyAsync(d_in, stage, total_in, cudaMemcpyHostToDevice, cs));
+                return DEFT4CU_OK;   // (the block goes back to the pool after parse()'s first synchronisation)
+            }
+        }
         D4_CUDA_CHECK(cudaMemsetAsync(d_in, 0, total_in, cs));
         for (uint32_t i = 0; i < n; i++)
             if (in_len[i]) D4_CUDA_CHECK(cudaMemcpyAsync(d_in + in_off[i], in[i], in_len[i], cudaMemcpyHostToDevice, cs));
         return DEFT4CU_OK;
+    }
+    uint8_t* stage = nullptr;   // pinned staging block of upload(), held until the copy has completed
+    void drop_stage() {
+        if (stage) { cudaStreamSynchronize(cs); host_release(stage); stage = nullptr; }
     }
 
     // the same from streams that already sit in other batches' input buffers (device to device)
@@ -241,6 +300,7 @@ class Batch {
     uint32_t parse_rewalks = 0, parse_walkers = 0;
 
     int parse() {
+        HostTimer ht("parse");
         release_model();
         too_big = false;
         cudaEvent_t ev[4];
@@ -309,6 +369,7 @@ class Batch {
             if (W) LAUNCH_SM(k_count, W, PARSE_NT, WIN_BYTES + WIN_SLACK + 16, cs, d_in, d_descs, d_infos, d_blocks, d_chunks, d_list, seg_bits, spec_max_bits);
             D4_CUDA_CHECK(cudaMemcpyAsync(winfos.data(), d_infos, sizeof(StreamInfo) * W, cudaMemcpyDeviceToHost, cs));
             D4_CUDA_CHECK(cudaStreamSynchronize(cs));
+            if (stage && cs == own_cs) { host_release(stage); stage = nullptr; }   // upload()'s copy is behind us
             // ---- follow every stream's chain from walker 0; re-walk what was guessed wrong ---------------------
             std::vector<uint32_t> cur(n), pending;
             std::vector<uint8_t> fin(n, 0);
@@ -518,6 +579,7 @@ class Batch {
 
     // ---- optimise: phase A over blocks, then per-stream replay/merge/layout ----------------------------
     int optimise(uint32_t flags, const std::vector<uint8_t>& selected) {
+        HostTimer ht("optimise");
         cudaEvent_t ev[3];
         for (auto& e : ev) cudaEventCreate(&e);
         const int merge = (flags & DEFT4CU_MERGE_BLOCKS) ? 1 : 0;
@@ -631,11 +693,13 @@ class Batch {
             return DEFT4CU_ERR_UNSUPPORTED;
         }
         dfree(d_dst, cs);  // stale output
+        h_dst.clear();
         return DEFT4CU_OK;
     }
 
     // ---- write ---------------------------------------------------------------------------------------
     int write() {
+        HostTimer ht("write");
         cudaEvent_t ev[2];
         for (auto& e : ev) cudaEventCreate(&e);
         dst_off.assign(n, 0); dst_len.assign(n, 0);
@@ -648,6 +712,7 @@ class Batch {
         }
         dst_total = off + 8;
         dfree(d_dst, cs); dfree(d_dst_off, cs);
+        h_dst.clear();
         D4_CUDA_CHECK(dalloc(&d_dst, dst_total, cs));
         D4_CUDA_CHECK(dalloc(&d_dst_off, n, cs));
         D4_CUDA_CHECK(cudaMemsetAsync(d_dst, 0, dst_total, cs));
@@ -675,6 +740,7 @@ class Batch {
 
     int checksums() {
         if (have_sums) return DEFT4CU_OK;
+        HostTimer ht("checksums");
         static std::once_flag once;
         std::call_once(once, [] { k_crc_init<<<1, 1>>>(); cudaDeviceSynchronize(); });
         cudaEvent_t ev[2];
@@ -919,6 +985,16 @@ int deft4cu_stream_write(const deft4cu_stream* s, uint8_t* dst, uint64_t cap, ui
     uint64_t l = b.dst_len[s->idx];
     if (len) *len = l;
     if (dst && cap >= l) {
+        // a container asks stream by stream (PNGFile/ZipFile.write): the whole batch comes over in one copy the first time
+        if (b.n > 1 && b.dst_total <= (1ull << 30)) {
+            if (b.h_dst.empty()) {
+                b.h_dst.resize(b.dst_total);
+                D4_CUDA_CHECK(cudaMemcpyAsync(b.h_dst.data(), b.d_dst, b.dst_total, cudaMemcpyDeviceToHost, b.cs));
+                D4_CUDA_CHECK(cudaStreamSynchronize(b.cs));
+            }
+            if (l) memcpy(dst, b.h_dst.data() + b.dst_off[s->idx], l);
+            return DEFT4CU_OK;
+        }
         if (l) D4_CUDA_CHECK(cudaMemcpyAsync(dst, b.d_dst + b.dst_off[s->idx], l, cudaMemcpyDeviceToHost, b.cs));
         D4_CUDA_CHECK(cudaStreamSynchronize(b.cs));
     }
@@ -1114,6 +1190,7 @@ int deft4cu_device_batch_create(const uint8_t* const* in, const uint64_t* in_len
     rc = b->upload(in, in_len, n);
     if (rc) return rc;
     D4_CUDA_CHECK(cudaStreamSynchronize(b->cs));
+    b->drop_stage();
     *out = new deft4cu_device_batch{b};
     return DEFT4CU_OK;
 }

@@ -100,6 +100,7 @@ __device__ __forceinline__ int decode_sym_lut(const DecTab& t, const uint16_t* l
 // registers) and every peek reads shared memory.  `avail` bytes of the source are valid; the rest is zero-filled.
 constexpr int WIN_BYTES = PARSE_NT * CHUNK_BITS / 8;      // 32 KiB
 constexpr int WIN_SLACK = 64;                              // a unit is <= 48 bits and a peek reads 16 bytes
+constexpr int HDR_STAGE = 1024;                            // a dynamic header is at most 4551 bits (+ 16 bytes of alignment and a peek's over-read)
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
@@ -160,29 +161,30 @@ __device__ inline void fixed_lens(uint8_t* L, uint8_t* D) {  // HuffmanTable.jav
 }
 
 // DeflateBlockHuffman.initDynamicDecoder (:892-1010), run by one thread.  Returns bits consumed or 0.
-__device__ inline uint32_t parse_dynamic_header(const uint8_t* in, uint64_t pos, uint64_t total_bits, BlockRec& b,
-                                                DecTab& scratch) {
+// `peek(p)` returns the (>= 57) bits at stream bit position p; `lens`: MAX_LL + MAX_D bytes of scratch.
+template <class Peek>
+__device__ inline uint32_t parse_dynamic_header(Peek peek, uint64_t pos, uint64_t total_bits, BlockRec& b, DecTab& scratch,
+                                                uint8_t* lens) {
     uint64_t p = pos;
     if (p + 14 > total_bits) return 0;
-    uint64_t w = peek_bits(in, p);
+    uint64_t w = peek(p);
     int nL = (int)(w & 31) + 257, nD = (int)((w >> 5) & 31) + 1, ncl = (int)((w >> 10) & 15) + 4;
     p += 14;
     if (p + 3ull * ncl > total_bits) return 0;
     for (int i = 0; i < 19; i++) b.hdr.CL[i] = 0;
     for (int i = 0; i < ncl; i++) {
-        b.hdr.CL[c_codelen_order[i]] = (uint8_t)(peek_bits(in, p) & 7);
+        b.hdr.CL[c_codelen_order[i]] = (uint8_t)(peek(p) & 7);
         p += 3;
     }
     int hbits = 14 + 3 * ncl;
     build_dectab(b.hdr.CL, 19, scratch);
     // HLIT up to 288 is accepted by the reference parser (asserts only); the tables then have 287/288
     // entries.  Our Tab holds 288.
-    uint8_t lens[MAX_LL + MAX_D];
     int i = 0, np = 0;
     const int combined = nL + nD;
     while (i < combined) {
         if (p >= total_bits) return 0;
-        w = peek_bits(in, p);
+        w = peek(p);
         int l;
         int s = decode_sym(scratch, w, &l);
         if (s < 0) return 0;
@@ -406,15 +408,28 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
     bool done = false;
 
     while (!done) {
-        // ---- block header (thread 0) --------------------------------------------------------------
+        // ---- block header (thread 0), from a staged copy of its bytes: a dynamic header is a few hundred dependent
+        //      reads, far too slow from global memory --------------------------------------------------------------
+        const uint64_t hbyte = (s_pos >> 3) & ~15ull;
+        {
+            const int64_t valid = (int64_t)(sd.in_len + 32) - (int64_t)hbyte;
+            for (int o = t * 16; o < HDR_STAGE; o += PARSE_NT * 16) {
+                const int64_t left = valid - o;
+                const int nb = left >= 16 ? 16 : left > 0 ? (int)left : 0;
+                cp_async16(s_win + o, in + hbyte + (nb ? o : 0), nb);
+            }
+            cp_async_wait_all();
+            __syncthreads();
+        }
         if (t == 0) {
+            auto peek = [&](uint64_t p) { return peek_bits_smem(s_win, (uint32_t)(p - hbyte * 8)); };
             uint64_t pos = s_pos;
             s_blk.hdr_bit = pos;
             s_blk.hdr.np = 0; s_blk.hdr.ncl = 0; s_blk.hdr.bits = 0;
             s_blk.tab.nL = 0; s_blk.tab.nD = 0;
             if (pos + 3 > total_bits) { s_status = ST_PARSE; }
             else {
-                uint64_t w = peek_bits(in, pos);
+                uint64_t w = peek(pos);
                 s_final = (int)(w & 1);
                 int type = (int)((w >> 1) & 3);
                 s_type = type;
@@ -424,7 +439,7 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
                     pos = (pos + 7) & ~7ull;
                     if (pos + 32 > total_bits) s_status = ST_PARSE;
                     else {
-                        uint64_t v = peek_bits(in, pos);
+                        uint64_t v = peek(pos);
                         uint32_t len = (uint32_t)(v & 0xffff), nlen = (uint32_t)((v >> 16) & 0xffff);
                         pos += 32;
                         if (nlen != (~len & 0xffff)) s_status = ST_PARSE;
@@ -448,7 +463,7 @@ k_count(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, 
                     for (int k = 30; k < MAX_D; k++) s_blk.tab.D[k] = 0;
                     s_blk.data_bit = pos;
                 } else {
-                    uint32_t used = parse_dynamic_header(in, pos, total_bits, s_blk, s_lit);
+                    uint32_t used = parse_dynamic_header(peek, pos, total_bits, s_blk, s_lit, s_win + HDR_STAGE);
                     if (used == 0) s_status = ST_PARSE;
                     else {
                         pos += used;

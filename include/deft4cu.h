@@ -116,6 +116,30 @@ void deft4cu_free_buffer(uint8_t* p);
 int64_t deft4cu_size_bits_fallback(const uint8_t* in, uint64_t len);
 
 /* ------------------------------------------------------------------------------------------------
+ * File front-end for PNG / APNG — replaces, for a LIST of files, PNGFile.read (deft4j-container/.../
+ * container/PNGFile.java:574-605, chunk reader :162-215, PNGChunkHelper :413-572), the container's
+ * optimise (DeflateFilesContainer.java:18-43 over getDeflateStreams(), PNGFile.java:376-389) and
+ * PNGFile.write (:391-411 with syncStreams :262-369).  The chunk model runs on host threads; the IDAT /
+ * fdAT / zTXt / iCCP / iTXt zlib streams of all files are ONE device batch.
+ * status: OK; ERR_PARSE where PNGFile.read returns false; ERR_WRITE where write() throws; ERR_UNSUPPORTED
+ * where a stream hit an internal limit.  Streams are listed in getDeflateStreams() order.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct deft4cu_file_result {
+    int32_t  status;
+    uint32_t n_streams;          /* getDeflateStreams().size() */
+    int64_t  saved_bits;         /* return value of DeflateFilesContainer.optimise (:18-43) */
+    uint8_t* out;                /* PNGFile.write(); library-owned */
+    uint64_t out_len;
+    int64_t* stream_saved;       /* n_streams entries: bits saved per stream */
+    char   (*stream_name)[24];   /* n_streams entries: "IDAT chunk", "fdAT chunk 2", "zTXt chunk" (:441,:458,:536) */
+} deft4cu_file_result;
+int  deft4cu_png_optimise_batch(const uint8_t* const* files, const uint64_t* lens, uint32_t n, uint32_t flags,
+                                deft4cu_file_result* results);
+void deft4cu_free_file_results(deft4cu_file_result* results, uint32_t n);
+/* java.util.zip.CRC32 as the chunk writer uses it (PNGFile.java:140-158); crc = 0 starts a new checksum */
+uint32_t deft4cu_crc32(uint32_t crc, const uint8_t* data, uint64_t len);
+
+/* ------------------------------------------------------------------------------------------------
  * Device-resident benchmarking entry (bench.py `value`): inputs already in HBM.  Times nothing itself;
  * runs parse → optimise → write for a batch whose input bytes live at d_in (device pointer) and leaves
  * the output on the device.  Kernel launch counts are returned for the `gpu_launches` bench key.

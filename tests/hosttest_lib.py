@@ -85,3 +85,25 @@ def huff_tree_tiny(freq, limit):
     L.host_huff_tree_tiny.argtypes = [C.POINTER(C.c_uint32), C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int)]
     rc = L.host_huff_tree_tiny(f, n, limit, lens, C.byref(fb))
     return rc, list(lens), fb.value
+
+
+# ---- the native file front-ends over the CPU oracle (no GPU needed) ------------------------------------------------
+_FRONT_SO = os.path.join(_ROOT, "tests", "_build", "libfront_oracle.so")
+_front = None
+
+
+def front_oracle_lib():
+    """deft4j_b200/csrc/png_front.cpp linked against tests/front_oracle_shim.cpp (deft4cu_optimise_batch done by the
+    oracle): the chunk model of the shipped front-end, checked on the CPU."""
+    global _front
+    if _front is None:
+        srcs = [os.path.join(_SRC, "png_front.cpp"), os.path.join(_ROOT, "tests", "front_oracle_shim.cpp"),
+                os.path.join(_ROOT, "oracle", "deft_oracle.cpp")]
+        deps = srcs + [os.path.join(_ROOT, "include", "deft4cu.h"), os.path.join(_ROOT, "oracle", "deft_oracle.h")]
+        if (not os.path.exists(_FRONT_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_FRONT_SO) for s in deps):
+            os.makedirs(os.path.dirname(_FRONT_SO), exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", _FRONT_SO] + srcs)
+        _front = C.CDLL(_FRONT_SO)
+        _front.deft4cu_crc32.restype = C.c_uint32
+        _front.deft4cu_crc32.argtypes = [C.c_uint32, C.c_char_p, C.c_uint64]
+    return _front

@@ -564,3 +564,78 @@ def test_batches_beyond_the_decoded_limit_are_split(gpu, oracle, monkeypatch):
     for a, b in zip(res, ref):
         assert (a["status"], a["saved_bits"], a["out"], a["crc32"]) == (b["status"], b["saved_bits"], b["out"], b["crc32"])
     assert any(r["status"] == 0 for r in res)
+
+
+def test_png_files_read_as_one_device_batch(gpu, oracle):
+    """read_containers: the IDAT streams of many PNG files (Pillow-written) are parsed by ONE batch
+    parse and optimised by ONE engine launch; every rewritten file equals what the oracle's stream class produces
+    through the same PNGFile mirror, and the fixtures' goldens still come out."""
+    from deft4j_b200 import _native
+    from deft4j_b200.container import getContainerForBytes, read_containers, optimise_containers
+    L = _native.lib()
+    files = W.c3_png_files(12, first=400) + [read_golden("apng/ball.png"), read_golden("text.png"), b"not a container"]
+    names = ["f%d.png" % i for i in range(len(files) - 1)] + ["junk.bin"]
+    n0 = L.deft4cu_debug_engine_launches()
+    conts = read_containers(files, names, gpu.DeflateStream)
+    assert conts[-1] is None and all(c is not None for c in conts[:-1])
+    saved = optimise_containers(conts[:-1], True)
+    assert L.deft4cu_debug_engine_launches() - n0 == 1
+    assert conts[12].write() == read_golden("apng/ball-opt.png")
+    assert conts[13].write() == read_golden("text-opt.png")
+    for k in range(12):
+        ref = getContainerForBytes(files[k], names[k], oracle.OracleDeflateStream)
+        assert ref.read(files[k])
+        assert ref.optimise(True, None) == saved[k]
+        assert conts[k].write() == ref.write(), k
+
+
+def test_native_png_front_end_on_the_device(gpu, oracle):
+    """deft4cu_png_optimise_batch (csrc/png_front.cpp over the device batch entry): ONE engine launch for a list of
+    files, the reference's golden outputs for its PNG fixtures, and for Pillow files and structurally mutated files
+    exactly what the same front-end produces over the oracle (tests/front_oracle_shim.cpp)."""
+    import hosttest_lib
+    from test_png_front import mutants
+    from deft4j_b200 import _native
+    from deft4j_b200.container import optimise_png_files
+    L = _native.lib()
+    pairs = [("apng/ball.png", "apng/ball-opt.png"), ("text.png", "text-opt.png"), ("284-edge-case/284.png", "284-edge-case/284-opt.png")]
+    files = [read_golden(a) for a, _ in pairs] + W.c3_png_files(40, first=700) + [b"junk"]
+    n0 = L.deft4cu_debug_engine_launches()
+    res = optimise_png_files(files, True)
+    assert L.deft4cu_debug_engine_launches() - n0 == 1
+    for (a, g), r in zip(pairs, res):
+        assert r["status"] == 0 and r["out"] == read_golden(g), a
+    assert res[-1]["status"] == 1
+    ref = optimise_png_files(files[3:15], True, lib=hosttest_lib.front_oracle_lib())
+    assert res[3:15] == ref
+    muts = mutants(per_base=12, seed=5)
+    assert optimise_png_files(muts, True) == optimise_png_files(muts, True, lib=hosttest_lib.front_oracle_lib())
+    assert optimise_png_files([], True) == []
+
+
+def test_cli_folder_of_pngs_uses_the_native_front_end(gpu, oracle, tmp_path, capsys):
+    """`optimise-folder` on a folder that holds only PNG files: one engine launch, the lines CMDUtil.optimiseFile prints,
+    and the files the Python mirror of PNGFile writes with the oracle's streams."""
+    from deft4j_b200 import _native
+    from deft4j_b200.container import PNGFile
+    from deft4j_b200.__main__ import main
+    L = _native.lib()
+    files = {"a%d.png" % i: d for i, d in enumerate(W.c3_png_files(5, first=900))}
+    files["ball.png"] = read_golden("apng/ball.png")
+    files["broken.png"] = read_golden("text.png")[:300]
+    for name, d in files.items():
+        (tmp_path / name).write_bytes(d)
+    n0 = L.deft4cu_debug_engine_launches()
+    assert main(["optimise-folder", str(tmp_path)]) == 1      # broken.png fails, the rest is optimised
+    assert L.deft4cu_debug_engine_launches() - n0 == 1
+    cap = capsys.readouterr()
+    assert cap.out.count("File type recognised as PNG") == 6 and "Invalid file" in cap.err
+    assert "bits saved in stream 1 (fdAT chunk 1)" in cap.out
+    assert (tmp_path / "ball.png").read_bytes() == read_golden("apng/ball-opt.png")
+    assert (tmp_path / "broken.png").read_bytes() == files["broken.png"]
+    for i in range(5):
+        c = PNGFile(oracle.OracleDeflateStream)
+        assert c.read(files["a%d.png" % i])
+        saved = c.optimise(True, None)
+        assert (tmp_path / ("a%d.png" % i)).read_bytes() == c.write()
+        assert ("Saved %d bits with optimisation" % saved) in cap.out

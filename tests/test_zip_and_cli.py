@@ -148,3 +148,30 @@ def test_cli_has_no_cpu_fallback(tmp_path):
     with pytest.raises(Deft4cuError):
         main(["optimise", golden_path("lz-twice-twice.txt.gz"), str(tmp_path / "o.gz")])
     assert not (tmp_path / "o.gz").exists()
+
+
+def test_read_containers_record_and_replay(oracle):
+    """The two-pass container read (deft4j_b200.container.read_containers) with a batching stand-in built on the
+    oracle: every stream goes through ONE parse_batch call and the rewritten files are the reference's goldens."""
+    from deft4j_b200.container import read_containers, optimise_containers
+    calls = []
+
+    class Batching(oracle.OracleDeflateStream):
+        @classmethod
+        def parse_batch(cls, buffers, names=None):
+            calls.append(len(buffers))
+            out = []
+            for i, b in enumerate(buffers):
+                s = cls(names[i] if names else None)
+                out.append(s if oracle.OracleDeflateStream.parse(s, b) else None)
+            return out
+
+    pairs = [(a, g) for a, g, fast in GOLDEN_PAIRS if fast and "zopfli" not in a]
+    files = [read_golden(a) for a, _ in pairs] + [b"\xff\xff not deflate"]
+    names = [os.path.basename(a) for a, _ in pairs] + ["junk.bin"]
+    conts = read_containers(files, names, Batching)
+    assert len(calls) == 1 and calls[0] >= len(pairs)
+    assert conts[-1] is None
+    optimise_containers(conts[:-1], True)
+    for (a, gold), c in zip(pairs, conts):
+        assert c.write() == read_golden(gold), a

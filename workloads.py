@@ -91,9 +91,8 @@ def c2_text(nbytes, seed=0xDEF7):
     return b"".join(parts)[:nbytes]
 
 
-def _png_filtered(index, w=256, h=256):
-    """Filtered scanlines (Sub filter on gradients / None on flats) of a synthetic RGBA image: a mix of flat
-    regions, linear gradients and 5 % uniform noise; 262 400 bytes."""
+def _png_image(index, w=256, h=256):
+    """Synthetic 256x256 RGBA image: a mix of flat regions, linear gradients and 5 % uniform noise."""
     rng = np.random.default_rng(index)
     img = np.zeros((h, w, 4), dtype=np.uint8)
     # flat regions
@@ -111,27 +110,35 @@ def _png_filtered(index, w=256, h=256):
     # 5 % noise
     m = rng.random((h, w)) < 0.05
     img[m] = rng.integers(0, 256, (int(m.sum()), 4), dtype=np.uint8)
-    raw = img.reshape(h, w * 4)
-    sub = raw.copy()
-    sub[:, 4:] = raw[:, 4:] - raw[:, :-4]
-    # adaptive choice per line: minimum sum of absolute differences heuristic between None and Sub
-    cost_none = np.minimum(raw, 256 - raw.astype(np.int16)).sum(1)
-    cost_sub = np.minimum(sub, 256 - sub.astype(np.int16)).sum(1)
-    use_sub = cost_sub < cost_none
-    lines = np.where(use_sub[:, None], sub, raw)
-    out = np.empty((h, w * 4 + 1), dtype=np.uint8)
-    out[:, 0] = use_sub.astype(np.uint8)
-    out[:, 1:] = lines
-    return out.tobytes()
+    return img
+
+
+def c3_png_files(count, first=0):
+    """`count` PNG files as SURVEY.md 8(d) specifies them: Pillow `save(compress_level=6)` (adaptive filter, zlib IDAT),
+    seed = index."""
+    import io
+    from PIL import Image
+    out = []
+    for i in range(first, first + count):
+        b = io.BytesIO()
+        Image.fromarray(_png_image(i), "RGBA").save(b, format="PNG", compress_level=6)
+        out.append(b.getvalue())
+    return out
+
+
+def _idat_payload(png):
+    pos, z = 8, b""
+    while pos + 12 <= len(png):
+        n = int.from_bytes(png[pos:pos + 4], "big")
+        if png[pos + 4:pos + 8] == b"IDAT":
+            z += png[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    return z
 
 
 def c3_streams(count, first=0):
-    """Raw deflate payloads of `count` PNG IDAT streams (the zlib wrapper is the container's business)."""
-    out = []
-    for i in range(first, first + count):
-        co = zlib.compressobj(6, zlib.DEFLATED, -15, 8)
-        out.append(co.compress(_png_filtered(i)) + co.flush())
-    return out
+    """Raw deflate payloads of the IDAT streams of c3_png_files (the zlib wrapper is the container's business)."""
+    return [_idat_payload(p)[2:-4] for p in c3_png_files(count, first)]
 
 
 def c4_streams(count, seed=4):
