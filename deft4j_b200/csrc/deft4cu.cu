@@ -488,22 +488,29 @@ class Batch {
         if (ob) {
             uint32_t* d_ptr = nullptr;
             int* d_changed = nullptr;
+            uint8_t* d_done = nullptr;
             D4_CUDA_CHECK(dalloc(&d_ptr, ob, cs));
             D4_CUDA_CHECK(dalloc(&d_changed, 1, cs));
+            D4_CUDA_CHECK(dalloc(&d_done, ob, cs));
+            D4_CUDA_CHECK(cudaMemsetAsync(d_done, 0, ob, cs));
             if (sb) LAUNCH(k_lz_fill, (unsigned)((sb + 255) / 256), 256, cs, d_sym, d_symout, sb, d_out, d_ptr);
             // stored bytes are roots (k_emit wrote them into d_out; their pointers are set here)
             LAUNCH(k_lz_root_stored, (unsigned)std::max<uint64_t>(1, nblk_total), 256, cs, d_descs, d_blocks, d_jobs, (uint32_t)nblk_total, d_ptr);
             for (int it = 0; it < 64; it++) {
                 int changed = 0;
                 D4_CUDA_CHECK(cudaMemsetAsync(d_changed, 0, sizeof(int), cs));
-                for (int rep = 0; rep < (it == 0 ? 2 : 1); rep++) LAUNCH(k_lz_jump, (unsigned)((ob + 255) / 256), 256, cs, d_ptr, ob, d_changed);
+                if (it == 0) {
+                    uint32_t tile = LZJ_TILE;
+                    if (const char* e = getenv("D4_LZ_TILE")) tile = (uint32_t)std::max(512, atoi(e)) / LZJ_NT * LZJ_NT;
+                    LAUNCH(k_lz_jump_tiles, (unsigned)((ob + tile - 1) / tile), LZJ_NT, cs, d_ptr, d_out, d_done, ob, tile, d_changed);
+                }
+                else LAUNCH(k_lz_jump, (unsigned)((ob + 1023) / 1024), 256, cs, d_ptr, d_out, d_done, ob, d_changed);
                 D4_CUDA_CHECK(cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, cs));
                 D4_CUDA_CHECK(cudaStreamSynchronize(cs));
                 if (!changed) break;
                 if (it == 63) { set_error("LZ77 resolve did not converge"); return DEFT4CU_ERR_CUDA; }
             }
-            LAUNCH(k_lz_gather, (unsigned)((ob + 255) / 256), 256, cs, d_out, d_ptr, ob);
-            dfree(d_ptr, cs); dfree(d_changed, cs);
+            dfree(d_ptr, cs); dfree(d_changed, cs); dfree(d_done, cs);
         }
         cudaEventRecord(ev[3], cs);
         // compact the BlockRec array to stream order without gaps: rebase through a gather of summaries

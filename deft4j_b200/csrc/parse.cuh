@@ -721,8 +721,7 @@ k_emit(const uint8_t* __restrict__ d_in, const StreamDesc* __restrict__ descs, c
 // LZ77 resolution (replaces DeflateBlock.readSlice, DeflateBlock.java:147-222)
 //   k_lz_fill : per symbol, literal -> out byte + root pointer; match -> every byte points at
 //               (position - distance), folded into the non-overlapping source for overlapped copies.
-//   k_lz_jump : pointer doubling until every pointer is a root.
-//   k_lz_gather: out[i] = out[root(i)].
+//   k_lz_jump : pointer doubling; a byte that reaches a root copies its value and becomes a root itself.
 // A match reaching before the start of its stream is a parse failure (the reference dereferences a
 // null prevBlock there).
 // --------------------------------------------------------------------------------------------------
@@ -772,33 +771,86 @@ __global__ void k_compact_blocks(const StreamDesc* __restrict__ descs, const Blo
     if (lane == 0) { dst[w].sym_base += sd.sym_base; dst[w].out_base += sd.out_base; }  // walker relative -> pool index
 }
 
-__global__ void k_lz_jump(uint32_t* __restrict__ ptr, uint64_t n, int* __restrict__ changed) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// First pass, in output order inside a tile: a CTA walks its tile chunk by chunk, so by the time a byte is looked at,
+// whatever it copies from further back in the same tile is already resolved (`done`, value in `out`) and costs one hop;
+// only sources in the same chunk or in another CTA's tile are followed link by link (at most 8, as in k_lz_jump).
+// A `done` flag of ANOTHER tile is never trusted here (its value may not be visible yet); the pointer chain is.
+constexpr int LZJ_NT = 512, LZJ_TILE = 32768;
+__global__ void __launch_bounds__(LZJ_NT)
+k_lz_jump_tiles(uint32_t* ptr, uint8_t* out, uint8_t* done, uint64_t n, uint32_t tile, int* __restrict__ changed) {
+    const uint64_t t0 = (uint64_t)blockIdx.x * tile;
+    const uint64_t t1 = t0 + tile < n ? t0 + tile : n;
     bool ch = false;
-    if (i < n) {
-        // follow up to 8 links per pass (any value read on the way is an ancestor, so concurrent updates by
-        // other threads only shorten the walk); the chain depth shrinks by at least 8x per pass
-        uint32_t p = ptr[i];
-        if (p != i) {
-            const uint32_t p0 = p;
+    uint32_t nextp = t0 + threadIdx.x < t1 ? ptr[t0 + threadIdx.x] : 0u;
 #pragma unroll 1
-            for (int h = 0; h < 8; h++) {
-                const uint32_t q = ptr[p];
-                if (q == p) break;
-                p = q;
+    for (uint64_t c = t0; c < t1; c += LZJ_NT) {
+        const uint64_t i = c + threadIdx.x;
+        // the byte's own pointer does not depend on the chunks before it: the next chunk's load is in flight while this
+        // one follows its links
+        const uint32_t mine = nextp;
+        if (i + LZJ_NT < t1) nextp = ptr[i + LZJ_NT];
+        if (i < t1) {
+            uint32_t p = mine;
+            bool root = p == (uint32_t)i;
+            if (!root) {
+                const uint32_t p0 = p;
+                uint32_t to = p;
+#pragma unroll 1
+                for (int h = 0; h < 8; h++) {
+                    // (loading ptr / out / done of p together, one round trip per hop, was measured slower: the pass is
+                    //  bound by the number of scattered accesses, not by their latency)
+                    if (p >= t0 && p < c && done[p]) { root = true; to = ptr[p]; break; }   // resolved earlier by this CTA
+                    const uint32_t q = ptr[p];
+                    if (q == p) { root = true; to = p; break; }
+                    p = q;
+                    to = p;
+                }
+                if (root) out[i] = out[p];
+                if (to != p0) ptr[i] = to;
+                ch |= !root;
             }
-            if (p != p0) ptr[i] = p;
-            ch = ptr[p] != p;   // not at a root yet
+            if (root) done[i] = 1;
         }
+        __syncthreads();
     }
     if (__syncthreads_or(ch) && threadIdx.x == 0) *changed = 1;
 }
 
-__global__ void k_lz_gather(uint8_t* __restrict__ out, const uint32_t* __restrict__ ptr, uint64_t n) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t p = ptr[i];
-    if (p != i) out[i] = out[p];
+// One pass: follow up to 8 links.  Pointers only ever move towards the root and a root's pointer and value never
+// change during the passes, so plain (cached, possibly stale) loads are safe: whatever is read on the way is an ancestor.
+// A byte that reaches a root takes the root's value, points at that root and sets its `done` flag: later passes skip it
+// after a one-byte read, and no gather pass is needed at the end.  (It does not become a root itself: a walker running
+// in the same pass could then read its value before it is written.)
+__global__ void k_lz_jump(uint32_t* ptr, uint8_t* out, uint8_t* done, uint64_t n, int* __restrict__ changed) {
+    // four bytes per thread: one 32-bit read of their flags decides whether there is anything to do
+    const uint64_t i4 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    bool ch = false;
+    if (i4 < n) {
+        const uint32_t flags = i4 + 4 <= n ? *(const uint32_t*)(done + i4) : 0u;
+        if (flags != 0x01010101u) {
+#pragma unroll 1
+            for (int b = 0; b < 4; b++) {
+                const uint64_t i = i4 + b;
+                if (i >= n || done[i]) continue;
+                uint32_t p = ptr[i];
+                bool root = p == (uint32_t)i;
+                if (!root) {
+                    const uint32_t p0 = p;
+#pragma unroll 1
+                    for (int h = 0; h < 8; h++) {
+                        const uint32_t q = ptr[p];
+                        if (q == p) { root = true; break; }
+                        p = q;
+                    }
+                    if (root) out[i] = out[p];
+                    if (p != p0) ptr[i] = p;
+                    ch |= !root;
+                }
+                if (root) done[i] = 1;
+            }
+        }
+    }
+    if (__syncthreads_or(ch) && threadIdx.x == 0) *changed = 1;
 }
 
 }  // namespace d4
