@@ -187,11 +187,13 @@ __device__ void finish_stream(EngSmem& S, Eng& e, StreamState& st, BlkState* __r
         __shared__ long long s_rpos, s_rsaved;
         __shared__ int s_stop;
         __shared__ uint32_t s_first_alive, s_n_alive;
-        if (tid == 0) {
-            s_rpos = 0; s_rsaved = 0; s_stop = 0;
+        if (tid == 0) { s_rpos = 0; s_rsaved = 0; s_stop = 0; s_first_alive = nb; s_n_alive = 0; }
+        __syncthreads();
+        {   // first live block and their number: every thread looks at its share (one thread walking all the block
+            // states paid a global-memory round trip per block)
             uint32_t fa = nb, na = 0;
-            for (uint32_t k = 0; k < nb; k++) if (B[k].alive) { if (fa == nb) fa = k; na++; }
-            s_first_alive = fa; s_n_alive = na;
+            for (uint32_t k = tid; k < nb; k += ENG_NT) if (B[k].alive) { if (fa == nb) fa = k; na++; }
+            if (na) { atomicMin(&s_first_alive, fa); atomicAdd(&s_n_alive, na); }
         }
         __syncthreads();
         const uint32_t first_alive = s_first_alive, n_alive = s_n_alive;

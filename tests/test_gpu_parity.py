@@ -639,3 +639,24 @@ def test_cli_folder_of_pngs_uses_the_native_front_end(gpu, oracle, tmp_path, cap
         saved = c.optimise(True, None)
         assert (tmp_path / ("a%d.png" % i)).read_bytes() == c.write()
         assert ("Saved %d bits with optimisation" % saved) in cap.out
+
+
+def test_zip_archive_entries_are_one_device_batch(gpu, oracle):
+    """A ZIP archive with many method-8 entries (workloads.c4_zip_archive) read through read_containers: every entry's
+    stream in ONE batch parse and ONE engine launch; the rewritten archive equals the mirror's output over the oracle."""
+    import io
+    import zipfile
+    from deft4j_b200 import _native
+    from deft4j_b200.container import getContainerForBytes, read_containers, optimise_containers
+    L = _native.lib()
+    arch = W.c4_zip_archive(24, seed=31)
+    n0 = L.deft4cu_debug_engine_launches()
+    conts = read_containers([arch], ["a.zip"], gpu.DeflateStream)
+    saved = optimise_containers(conts, True)[0]
+    assert L.deft4cu_debug_engine_launches() - n0 == 1
+    out = conts[0].write()
+    ref = getContainerForBytes(arch, "a.zip", oracle.OracleDeflateStream)
+    assert ref.read(arch) and ref.optimise(True, None) == saved
+    assert out == ref.write()
+    zo = zipfile.ZipFile(io.BytesIO(out))
+    assert zo.testzip() is None and len(zo.infolist()) == 24

@@ -161,6 +161,28 @@ def c4_streams(count, seed=4):
     return out
 
 
+def c4_zip_archive(count, seed=4):
+    """One ZIP archive whose `count` method-8 entries carry the payloads of c4_streams: local headers,
+    central directory and end record written by hand so that the entry data is exactly those raw deflate streams."""
+    import struct
+    streams = c4_streams(count, seed)
+    out = bytearray()
+    central = bytearray()
+    for k, raw in enumerate(streams):
+        data = zlib.decompress(raw, -15)
+        name = ("dir%d/entry%05d.txt" % (k % 7, k)).encode()
+        crc = zlib.crc32(data) & 0xffffffff
+        off = len(out)
+        # version needed 20, flags 0, method 8, time / date, crc, sizes, name length, extra length
+        out += struct.pack("<IHHHHHIIIHH", 0x04034b50, 20, 0, 8, 0x6000, 0x5821, crc, len(raw), len(data), len(name), 0) + name + raw
+        central += struct.pack("<IHHHHHHIIIHHHHHII", 0x02014b50, 20, 20, 0, 8, 0x6000, 0x5821, crc, len(raw), len(data),
+                               len(name), 0, 0, 0, 0, 0, off) + name
+    cd_off = len(out)
+    out += central
+    out += struct.pack("<IHHHHIIH", 0x06054b50, 0, 0, count, count, len(central), cd_off, 0)
+    return bytes(out)
+
+
 def c5_streams(scale=1):
     """Adversarial streams (scaled: `scale` MiB per long-match stream)."""
     rng = np.random.default_rng(5)
