@@ -141,12 +141,14 @@ def optimise_files_batched(paths, merge_blocks, stream_cls, out, err, max_bytes=
 
     pending = []   # (path, data) of the group being collected
 
-    def native_png_group():
-        """A group made of PNG files only goes through the native front-end (deft4cu_png_optimise_batch): same lines, same
-        files, the chunk work on host threads instead of in this interpreter."""
+    def native_group(fmt):
+        """A group made of PNG files only (or of ZIP archives only) goes through the native front-end
+        (deft4cu_png_optimise_batch / deft4cu_zip_optimise_batch): same lines, same files, the container work on host
+        threads in C++ instead of in this interpreter."""
         nonlocal ok
-        from .container.png_file import optimise_png_files
-        res = optimise_png_files([d for _, d in pending], merge_blocks)
+        from .container import optimise_png_files, optimise_zip_files
+        fn, label = (optimise_png_files, "PNG") if fmt == "png" else (optimise_zip_files, "Zip")
+        res = fn([d for _, d in pending], merge_blocks)
         for (path, _), r in zip(pending, res):
             print("Optimising file " + path, file=out)
             if r["status"] == 1:
@@ -155,7 +157,7 @@ def optimise_files_batched(paths, merge_blocks, stream_cls, out, err, max_bytes=
                 print("Error when optimising file " + path, file=err)
                 ok = False
                 continue
-            print("File type recognised as PNG", file=out)
+            print("File type recognised as " + label, file=out)
             if r["status"] == 3:
                 print("Error when optimising file " + path, file=err)
                 ok = False
@@ -178,11 +180,13 @@ def optimise_files_batched(paths, merge_blocks, stream_cls, out, err, max_bytes=
     def read_group():
         from .container.deflate_files_container import read_containers
         from .container.container_util import detectFormat
-        if native_png and pending and all(detectFormat(d) == "png" for _, d in pending):
-            if group:
-                flush()
-            native_png_group()
-            return
+        if native_png and pending:
+            kinds = {detectFormat(d) for _, d in pending}
+            if kinds == {"png"} or kinds == {"zip"}:
+                if group:
+                    flush()
+                native_group(kinds.pop())
+                return
         conts = read_containers([d for _, d in pending], [os.path.basename(p) for p, _ in pending], stream_cls)
         for (path, data), cont in zip(pending, conts):
             group.append((path, data, cont))

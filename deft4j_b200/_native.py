@@ -31,7 +31,7 @@ class BlockInfo(C.Structure):
 class FileResult(C.Structure):
     _fields_ = [("status", C.c_int32), ("n_streams", C.c_uint32), ("saved_bits", C.c_int64),
                 ("out", C.POINTER(C.c_uint8)), ("out_len", C.c_uint64), ("stream_saved", C.POINTER(C.c_int64)),
-                ("stream_name", C.POINTER(C.c_char * 24))]
+                ("stream_name", C.POINTER(C.c_char_p))]
 
 
 # every symbol include/deft4cu.h declares: (restype, argtypes)
@@ -64,6 +64,7 @@ SYMBOLS = {
     "deft4cu_free_buffer": (None, [C.POINTER(C.c_uint8)]),
     "deft4cu_size_bits_fallback": (C.c_int64, [C.c_char_p, C.c_uint64]),
     "deft4cu_png_optimise_batch": (C.c_int, [_U8PP, _U64P, C.c_uint32, C.c_uint32, C.POINTER(FileResult)]),
+    "deft4cu_zip_optimise_batch": (C.c_int, [_U8PP, _U64P, C.c_uint32, C.c_uint32, C.POINTER(FileResult)]),
     "deft4cu_free_file_results": (None, [C.POINTER(FileResult), C.c_uint32]),
     "deft4cu_crc32": (C.c_uint32, [C.c_uint32, C.c_char_p, C.c_uint64]),
     "deft4cu_device_batch_create": (C.c_int, [_U8PP, _U64P, C.c_uint32, _PP]),

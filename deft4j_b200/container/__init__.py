@@ -4,8 +4,8 @@ from .gz_file import GZFile
 from .png_file import PNGFile, optimise_png_files
 from .raw_deflate_file import RawDeflateFile
 from .zlib_file import ZLibFile
-from .zip_file import ZipFile
+from .zip_file import ZipFile, optimise_zip_files
 from .container_util import getContainerForExt, getContainerForBytes
 
-__all__ = ["DeflateFilesContainer", "optimise_streams", "optimise_containers", "read_containers", "GZFile", "PNGFile", "optimise_png_files", "RawDeflateFile", "ZLibFile", "ZipFile",
+__all__ = ["DeflateFilesContainer", "optimise_streams", "optimise_containers", "read_containers", "GZFile", "PNGFile", "optimise_png_files", "optimise_zip_files", "RawDeflateFile", "ZLibFile", "ZipFile",
            "getContainerForExt", "getContainerForBytes"]

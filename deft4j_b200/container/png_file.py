@@ -295,45 +295,13 @@ class PNGFile(DeflateFilesContainer):
 
 
 def _png_call(datas, merge_blocks, lib):
-    """The C-ABI call of optimise_png_files: (library, result array, n); the caller frees with deft4cu_free_file_results."""
-    import ctypes as C
-    from .. import _native as N
-    L = lib if lib is not None else N.lib()
-    n = len(datas)
-    ptrs, lens = N.make_ptr_arrays(datas)
-    res = (N.FileResult * max(n, 1))()
-    fn = L.deft4cu_png_optimise_batch
-    if lib is not None:
-        fn.restype = C.c_int
-        fn.argtypes = N.SYMBOLS["deft4cu_png_optimise_batch"][1]
-        L.deft4cu_free_file_results.restype = None
-        L.deft4cu_free_file_results.argtypes = N.SYMBOLS["deft4cu_free_file_results"][1]
-    rc = fn(ptrs, lens, n, N.MERGE_BLOCKS if merge_blocks else 0, res)
-    if rc != N.OK:
-        raise N.Deft4cuError("deft4cu_png_optimise_batch failed (%d): %s" % (rc, N.last_error() if lib is None else ""))
-    return L, res, n
+    from ._front import front_call
+    return front_call("deft4cu_png_optimise_batch", datas, merge_blocks, lib)
 
 
 def optimise_png_files(datas, merge_blocks=True, lib=None):
     """A LIST of PNG / APNG files through the native front-end (`deft4cu_png_optimise_batch`, csrc/png_front.cpp): the
     chunk model of this module done by host threads in C++, the zlib streams of all files as one device batch.
-
-    Returns one dict per file: status (0 = read, optimised and written; 1 = `PNGFile.read` is False; 2 = `write` raises),
-    out (the bytes `PNGFile.write()` returns), saved_bits, and streams = [(name, saved bits)] in
-    `getDeflateStreams()` order — everything `CMDUtil.optimiseFile` prints or writes for the file.
-    `lib`: another library with the same entry point (the CPU tests pass a build of the front-end over the oracle)."""
-    import ctypes as C
-    from .. import _native as N
-    L, res, n = _png_call(datas, merge_blocks, lib)
-    out = []
-    try:
-        for i in range(n):
-            r = res[i]
-            d = {"status": r.status, "saved_bits": r.saved_bits, "out": None, "streams": []}
-            if r.status == N.OK:
-                d["out"] = C.string_at(r.out, r.out_len)
-                d["streams"] = [(r.stream_name[k].value.decode("latin-1"), r.stream_saved[k]) for k in range(r.n_streams)]
-            out.append(d)
-    finally:
-        L.deft4cu_free_file_results(res, n)
-    return out
+    Returns one dict per file (see `_front.front_optimise`): status, out, saved_bits, streams."""
+    from ._front import front_optimise
+    return front_optimise("deft4cu_png_optimise_batch", datas, merge_blocks, lib)

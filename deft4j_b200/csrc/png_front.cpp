@@ -27,8 +27,10 @@
 #endif
 
 #include "../../include/deft4cu.h"
+#include "front_util.h"
 
 namespace {
+using d4front::parallel_for;
 
 // ---- CRC-32 (IEEE, reflected) of chunk type + data (PNGFile.java:140-158 uses java.util.zip.CRC32) -----------------
 uint32_t g_tab[8][256];
@@ -430,26 +432,6 @@ void write_file(const File& f, const deft4cu_result* res, uint8_t* out, uint64_t
     *out_len = pos;
 }
 
-template <typename F>
-void parallel_for(uint32_t n, F&& fn) {
-    unsigned hw = std::thread::hardware_concurrency();
-    if (const char* e = getenv("D4_HOST_THREADS")) hw = (unsigned)atoi(e);
-    const unsigned nt = std::max(1u, std::min({hw ? hw : 1u, 32u, (n + 7) / 8}));
-    if (nt <= 1) { for (uint32_t i = 0; i < n; i++) fn(i); return; }
-    std::atomic<uint32_t> next{0};
-    auto body = [&] {
-        for (;;) {
-            const uint32_t i0 = next.fetch_add(8);
-            if (i0 >= n) break;
-            for (uint32_t i = i0; i < std::min(n, i0 + 8); i++) fn(i);
-        }
-    };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; t++) th.emplace_back(body);
-    body();
-    for (auto& t : th) t.join();
-}
-
 }  // namespace
 
 extern "C" {
@@ -504,20 +486,14 @@ int deft4cu_png_optimise_batch(const uint8_t* const* files, const uint64_t* lens
             fr.status = st == DEFT4CU_ERR_PARSE ? DEFT4CU_ERR_PARSE : DEFT4CU_ERR_UNSUPPORTED;
             return;
         }
-        uint32_t ns = 0;
-        for (auto& z : f.zs) ns += z.dropped ? 0 : 1;
-        fr.n_streams = ns;
-        fr.stream_saved = (int64_t*)calloc(ns ? ns : 1, sizeof(int64_t));
-        fr.stream_name = (char(*)[24])calloc(ns ? ns : 1, 24);
-        if (!fr.stream_saved || !fr.stream_name) { oom = 1; return; }
-        uint32_t k = 0;
+        std::vector<std::string> names;
+        std::vector<int64_t> saved;
         for (auto& z : f.zs) {
             if (z.dropped) continue;
-            fr.stream_saved[k] = R[z.slot].saved_bits;
-            memcpy(fr.stream_name[k], z.name, 24);
-            fr.saved_bits += R[z.slot].saved_bits;
-            k++;
+            names.emplace_back(z.name);
+            saved.push_back(R[z.slot].saved_bits);
         }
+        if (!d4front::set_streams(fr, names, saved)) { oom = 1; return; }
         if (!sync_streams(f)) { fr.status = DEFT4CU_ERR_WRITE; return; }
         uint64_t need = 0;
         write_file(f, R.data(), nullptr, &need);
@@ -535,10 +511,7 @@ int deft4cu_png_optimise_batch(const uint8_t* const* files, const uint64_t* lens
 }
 
 void deft4cu_free_file_results(deft4cu_file_result* results, uint32_t n) {
-    for (uint32_t i = 0; i < n; i++) {
-        free(results[i].out); free(results[i].stream_saved); free(results[i].stream_name);
-        results[i].out = nullptr; results[i].stream_saved = nullptr; results[i].stream_name = nullptr;
-    }
+    for (uint32_t i = 0; i < n; i++) d4front::free_result(results[i]);
 }
 
 }  // extern "C"

@@ -131,9 +131,17 @@ typedef struct deft4cu_file_result {
     uint8_t* out;                /* PNGFile.write(); library-owned */
     uint64_t out_len;
     int64_t* stream_saved;       /* n_streams entries: bits saved per stream */
-    char   (*stream_name)[24];   /* n_streams entries: "IDAT chunk", "fdAT chunk 2", "zTXt chunk" (:441,:458,:536) */
+    char**   stream_name;        /* n_streams NUL-terminated names: "IDAT chunk", "fdAT chunk 2", "zTXt chunk"
+                                    (PNGFile.java:441,:458,:536); the entry's file name for ZIP (ZipFile.java:100-124) */
 } deft4cu_file_result;
 int  deft4cu_png_optimise_batch(const uint8_t* const* files, const uint64_t* lens, uint32_t n, uint32_t flags,
+                                deft4cu_file_result* results);
+/* The same for ZIP archives — ZipFile.read (deft4j-container/.../container/ZipFile.java:82-127: entries with method 8
+ * become streams, in local-file order), optimise, ZipFile.write (:46-79) through RecalculatingZipWriter
+ * (container/lljzip/RecalculatingZipWriter.java:23-136).  The archive reader restates the standard strategy of the
+ * un-vendored lljzip 2.3.0 (parity unpinned).  ERR_PARSE: no end record / Zip64 / no local headers / an entry that does
+ * not parse; ERR_WRITE: a central directory entry without its local header. */
+int  deft4cu_zip_optimise_batch(const uint8_t* const* files, const uint64_t* lens, uint32_t n, uint32_t flags,
                                 deft4cu_file_result* results);
 void deft4cu_free_file_results(deft4cu_file_result* results, uint32_t n);
 /* java.util.zip.CRC32 as the chunk writer uses it (PNGFile.java:140-158); crc = 0 starts a new checksum */

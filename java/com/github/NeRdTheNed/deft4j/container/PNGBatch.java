@@ -1,4 +1,5 @@
-// Panama FFM binding of deft4cu_png_optimise_batch: PNGFile.read / optimise / write (deft4j-container's PNGFile.java:574-605,
+// Panama FFM binding of deft4cu_png_optimise_batch (deft4cu_zip_optimise_batch has the same signature and result record:
+// bind it the same way for ZipFile, ZipFile.java:46-127): PNGFile.read / optimise / write (deft4j-container's PNGFile.java:574-605,
 // :262-369, :391-411 and DeflateFilesContainer.java:18-43) for a LIST of files in one native call.
 // NOT compiled or tested in this repository's image (no JDK): see INTEGRATION.md.  JDK 22+.
 package com.github.NeRdTheNed.deft4j.container;
@@ -58,12 +59,12 @@ public final class PNGBatch {
                     if (x.status == 0) {
                         long len = r.get(JAVA_LONG, 24);
                         x.out = r.get(ADDRESS, 16).reinterpret(len).toArray(JAVA_BYTE);
-                        MemorySegment saved = r.get(ADDRESS, 32).reinterpret(8L * ns), names = r.get(ADDRESS, 40).reinterpret(24L * ns);
+                        MemorySegment saved = r.get(ADDRESS, 32).reinterpret(8L * ns), names = r.get(ADDRESS, 40).reinterpret(8L * ns);
                         x.streamSaved = new long[ns];
                         x.streamName = new String[ns];
                         for (int k = 0; k < ns; k++) {
                             x.streamSaved[k] = saved.getAtIndex(JAVA_LONG, k);
-                            x.streamName[k] = names.asSlice(24L * k, 24).getString(0, StandardCharsets.ISO_8859_1);
+                            x.streamName[k] = names.getAtIndex(ADDRESS, k).reinterpret(65536).getString(0, StandardCharsets.ISO_8859_1);
                         }
                     }
                     out.add(x);

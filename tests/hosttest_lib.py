@@ -97,9 +97,10 @@ def front_oracle_lib():
     oracle): the chunk model of the shipped front-end, checked on the CPU."""
     global _front
     if _front is None:
-        srcs = [os.path.join(_SRC, "png_front.cpp"), os.path.join(_ROOT, "tests", "front_oracle_shim.cpp"),
+        srcs = [os.path.join(_SRC, "png_front.cpp"), os.path.join(_SRC, "zip_front.cpp"), os.path.join(_ROOT, "tests", "front_oracle_shim.cpp"),
                 os.path.join(_ROOT, "oracle", "deft_oracle.cpp")]
-        deps = srcs + [os.path.join(_ROOT, "include", "deft4cu.h"), os.path.join(_ROOT, "oracle", "deft_oracle.h")]
+        deps = srcs + [os.path.join(_ROOT, "include", "deft4cu.h"), os.path.join(_ROOT, "oracle", "deft_oracle.h"),
+                       os.path.join(_SRC, "front_util.h")]
         if (not os.path.exists(_FRONT_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_FRONT_SO) for s in deps):
             os.makedirs(os.path.dirname(_FRONT_SO), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", _FRONT_SO] + srcs)

@@ -660,3 +660,28 @@ def test_zip_archive_entries_are_one_device_batch(gpu, oracle):
     assert out == ref.write()
     zo = zipfile.ZipFile(io.BytesIO(out))
     assert zo.testzip() is None and len(zo.infolist()) == 24
+
+
+def test_native_zip_front_end_on_the_device(gpu, oracle, tmp_path, capsys):
+    """deft4cu_zip_optimise_batch (csrc/zip_front.cpp over the device batch entry): one engine launch for a list of
+    archives, identical to the same front-end over the oracle, and `optimise-folder` on a folder of archives."""
+    import hosttest_lib
+    from test_zip_front import archives
+    from deft4j_b200 import _native
+    from deft4j_b200.container import optimise_zip_files
+    from deft4j_b200.__main__ import main
+    L = _native.lib()
+    files = archives() + [W.c4_zip_archive(40, seed=77)]
+    n0 = L.deft4cu_debug_engine_launches()
+    res = optimise_zip_files(files, True)
+    assert L.deft4cu_debug_engine_launches() - n0 == 1
+    assert res == optimise_zip_files(files, True, lib=hosttest_lib.front_oracle_lib())
+    good = [k for k, r in enumerate(res) if r["status"] == 0]
+    for k in good[:3]:
+        (tmp_path / ("z%d.zip" % k)).write_bytes(files[k])
+    n0 = L.deft4cu_debug_engine_launches()
+    assert main(["optimise-folder", str(tmp_path)]) == 0
+    assert L.deft4cu_debug_engine_launches() - n0 == 1
+    assert capsys.readouterr().out.count("File type recognised as Zip") == 3
+    for k in good[:3]:
+        assert (tmp_path / ("z%d.zip" % k)).read_bytes() == res[k]["out"]
