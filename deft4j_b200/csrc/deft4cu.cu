@@ -838,7 +838,7 @@ int deft4cu_init(int device) {
     return DEFT4CU_OK;
 }
 const char* deft4cu_last_error(void) { return g_err.c_str(); }
-const char* deft4cu_version(void) { return "deft4cu 0.1 (sm_100a)"; }
+const char* deft4cu_version(void) { return "deft4cu 0.2 (sm_100a)"; }
 
 // ---- parity-debug trace (engine.cuh g_trace) ---------------------------------------------------------------
 int deft4cu_debug_trace_begin(uint32_t cap) {

@@ -60,7 +60,10 @@ constexpr int DCN = 16;           // per-table sign masks kept per block (round-
 constexpr int LCN = 12;           // literal-cost arrays kept per block (round-robin eviction)
 constexpr int MAXLIT = 64;        // distinct sets of literal code lengths tracked per block
 constexpr int WS_BYTES = 3072;    // per-warp workspace for trees / header work
-constexpr int HQS = 4608, HQL = 1024;   // queue of freshly replaced matches (all / long ones) for the histogram update
+#ifndef D4_HQS
+#define D4_HQS 4608
+#endif
+constexpr int HQS = D4_HQS, HQL = 1024;   // queue of freshly replaced matches (all / long ones) for the histogram update
 constexpr int SLOT_B = MAXM, SLOT_BEST = MAXM + 1;   // extra mask / histogram slots: the records of B and of the winner
 static_assert(DC_TILE == 32 * 16 && DC_TILE > 258, "a tile is one warp-wide 128-bit load and no match spans more than two tiles");
 
@@ -1434,7 +1437,11 @@ struct Eng {
     // TRIAL_GROUP tables at a time: a warp cuts each table into runs (shared memory), then 28 threads per table evaluate
     // one rewrite strategy each for both prune values; the two header-code trees of a thread run in its own 100 bytes of
     // shared memory (huff_tree_tiny; the full algorithm in local memory only when a tree is deeper than 7)
+#ifdef D4_TRIAL_GROUP
+    static constexpr int TRIAL_GROUP = D4_TRIAL_GROUP;
+#else
     static constexpr int TRIAL_GROUP = (ENG_NT / 28) < 6 ? (ENG_NT / 28) : 6;
+#endif
     static constexpr int TRIAL_RL = 964, TRIAL_WS0 = ((TRIAL_GROUP * TRIAL_RL + 127) / 128) * 128;
     static_assert(TRIAL_WS0 + TRIAL_GROUP * 28 * TINY_WS_BYTES <= ENG_NW * WS_BYTES && TRIAL_WS0 + TRIAL_GROUP * 640 <= ENG_NW * WS_BYTES,
                   "trial workspaces fit the shared union");
