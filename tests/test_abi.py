@@ -39,6 +39,13 @@ def test_no_cpu_fallback_without_device():
         optimise_batch([b"\x03\x00"])
     with pytest.raises(_native.Deft4cuError):
         Deft.optimiseDeflateStream(b"\x03\x00")
+    # the native file front-ends sit on the same device entry: no device, no result
+    import workloads as W
+    from deft4j_b200.container import optimise_png_files, optimise_zip_files
+    with pytest.raises(_native.Deft4cuError):
+        optimise_png_files(W.c3_png_files(1))
+    with pytest.raises(_native.Deft4cuError):
+        optimise_zip_files([W.c4_zip_archive(2)])
 
 
 def test_product_does_not_import_the_oracle():
@@ -46,7 +53,7 @@ def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "deft4j_b200")
     for dirpath, _, files in os.walk(pkg):
         for fn in files:
-            if fn.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".sh")):
                 with open(os.path.join(dirpath, fn)) as f:
                     text = f.read()
                 assert "oracle_lib" not in text and "libdeft_oracle" not in text and "deft_oracle.h" not in text, fn
