@@ -169,19 +169,96 @@ def run_cpu_baseline(a, merge, budget_s, streams=None, what=None):
 
 # ---- clocks -------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    In-process NVML (nvidia_ml_py) on a thread: a spawned `nvidia-smi -lms` holds up the host side of CUDA calls in every
+    process of the box for 0.1-0.5 s at start-up and again at every sample on a multi-GPU box, which starves a GPU that
+    runs short kernels (measured: C3 on 2 GPUs 507 instead of 110 ms per step).  NVML is initialised before the warm-up
+    steps; only samples taken after mark() count.  Falls back to `nvidia-smi` when the module is missing."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
+    def __init__(self, device, period=0.1):
+        import threading
+        self.samples = []          # (time, sm MHz, max MHz, reasons bitmask)
+        self.t_mark = 0.0
+        self.p = self.f = None
+        self.nv = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES renumbers CUDA devices, NVML does not: go through the PCI bus id
+            try:
+                import torch
+                bus = getattr(torch.cuda.get_device_properties(device), "pci_bus_id", None)
+            except Exception:  # noqa: BLE001
+                bus = None
+            h = None
+            if bus is not None:
+                for k in range(pynvml.nvmlDeviceGetCount()):
+                    hk = pynvml.nvmlDeviceGetHandleByIndex(k)
+                    if pynvml.nvmlDeviceGetPciInfo(hk).bus == bus:
+                        h = hk
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.nv, self.h = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        rs = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        self.samples.append((time.time(), mhz, rs))
+                    except Exception:  # noqa: BLE001
+                        pass
+                    self._stop.wait(period)
+
+            self.th = threading.Thread(target=loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:  # noqa: BLE001 - no NVML module: the command-line tool
+            self.nv = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "500"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
+    def wait_ready(self, timeout=5.0):
+        """the first sample is there: start-up is over"""
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            if self.nv is not None:
+                if self.samples:
+                    return
+            elif self.p is None or self.p.poll() is not None or os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.02)
+
+    def mark(self):
+        self.t_mark = time.time()
+
     def stop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.nv is not None:
+            nv = self.nv
+            self._stop.set()
+            self.th.join(timeout=2)
+            bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+            inside = [x for x in self.samples if x[0] >= self.t_mark - 0.05] or self.samples[-1:]
+            reasons = sorted({n for _, _, rs in inside for n, b in zip(names, bits) if rs & b})
+            sm = [x[1] for x in inside]
+            try:
+                nv.nvmlShutdown()
+            except Exception:  # noqa: BLE001
+                pass
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -189,11 +266,17 @@ class ClockSampler:
         self.f.flush()
         self.f.seek(0)
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
         for line in self.f:
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
+            try:
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if ts < self.t_mark - 0.1:
+                    continue
+            except ValueError:
+                pass
             try:
                 sm.append(float(c[1])); mx.append(float(c[2]))
             except ValueError:
@@ -203,7 +286,7 @@ class ClockSampler:
                     reasons.add(n)
         os.unlink(self.f.name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def peaks():
@@ -303,10 +386,15 @@ def measure(ctx, L, N, streams, merge, steps, warmup, sample_clocks=False, verif
         assert rc == 0, N.last_error()
 
     with torch.cuda.stream(stream):
+        sampler = ClockSampler(ctx.local) if sample_clocks and ctx.rank == 0 else None
+        if sampler:
+            sampler.wait_ready()
+        ctx.barrier()
         for _ in range(warmup):
             step()
         ctx.barrier()
-        sampler = ClockSampler(ctx.local) if sample_clocks and ctx.rank == 0 else None
+        if sampler:
+            sampler.mark()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         total_launches = 0
