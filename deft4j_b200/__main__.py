@@ -142,12 +142,13 @@ def optimise_files_batched(paths, merge_blocks, stream_cls, out, err, max_bytes=
     pending = []   # (path, data) of the group being collected
 
     def native_group(fmt):
-        """A group made of PNG files only (or of ZIP archives only) goes through the native front-end
-        (deft4cu_png_optimise_batch / deft4cu_zip_optimise_batch): same lines, same files, the container work on host
-        threads in C++ instead of in this interpreter."""
+        """A group made of files of ONE kind (PNG, ZIP, gzip or zlib by magic) goes through that kind's native front-end
+        (deft4cu_{png,zip,gz,zlib}_optimise_batch): same lines, same files, the container work in C++ instead of in this
+        interpreter."""
         nonlocal ok
-        from .container import optimise_png_files, optimise_zip_files
-        fn, label = (optimise_png_files, "PNG") if fmt == "png" else (optimise_zip_files, "Zip")
+        from .container import optimise_png_files, optimise_zip_files, optimise_gz_files, optimise_zlib_files
+        fn, label = {"png": (optimise_png_files, "PNG"), "zip": (optimise_zip_files, "Zip"),
+                     "gzip": (optimise_gz_files, "GZip"), "zlib": (optimise_zlib_files, "ZLib")}[fmt]
         res = fn([d for _, d in pending], merge_blocks)
         for (path, _), r in zip(pending, res):
             print("Optimising file " + path, file=out)
@@ -182,7 +183,7 @@ def optimise_files_batched(paths, merge_blocks, stream_cls, out, err, max_bytes=
         from .container.container_util import detectFormat
         if native_png and pending:
             kinds = {detectFormat(d) for _, d in pending}
-            if kinds == {"png"} or kinds == {"zip"}:
+            if len(kinds) == 1 and next(iter(kinds)) in ("png", "zip", "gzip", "zlib"):
                 if group:
                     flush()
                 native_group(kinds.pop())

@@ -65,6 +65,8 @@ SYMBOLS = {
     "deft4cu_size_bits_fallback": (C.c_int64, [C.c_char_p, C.c_uint64]),
     "deft4cu_png_optimise_batch": (C.c_int, [_U8PP, _U64P, C.c_uint32, C.c_uint32, C.POINTER(FileResult)]),
     "deft4cu_zip_optimise_batch": (C.c_int, [_U8PP, _U64P, C.c_uint32, C.c_uint32, C.POINTER(FileResult)]),
+    "deft4cu_gz_optimise_batch": (C.c_int, [_U8PP, _U64P, C.c_uint32, C.c_uint32, C.POINTER(FileResult)]),
+    "deft4cu_zlib_optimise_batch": (C.c_int, [_U8PP, _U64P, C.c_uint32, C.c_uint32, C.POINTER(FileResult)]),
     "deft4cu_free_file_results": (None, [C.POINTER(FileResult), C.c_uint32]),
     "deft4cu_crc32": (C.c_uint32, [C.c_uint32, C.c_char_p, C.c_uint64]),
     "deft4cu_device_batch_create": (C.c_int, [_U8PP, _U64P, C.c_uint32, _PP]),

@@ -118,3 +118,11 @@ class GZFile(DeflateFilesContainer):
 
     def fileType(self):
         return "GZip"
+
+
+def optimise_gz_files(datas, merge_blocks=True, lib=None):
+    """A LIST of gzip files through the native front-end (`deft4cu_gz_optimise_batch`, csrc/gz_front.cpp): this module's
+    header model in C++, the members' streams as one device batch, CRC-32 / ISIZE from the device.  Result records as
+    `optimise_png_files`."""
+    from ._front import front_optimise
+    return front_optimise("deft4cu_gz_optimise_batch", datas, merge_blocks, lib)

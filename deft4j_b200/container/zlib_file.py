@@ -57,3 +57,9 @@ class ZLibFile(DeflateFilesContainer):
         gz = GZFile(self.stream_cls)
         gz.setData(self.deflateStream)
         return [gz]
+
+
+def optimise_zlib_files(datas, merge_blocks=True, lib=None):
+    """A LIST of zlib files through the native front-end (`deft4cu_zlib_optimise_batch`, csrc/gz_front.cpp)."""
+    from ._front import front_optimise
+    return front_optimise("deft4cu_zlib_optimise_batch", datas, merge_blocks, lib)

@@ -143,6 +143,14 @@ int  deft4cu_png_optimise_batch(const uint8_t* const* files, const uint64_t* len
  * not parse; ERR_WRITE: a central directory entry without its local header. */
 int  deft4cu_zip_optimise_batch(const uint8_t* const* files, const uint64_t* lens, uint32_t n, uint32_t flags,
                                 deft4cu_file_result* results);
+/* The same for gzip members — GZFile.read (deft4j-container/.../container/GZFile.java:42-87), optimise, GZFile.write
+ * (:92-152: header fields written back, FCOMMENT without its NUL, CRC-32 and ISIZE recalculated from the decoded data —
+ * here: taken from the device) — and for zlib streams — ZLibFile.read (container/ZLibFile.java:59-95), ZLibFile.write
+ * (:33-57, Adler-32 recalculated).  One stream per file, named after FNAME (gzip) or "unnamed stream". */
+int  deft4cu_gz_optimise_batch(const uint8_t* const* files, const uint64_t* lens, uint32_t n, uint32_t flags,
+                               deft4cu_file_result* results);
+int  deft4cu_zlib_optimise_batch(const uint8_t* const* files, const uint64_t* lens, uint32_t n, uint32_t flags,
+                                 deft4cu_file_result* results);
 void deft4cu_free_file_results(deft4cu_file_result* results, uint32_t n);
 /* java.util.zip.CRC32 as the chunk writer uses it (PNGFile.java:140-158); crc = 0 starts a new checksum */
 uint32_t deft4cu_crc32(uint32_t crc, const uint8_t* data, uint64_t len);

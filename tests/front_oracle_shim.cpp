@@ -14,6 +14,15 @@ static uint32_t adler32(const uint8_t* p, size_t n) {
     return (b << 16) | a;
 }
 
+static uint32_t crc32_of(const uint8_t* p, size_t n) {
+    uint32_t c = ~0u;
+    for (size_t i = 0; i < n; i++) {
+        c ^= p[i];
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1)));
+    }
+    return ~c;
+}
+
 extern "C" {
 int deft4cu_optimise_batch(const uint8_t* const* in, const uint64_t* in_len, uint32_t n, uint32_t flags, deft4cu_result* results) {
     for (uint32_t i = 0; i < n; i++) {
@@ -34,6 +43,7 @@ int deft4cu_optimise_batch(const uint8_t* const* in, const uint64_t* in_len, uin
         ora_uncompressed(s, data.data());
         r.uncompressed_len = u;
         r.adler32 = adler32(data.data(), u);
+        r.crc32 = crc32_of(data.data(), u);
         ora_free(s);
     }
     return DEFT4CU_OK;

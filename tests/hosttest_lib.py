@@ -97,7 +97,7 @@ def front_oracle_lib():
     oracle): the chunk model of the shipped front-end, checked on the CPU."""
     global _front
     if _front is None:
-        srcs = [os.path.join(_SRC, "png_front.cpp"), os.path.join(_SRC, "zip_front.cpp"), os.path.join(_ROOT, "tests", "front_oracle_shim.cpp"),
+        srcs = [os.path.join(_SRC, "png_front.cpp"), os.path.join(_SRC, "zip_front.cpp"), os.path.join(_SRC, "gz_front.cpp"), os.path.join(_ROOT, "tests", "front_oracle_shim.cpp"),
                 os.path.join(_ROOT, "oracle", "deft_oracle.cpp")]
         deps = srcs + [os.path.join(_ROOT, "include", "deft4cu.h"), os.path.join(_ROOT, "oracle", "deft_oracle.h"),
                        os.path.join(_SRC, "front_util.h")]

@@ -685,3 +685,34 @@ def test_native_zip_front_end_on_the_device(gpu, oracle, tmp_path, capsys):
     assert capsys.readouterr().out.count("File type recognised as Zip") == 3
     for k in good[:3]:
         assert (tmp_path / ("z%d.zip" % k)).read_bytes() == res[k]["out"]
+
+
+def test_native_gz_and_zlib_front_ends_on_the_device(gpu, oracle, tmp_path, capsys):
+    """deft4cu_gz_optimise_batch / deft4cu_zlib_optimise_batch over the device batch entry: the reference's gzip goldens, the
+    same results as the front-ends over the oracle, one engine launch per list, and `optimise-folder` on a folder of .gz."""
+    import hosttest_lib
+    from test_gz_front import gz_files, zlib_files
+    from deft4j_b200 import _native
+    from deft4j_b200.container import optimise_gz_files, optimise_zlib_files
+    from deft4j_b200.__main__ import main
+    L = _native.lib()
+    ref = hosttest_lib.front_oracle_lib()
+    pairs = [("lz-twice-twice.txt.gz", "lz-twice-twice-opt.txt.gz"), ("asyoulik/asyoulik-gzip.txt.gz", "asyoulik/asyoulik-gzip-opt.txt.gz"),
+             ("deflate-store-2.txt.gz", "deflate-store-2-opt.txt.gz")]
+    files = [read_golden(a) for a, _ in pairs] + gz_files()
+    n0 = L.deft4cu_debug_engine_launches()
+    res = optimise_gz_files(files, True)
+    assert L.deft4cu_debug_engine_launches() - n0 == 1
+    for (a, g), r in zip(pairs, res):
+        assert r["status"] == 0 and r["out"] == read_golden(g), a
+    assert res[3:] == optimise_gz_files(files[3:], True, lib=ref)
+    zf = zlib_files()
+    assert optimise_zlib_files(zf, True) == optimise_zlib_files(zf, True, lib=ref)
+    for a, _ in pairs:
+        (tmp_path / os.path.basename(a)).write_bytes(read_golden(a))
+    n0 = L.deft4cu_debug_engine_launches()
+    assert main(["optimise-folder", str(tmp_path)]) == 0
+    assert L.deft4cu_debug_engine_launches() - n0 == 1
+    assert capsys.readouterr().out.count("File type recognised as GZip") == 3
+    for a, g in pairs:
+        assert (tmp_path / os.path.basename(a)).read_bytes() == read_golden(g)
